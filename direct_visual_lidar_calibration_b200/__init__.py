@@ -1,0 +1,30 @@
+"""B200-native NID LiDAR-camera registration engine (hot path of koide3/direct_visual_lidar_calibration).
+
+The compute lives in ``libvlcal_nid.so`` (hand-written sm_100a CUDA behind the C ABI of ``include/vlcal_nid.h``);
+this package is the thin host-side mirror of the reference's interface for that path:
+
+  create_camera                 <- camera::create_camera             (src/camera/create_camera.cpp:34-50)
+  VisualLiDARData               <- vlcal::VisualLiDARData            (include/vlcal/common/visual_lidar_data.hpp)
+  NIDCostParams, CostCalculatorNID <- vlcal::CostCalculatorNID       (include/vlcal/calib/cost_calculator_nid.hpp)
+  ViewCullingParams, ViewCulling   <- vlcal::ViewCulling             (include/vlcal/calib/view_culling.hpp)
+  NelderMead                    <- dfo::NelderMead<N>                (include/dfo/nelder_mead.hpp)
+  VisualCameraCalibrationParams, VisualCameraCalibration <- vlcal::VisualCameraCalibration
+                                                                     (include/vlcal/calib/visual_camera_calibration.hpp)
+
+There is no CPU fallback: without the built library or without a CUDA device every compute call raises.
+"""
+from ._lib import VlcalError, build_library, device_count, library_path, load_library
+from .camera import GenericCamera, create_camera
+from .cost import CostCalculatorNID, NIDCostParams, VisualLiDARData
+from .culling import ViewCulling, ViewCullingParams
+from .nelder_mead import NelderMead, NelderMeadParams
+from .calibration import RegistrationType, VisualCameraCalibration, VisualCameraCalibrationParams, estimate_camera_fov, se3_expmap
+
+__all__ = [
+    "VlcalError", "build_library", "device_count", "library_path", "load_library",
+    "GenericCamera", "create_camera",
+    "CostCalculatorNID", "NIDCostParams", "VisualLiDARData",
+    "ViewCulling", "ViewCullingParams",
+    "NelderMead", "NelderMeadParams",
+    "RegistrationType", "VisualCameraCalibration", "VisualCameraCalibrationParams", "estimate_camera_fov", "se3_expmap",
+]

@@ -1,0 +1,126 @@
+"""vlcal::CostCalculatorNID mirror (reference: include/vlcal/calib/cost_calculator_nid.hpp, src/vlcal/calib/cost_calculator_nid.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .camera import GenericCamera, _dp
+
+
+def T_to_colmajor(T) -> np.ndarray:
+    """(…,4,4) row-major numpy transform(s) -> (…,16) column-major doubles (Eigen::Isometry3d::matrix().data())."""
+    T = np.asarray(T, dtype=np.float64)
+    return np.ascontiguousarray(np.swapaxes(T.reshape(-1, 4, 4), 1, 2)).reshape(-1, 16)
+
+
+def colmajor_to_T(v) -> np.ndarray:
+    return np.swapaxes(np.asarray(v, dtype=np.float64).reshape(-1, 4, 4), 1, 2).copy()
+
+
+class VisualLiDARData:
+    """vlcal::VisualLiDARData {cv::Mat image (CV_8UC1); FrameCPU::Ptr points} (visual_lidar_data.hpp:10-23).
+
+    points: (N,4) float64 homogeneous (x,y,z,1) = Eigen::Vector4d; (N,3) input gets w=1 appended.
+    intensities: (N,) float64 (frame.hpp:66,69)."""
+
+    def __init__(self, image, points, intensities):
+        self.image = np.ascontiguousarray(image, dtype=np.uint8)
+        if self.image.ndim != 2:
+            raise ValueError("image must be a single-channel uint8 array (cv::imread(path, 0))")
+        pts = np.asarray(points, dtype=np.float64)
+        if pts.ndim != 2 or pts.shape[1] not in (3, 4):
+            raise ValueError("points must be (N,3) or (N,4)")
+        if pts.shape[1] == 3:
+            pts = np.concatenate([pts, np.ones((pts.shape[0], 1))], axis=1)
+        self.points = np.ascontiguousarray(pts)
+        self.intensities = np.ascontiguousarray(np.asarray(intensities, dtype=np.float64).reshape(-1))
+        if self.intensities.shape[0] != self.points.shape[0]:
+            raise ValueError("intensities / points size mismatch")
+
+    def size(self) -> int:
+        return int(self.points.shape[0])
+
+
+class NIDCostParams:
+    """vlcal::NIDCostParams (cost_calculator_nid.cpp:7-9)."""
+
+    def __init__(self, bins: int = 16):
+        self.bins = bins
+
+
+class CostCalculatorNID:
+    """vlcal::CostCalculatorNID(proj, data, params) with calculate(T_camera_lidar) (cost_calculator_nid.cpp:13-67),
+    plus calculate_batch(Ts) which scores many poses in one pass over the cloud."""
+
+    def __init__(self, proj: GenericCamera, data: VisualLiDARData, params: NIDCostParams | None = None, device: int = -1, max_fov: float | None = None):
+        params = params or NIDCostParams()
+        L = _lib.load_library()
+        self._L = L
+        self._ctx = C.c_void_p()
+        self.params = params
+        self.proj = proj
+        self.data = data
+        h, w = data.image.shape
+        _lib.check(
+            L.vlcal_nid_create(
+                C.byref(self._ctx), device, _lib.MODE_HISTOGRAM, proj.model_id, _dp(proj.intrinsics), proj.intrinsics.size, _dp(proj.distortion), proj.distortion.size,
+                data.image.ctypes.data, w, h, data.image.strides[0], data.points.ctypes.data, data.intensities.ctypes.data, data.size(), params.bins,
+                -1.0 if max_fov is None else float(max_fov),
+            )
+        )
+
+    # --- reference surface ---------------------------------------------------------------
+    def calculate(self, T_camera_lidar) -> float:
+        return float(self.calculate_batch(np.asarray(T_camera_lidar, dtype=np.float64).reshape(1, 4, 4))[0])
+
+    # --- batched surface ------------------------------------------------------------------
+    def calculate_batch(self, Ts, return_hist: bool = False):
+        Tc = T_to_colmajor(Ts)
+        P = Tc.shape[0]
+        out = np.empty(P)
+        bins = self.params.bins
+        hist = np.empty((P, bins * bins), dtype=np.int32) if return_hist else None
+        _lib.check(self._L.vlcal_nid_evaluate(self._ctx, _dp(Tc), P, _dp(out), hist.ctypes.data if return_hist else None))
+        if return_hist:
+            # storage index = image_bin + lidar_bin*bins -> [P, lidar_bin, image_bin] -> [P, image_bin, lidar_bin]
+            return out, np.swapaxes(hist.reshape(P, bins, bins), 1, 2).copy()
+        return out
+
+    @property
+    def max_fov(self) -> float:
+        return float(self._L.vlcal_nid_max_fov(self._ctx))
+
+    @property
+    def points_are_f32(self) -> bool:
+        return bool(self._L.vlcal_nid_points_are_f32(self._ctx))
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    def set_profiling(self, enable: bool):
+        _lib.check(self._L.vlcal_nid_set_profiling(self._ctx, int(enable)))
+
+    def set_kernel_variant(self, variant: int):
+        _lib.check(self._L.vlcal_nid_set_kernel_variant(self._ctx, int(variant)))
+
+    def reset_profile(self):
+        _lib.check(self._L.vlcal_nid_reset_profile(self._ctx))
+
+    def profile(self):
+        launches, poses, ms = C.c_int64(), C.c_int64(), C.c_double()
+        _lib.check(self._L.vlcal_nid_get_profile(self._ctx, C.byref(launches), C.byref(ms), C.byref(poses)))
+        return {"kernel_launches": launches.value, "kernel_ms_total": ms.value, "poses_total": poses.value}
+
+    def close(self):
+        if self._ctx:
+            self._L.vlcal_nid_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

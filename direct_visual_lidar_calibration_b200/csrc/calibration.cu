@@ -1,0 +1,355 @@
+// calibration.cu -- the caller of the hot path: VisualCameraCalibration, NID_NELDER_MEAD branch
+// (reference: src/vlcal/calib/visual_camera_calibration.cpp:35-139, include/vlcal/calib/visual_camera_calibration.hpp).
+//
+// Same decisions as the reference (outer loop, culling at the start pose of every inner solve, one cost object per
+// bag, dfo::NelderMead<6> with the calibration parameters), but every Nelder-Mead iteration scores its candidate
+// poses {xo, xr, xe, xc} in ONE batched kernel launch per bag, and bags run concurrently on their own streams.
+#include <cstring>
+#include <vector>
+
+#include "host_math.hpp"
+#include "nid_context.cuh"
+
+using namespace vlcal;
+
+namespace {
+
+struct PoseObjective {
+  vlcal_nid_ctx* const* ctxs;
+  int n_ctxs;
+  const double* init_T;
+  vlcal_pose_callback callback;
+  vlcal_allreduce_fn allreduce;
+  void* user;
+  double best_cost = DBL_MAX;  // visual_camera_calibration.cpp:101
+  int status = VLCAL_OK;
+  std::vector<double> Ts, partial, vals;
+
+  // f(x) for a batch: T = init_T * Expmap(x)  (:104), sum over bags of calculate(T)  (:105-110)
+  void evaluate(const double* xs, int count, double* ys) {
+    Ts.resize(static_cast<size_t>(count) * 16);
+    partial.assign(count, 0.0);
+    vals.resize(count);
+    for (int i = 0; i < count; i++) {
+      double E[16];
+      host::se3_expmap_gtsam(xs + 6 * i, E);
+      host::isometry_mul(init_T, E, &Ts[16 * static_cast<size_t>(i)]);
+    }
+    if (status == VLCAL_OK) {
+      int launched = 0;
+      for (; launched < n_ctxs; launched++) {
+        const int rc = nid_evaluate_async(ctxs[launched], Ts.data(), count, false);
+        if (rc != VLCAL_OK) {
+          status = rc;
+          break;
+        }
+      }
+      for (int b = 0; b < launched; b++) {
+        const int rc = nid_wait(ctxs[b], vals.data(), nullptr);
+        if (rc != VLCAL_OK) {
+          status = rc;
+          continue;
+        }
+        for (int i = 0; i < count; i++) partial[i] += vals[i];  // sum_costs += costs[i]->calculate(T)
+      }
+    }
+    if (allreduce) allreduce(partial.data(), count, user);
+    for (int i = 0; i < count; i++) ys[i] = status == VLCAL_OK ? partial[i] : NAN;
+  }
+
+  // the objective's side effects, in the reference's evaluation order (:112-116)
+  void observe(const double* x, double y) {
+    if (y < best_cost) {
+      best_cost = y;
+      if (callback) {
+        double E[16], T[16];
+        host::se3_expmap_gtsam(x, E);
+        host::isometry_mul(init_T, E, T);
+        callback(T, y, user);
+      }
+    }
+  }
+};
+
+int run_inner_solve(
+  vlcal_nid_ctx* const* ctxs, int n_ctxs, const vlcal_calib_params* params, const double init_T[16], vlcal_pose_callback callback, vlcal_allreduce_fn allreduce, void* user,
+  double T_out[16], vlcal_nm_result* nm_result) {
+  PoseObjective obj;
+  obj.ctxs = ctxs, obj.n_ctxs = n_ctxs, obj.init_T = init_T, obj.callback = callback, obj.allreduce = allreduce, obj.user = user;
+
+  host::NelderMeadParams nm;  // :122-125
+  nm.init_step = params->nelder_mead_init_step;
+  nm.convergence_var_thresh = params->nelder_mead_convergence_criteria;
+  nm.max_iterations = params->max_inner_iterations;
+  const double x0[6] = {0, 0, 0, 0, 0, 0};
+  auto f = [&](const double* xs, int count, double* ys) { obj.evaluate(xs, count, ys); };
+  auto ob = [&](const double* x, double y) { obj.observe(x, y); };
+  const host::NelderMeadResult r = host::nelder_mead(6, f, ob, x0, nm, /*speculate=*/true);  // :126-127
+  if (obj.status != VLCAL_OK) return obj.status;
+
+  double E[16];
+  host::se3_expmap_gtsam(r.x.data(), E);
+  host::isometry_mul(init_T, E, T_out);  // :129
+  if (nm_result) {
+    std::memset(nm_result, 0, sizeof(*nm_result));
+    nm_result->converged = r.converged ? 1 : 0;
+    nm_result->num_iterations = r.num_iterations;
+    for (int d = 0; d < 6; d++) nm_result->x[d] = r.x[d];
+    nm_result->y = r.y;
+    nm_result->num_evaluations = r.num_evaluations;
+    nm_result->num_batches = r.num_batches;
+    nm_result->num_evaluations_computed = r.num_evaluations_computed;
+  }
+  return VLCAL_OK;
+}
+
+// a bag resident in HBM for the whole calibration (uploaded once, culled per outer iteration)
+struct ResidentBag {
+  std::shared_ptr<DeviceCloud> cloud;
+  std::shared_ptr<DeviceImage> image;
+  double max_fov = 0.0;  // estimate_camera_fov(proj, this bag's image size)  (cost_calculator_nid.cpp:17)
+};
+
+int upload_bags(int device, const CameraParams& cam, const vlcal_bag* bags, int n_bags, std::vector<ResidentBag>* out) {
+  out->resize(n_bags);
+  for (int b = 0; b < n_bags; b++) {
+    const vlcal_bag& bag = bags[b];
+    if (!bag.image || bag.width <= 0 || bag.height <= 0 || bag.row_stride_bytes < bag.width || bag.n_points < 0 || (bag.n_points > 0 && (!bag.points_xyzw || !bag.intensities))) {
+      set_last_error("invalid bag " + std::to_string(b));
+      return VLCAL_ERR_INVALID_ARGUMENT;
+    }
+    int rc = upload_cloud(device, bag.points_xyzw, bag.intensities, bag.n_points, nullptr, &(*out)[b].cloud);
+    if (rc != VLCAL_OK) return rc;
+    rc = upload_image(device, bag.image, bag.width, bag.height, bag.row_stride_bytes, nullptr, &(*out)[b].image);
+    if (rc != VLCAL_OK) return rc;
+    // identical for bags that share an image size; cheap (three 2-D Nelder-Mead solves on the host)
+    (*out)[b].max_fov = (b > 0 && bag.width == bags[0].width && bag.height == bags[0].height) ? (*out)[0].max_fov : estimate_camera_fov_host(cam, bag.width, bag.height);
+  }
+  return VLCAL_OK;
+}
+
+struct CtxList {
+  std::vector<vlcal_nid_ctx*> v;
+  ~CtxList() {
+    for (auto* c : v) delete c;
+  }
+};
+
+// estimate_pose_nelder_mead (:70-139) on resident bags
+int inner_solve_resident(
+  int device, const CameraParams& cam, const std::vector<ResidentBag>& bags, const vlcal_calib_params* params, const double init_T[16], vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce, void* user, int profiling, double T_out[16], vlcal_nm_result* nm_result, vlcal_calib_stats* stats, int outer_index) {
+  // :71-73 one ViewCulling object, built on dataset.front()'s image size
+  const double cull_fov = bags.empty() ? 0.0 : bags[0].max_fov;
+  CtxList ctxs;
+  for (size_t b = 0; b < bags.size(); b++) {
+    std::shared_ptr<DeviceCloud> culled;
+    int64_t kept = 0;
+    int rc = view_cull_device(cam, bags[0].image->width, bags[0].image->height, cull_fov, !params->disable_z_buffer_culling, *bags[b].cloud, init_T, nullptr, &culled, nullptr, &kept);  // :78
+    if (rc != VLCAL_OK) return rc;
+    if (stats && b == 0 && outer_index < 16) stats->culled_points[outer_index] = kept;
+    vlcal_nid_ctx* ctx = nullptr;
+    rc = nid_ctx_create(device, VLCAL_NID_MODE_HISTOGRAM, cam, bags[b].image, culled, params->nid_bins, bags[b].max_fov, &ctx);  // :82-84
+    if (rc != VLCAL_OK) return rc;
+    ctx->profiling = profiling != 0;
+    ctxs.v.push_back(ctx);
+  }
+  vlcal_nm_result local;
+  const int rc = run_inner_solve(ctxs.v.data(), static_cast<int>(ctxs.v.size()), params, init_T, callback, allreduce, user, T_out, &local);
+  if (rc != VLCAL_OK) return rc;
+  if (nm_result) *nm_result = local;
+  if (stats) {
+    stats->total_evaluations += local.num_evaluations;
+    stats->total_evaluations_computed += local.num_evaluations_computed;
+    stats->total_batches += local.num_batches;
+    if (outer_index < 16) {
+      stats->inner_iterations[outer_index] = local.num_iterations;
+      stats->inner_final_cost[outer_index] = local.y;
+    }
+    for (auto* c : ctxs.v) {
+      int64_t launches = 0, poses = 0;
+      double ms = 0.0;
+      if (vlcal_nid_get_profile(c, &launches, &ms, &poses) == VLCAL_OK) {
+        stats->kernel_launches += launches;
+        stats->kernel_ms_total += ms;
+      }
+    }
+  }
+  return VLCAL_OK;
+}
+
+int check_common(const vlcal_calib_params* params, const double* init_T, double* T_out, int n_bags) {
+  if (!params || !init_T || !T_out || n_bags <= 0) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  if (vlcal_nid_device_count() == 0) {
+    set_last_error("no CUDA device available: this library has no CPU fallback");
+    return VLCAL_ERR_NO_DEVICE;
+  }
+  return VLCAL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void vlcal_nm_default_params(vlcal_nm_params* p) {  // nelder_mead.hpp:12
+  const host::NelderMeadParams d;
+  p->init_step = d.init_step;
+  p->alpha = d.alpha;
+  p->gamma = d.gamma;
+  p->rho = d.rho;
+  p->sigma = d.sigma;
+  p->max_iterations = d.max_iterations;
+  p->convergence_var_thresh = d.convergence_var_thresh;
+}
+
+int vlcal_nelder_mead_batched(int n, vlcal_nm_batch_fn f, vlcal_nm_observe_fn observe, void* user, const double* x0, const vlcal_nm_params* params, vlcal_nm_result* result) {
+  if (n < 1 || n > host::NM_MAX_N || !f || !x0 || !params || !result) {
+    set_last_error("invalid arguments (1 <= n <= 8)");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  host::NelderMeadParams p;
+  p.init_step = params->init_step;
+  p.alpha = params->alpha;
+  p.gamma = params->gamma;
+  p.rho = params->rho;
+  p.sigma = params->sigma;
+  p.max_iterations = params->max_iterations;
+  p.convergence_var_thresh = params->convergence_var_thresh;
+  auto bf = [&](const double* xs, int count, double* ys) { f(xs, count, n, ys, user); };
+  auto ob = [&](const double* x, double y) {
+    if (observe) observe(x, n, y, user);
+  };
+  const host::NelderMeadResult r = host::nelder_mead(n, bf, ob, x0, p, /*speculate=*/true);
+  std::memset(result, 0, sizeof(*result));
+  result->converged = r.converged ? 1 : 0;
+  result->num_iterations = r.num_iterations;
+  for (int d = 0; d < n; d++) result->x[d] = r.x[d];
+  result->y = r.y;
+  result->num_evaluations = r.num_evaluations;
+  result->num_batches = r.num_batches;
+  result->num_evaluations_computed = r.num_evaluations_computed;
+  return VLCAL_OK;
+}
+
+void vlcal_calib_default_params(vlcal_calib_params* p) {  // visual_camera_calibration.hpp:12-26
+  p->max_outer_iterations = 10;
+  p->max_inner_iterations = 256;
+  p->delta_trans_thresh = 0.1;
+  p->delta_rot_thresh = 0.5 * M_PI / 180.0;
+  p->disable_z_buffer_culling = 0;
+  p->nid_bins = 16;
+  p->nelder_mead_init_step = 1e-3;
+  p->nelder_mead_convergence_criteria = 1e-8;
+}
+
+int vlcal_estimate_pose_nelder_mead_ctx(
+  vlcal_nid_ctx* const* ctxs,
+  int n_ctxs,
+  const vlcal_calib_params* params,
+  const double init_T_camera_lidar[16],
+  vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce,
+  void* user,
+  double T_out[16],
+  vlcal_nm_result* nm_result) {
+  if (!ctxs || n_ctxs < 0 || !params || !init_T_camera_lidar || !T_out) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  for (int i = 0; i < n_ctxs; i++) {
+    if (!ctxs[i]) {
+      set_last_error("NULL context");
+      return VLCAL_ERR_INVALID_ARGUMENT;
+    }
+  }
+  return run_inner_solve(ctxs, n_ctxs, params, init_T_camera_lidar, callback, allreduce, user, T_out, nm_result);
+}
+
+int vlcal_estimate_pose_nelder_mead(
+  int device,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  const vlcal_bag* bags,
+  int n_bags,
+  const vlcal_calib_params* params,
+  const double init_T_camera_lidar[16],
+  vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce,
+  void* user,
+  int profiling,
+  double T_out[16],
+  vlcal_nm_result* nm_result,
+  vlcal_calib_stats* stats) {
+  int rc = check_common(params, init_T_camera_lidar, T_out, n_bags);
+  if (rc != VLCAL_OK) return rc;
+  CameraParams cam;
+  rc = make_camera(camera_model, intrinsics, n_intrinsics, distortion, n_distortion, &cam);
+  if (rc != VLCAL_OK) return rc;
+  if (device < 0) VL_CUDA(cudaGetDevice(&device));
+  VL_CUDA(cudaSetDevice(device));
+  std::vector<ResidentBag> resident;
+  rc = upload_bags(device, cam, bags, n_bags, &resident);
+  if (rc != VLCAL_OK) return rc;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  rc = inner_solve_resident(device, cam, resident, params, init_T_camera_lidar, callback, allreduce, user, profiling, T_out, nm_result, stats, 0);
+  if (rc == VLCAL_OK && stats) stats->outer_iterations = 1;
+  return rc;
+}
+
+int vlcal_calibrate_nelder_mead(
+  int device,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  const vlcal_bag* bags,
+  int n_bags,
+  const vlcal_calib_params* params,
+  const double init_T_camera_lidar[16],
+  vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce,
+  void* user,
+  int profiling,
+  double T_out[16],
+  vlcal_calib_stats* stats) {
+  int rc = check_common(params, init_T_camera_lidar, T_out, n_bags);
+  if (rc != VLCAL_OK) return rc;
+  CameraParams cam;
+  rc = make_camera(camera_model, intrinsics, n_intrinsics, distortion, n_distortion, &cam);
+  if (rc != VLCAL_OK) return rc;
+  if (device < 0) VL_CUDA(cudaGetDevice(&device));
+  VL_CUDA(cudaSetDevice(device));
+  std::vector<ResidentBag> resident;
+  rc = upload_bags(device, cam, bags, n_bags, &resident);
+  if (rc != VLCAL_OK) return rc;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+
+  double T[16];
+  std::memcpy(T, init_T_camera_lidar, sizeof(T));
+  for (int i = 0; i < params->max_outer_iterations; i++) {  // visual_camera_calibration.cpp:39
+    double new_T[16];
+    rc = inner_solve_resident(device, cam, resident, params, T, callback, allreduce, user, profiling, new_T, nullptr, stats, i);  // :46
+    if (rc != VLCAL_OK) return rc;
+    double inv[16], delta[16];
+    host::isometry_inverse(new_T, inv);
+    host::isometry_mul(inv, T, delta);  // :50
+    std::memcpy(T, new_T, sizeof(T));   // :51
+    const double tx = host::m4(delta, 0, 3), ty = host::m4(delta, 1, 3), tz = host::m4(delta, 2, 3);
+    const double delta_t = std::sqrt((tx * tx + ty * ty) + tz * tz);  // :53
+    const double delta_r = host::rotation_angle(delta);               // :54
+    const bool converged = delta_t < params->delta_trans_thresh && delta_r < params->delta_rot_thresh;  // :55
+    if (stats) stats->outer_iterations = i + 1;
+    if (converged) break;  // :62-64
+  }
+  std::memcpy(T_out, T, sizeof(T));
+  return VLCAL_OK;
+}
+
+}  // extern "C"

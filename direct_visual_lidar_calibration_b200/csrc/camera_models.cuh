@@ -1,0 +1,184 @@
+// camera_models.cuh -- the six projection functors of camera::GenericCamera<Projection>
+// (reference: include/camera/{pinhole,fisheye,atan,omnidir,equirectangular,rational_polynomial}.hpp,
+// dispatched by string at src/camera/create_camera.cpp:34-50), re-implemented as __host__ __device__
+// functors selected per launch by a template parameter.
+//
+// Two flavours per model:
+//   project_exact<MODEL>  -- double, operation-for-operation in the reference's order (exact_math.cuh),
+//                            the arbiter for every point;
+//   project_fast<MODEL>   -- float, FMA-friendly, used only as a filter whose verdict is accepted when the
+//                            projection is provably far from every decision edge (nid_kernels.cuh).
+#pragma once
+
+#include "exact_math.cuh"
+
+namespace vlcal {
+
+enum CameraModel : int {
+  CAM_PLUMB_BOB = 0,            // PinholeProjection            pinhole.hpp:11-52
+  CAM_FISHEYE = 1,              // FisheyeProjection            fisheye.hpp:12-37
+  CAM_ATAN = 2,                 // ATANProjection               atan.hpp:12-40
+  CAM_OMNIDIR = 3,              // OmnidirectionalProjection    omnidir.hpp:12-42
+  CAM_EQUIRECTANGULAR = 4,      // EquirectangularProjection    equirectangular.hpp:12-29
+  CAM_RATIONAL_POLYNOMIAL = 5,  // RationalPolynomialProjection rational_polynomial.hpp:9-59
+  CAM_NUM_MODELS = 6
+};
+
+struct CameraParams {
+  int model;
+  int n_intr;
+  int n_dist;
+  int pad_;
+  double intr[5];  // zero-padded
+  double dist[8];  // zero-padded (create_camera.cpp:24-27)
+};
+
+// CameraModelTraits<>::num_intrinsic_params / num_distortion_params
+VL_HD bool camera_num_params(int model, int* n_intr, int* n_dist) {
+  switch (model) {
+    case CAM_PLUMB_BOB: *n_intr = 4, *n_dist = 5; return true;            // pinhole.hpp:57-58
+    case CAM_FISHEYE: *n_intr = 4, *n_dist = 4; return true;              // fisheye.hpp:42-43
+    case CAM_ATAN: *n_intr = 4, *n_dist = 1; return true;                 // atan.hpp:45-46
+    case CAM_OMNIDIR: *n_intr = 5, *n_dist = 4; return true;              // omnidir.hpp:47-48
+    case CAM_EQUIRECTANGULAR: *n_intr = 2, *n_dist = 0; return true;      // equirectangular.hpp:34-35
+    case CAM_RATIONAL_POLYNOMIAL: *n_intr = 4, *n_dist = 8; return true;  // rational_polynomial.hpp:64-65
+    default: return false;
+  }
+}
+
+// Eigen squaredNorm of a 3-vector ((x*x + y*y) + z*z) and normalized() (v / sqrt(|v|^2) when |v|^2 > 0)
+VL_HD xd sqnorm3(xd x, xd y, xd z) {
+  return (x * x + y * y) + z * z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact (double) projections
+// ---------------------------------------------------------------------------------------------
+
+template <int MODEL>
+VL_HD void project_exact(const CameraParams& c, xd px, xd py, xd pz, xd& u, xd& v) {
+  const double* in = c.intr;
+  const double* d = c.dist;
+  if constexpr (MODEL == CAM_PLUMB_BOB) {
+    // pinhole.hpp:41 pt_2d = head<2>() / z ; :13-38 distort ; :49-51
+    const xd x = px / pz;
+    const xd y = py / pz;
+    const xd k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
+    const xd x2 = x * x;
+    const xd y2 = y * y;
+    const xd r2 = x2 + y2;
+    const xd r4 = r2 * r2;
+    const xd r6 = r2 * r4;
+    const xd r_coeff = xd(1.0) + k1 * r2 + k2 * r4 + k3 * r6;
+    const xd t_coeff1 = xd(2.0) * x * y;
+    const xd t_coeff2 = r2 + xd(2.0) * x2;
+    const xd t_coeff3 = r2 + xd(2.0) * y2;
+    const xd xdst = r_coeff * x + p1 * t_coeff1 + p2 * t_coeff2;
+    const xd ydst = r_coeff * y + p1 * t_coeff3 + p2 * t_coeff1;
+    u = xd(in[0]) * xdst + xd(in[2]);
+    v = xd(in[1]) * ydst + xd(in[3]);
+  } else if constexpr (MODEL == CAM_FISHEYE) {
+    // fisheye.hpp:15-35 ; note abs(z) at :16, r == 0 -> NaN (kept)
+    const xd r = xsqrt(px * px + py * py);
+    const xd theta = xatan2(r, xabs(pz));
+    const xd theta2 = xpow(theta, 2);
+    const xd theta4 = xpow(theta, 4);
+    const xd theta6 = xpow(theta, 6);
+    const xd theta8 = xpow(theta, 8);
+    const xd k1 = d[0], k2 = d[1], k3 = d[2], k4 = d[3];
+    const xd theta_d = theta * (xd(1.0) + k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8);
+    const xd s = theta_d / r;
+    u = xd(in[0]) * (s * px) + xd(in[2]);
+    v = xd(in[1]) * (s * py) + xd(in[3]);
+  } else if constexpr (MODEL == CAM_ATAN) {
+    // atan.hpp:30-38 ; distort :14-27
+    const xd x = px / pz;
+    const xd y = py / pz;
+    xd xdst = x, ydst = y;
+    const xd d0 = d[0];
+    const xd r = xsqrt(x * x + y * y);
+    if (!(r < xd(1e-3) || d0 < xd(1e-7))) {
+      const xd d1 = xd(1.0) / d0;
+      const xd d2 = xd(2.0) * xtan(d0 / xd(2.0));
+      const xd factor = d1 * xatan(r * d2) / r;
+      xdst = factor * x;
+      ydst = factor * y;
+    }
+    u = xd(in[0]) * xdst + xd(in[2]);
+    v = xd(in[1]) * ydst + xd(in[3]);
+  } else if constexpr (MODEL == CAM_OMNIDIR) {
+    // omnidir.hpp:14-40
+    const xd fx = in[0], fy = in[1], cx = in[2], cy = in[3], xi = in[4];
+    const xd k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3];
+    xd sx = px, sy = py, sz = pz;
+    const xd n2 = sqnorm3(px, py, pz);
+    if (n2 > xd(0.0)) {
+      const xd n = xsqrt(n2);
+      sx = px / n, sy = py / n, sz = pz / n;
+    }
+    const xd ux = sx / (sz + xi);
+    const xd uy = sy / (sz + xi);
+    const xd r2 = ux * ux + uy * uy;
+    const xd r4 = r2 * r2;
+    const xd dr = (xd(1.0) + k1 * r2 + k2 * r4);
+    const xd x2 = ux * ux;
+    const xd y2 = uy * uy;
+    const xd xy = ux * uy;
+    const xd nx = ux * dr + xd(2.0) * p1 * xy + p2 * (r2 + xd(2.0) * x2);
+    const xd ny = uy * dr + p1 * (r2 + xd(2.0) * y2) + xd(2.0) * p2 * xy;
+    u = fx * nx + cx;
+    v = fy * ny + cy;
+  } else if constexpr (MODEL == CAM_EQUIRECTANGULAR) {
+    // equirectangular.hpp:14-28
+    const xd n2 = sqnorm3(px, py, pz);
+    if (n2 < xd(1e-3)) {
+      u = xd(in[0]) / xd(2.0);
+      v = xd(in[1]) / xd(2.0);
+      return;
+    }
+    const xd n = xsqrt(n2);  // n2 >= 1e-3 > 0 -> normalized() divides
+    const xd bx = px / n, by = py / n, bz = pz / n;
+    const xd lat = -xasin(by);
+    const xd lon = xatan2(bx, bz);
+    u = xd(in[0]) * (xd(0.5) + lon / xd(2.0 * M_PI));
+    v = xd(in[1]) * (xd(0.5) - lat / xd(M_PI));
+  } else {  // CAM_RATIONAL_POLYNOMIAL
+    // rational_polynomial.hpp:47-58 ; distort :11-44
+    const xd x = px / pz;
+    const xd y = py / pz;
+    const xd k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4], k4 = d[5], k5 = d[6], k6 = d[7];
+    const xd x2 = x * x;
+    const xd y2 = y * y;
+    const xd r2 = x2 + y2;
+    const xd r4 = r2 * r2;
+    const xd r6 = r2 * r4;
+    const xd numerator = xd(1.0) + k1 * r2 + k2 * r4 + k3 * r6;
+    const xd denominator = xd(1.0) + k4 * r2 + k5 * r4 + k6 * r6;
+    const xd r_coeff = denominator > xd(1e-8) ? numerator / denominator : numerator;  // :33
+    const xd t_coeff1 = xd(2.0) * x * y;
+    const xd t_coeff2 = r2 + xd(2.0) * x2;
+    const xd t_coeff3 = r2 + xd(2.0) * y2;
+    const xd xdst = r_coeff * x + p1 * t_coeff1 + p2 * t_coeff2;
+    const xd ydst = r_coeff * y + p1 * t_coeff3 + p2 * t_coeff1;
+    u = xd(in[0]) * xdst + xd(in[2]);
+    v = xd(in[1]) * ydst + xd(in[3]);
+  }
+}
+
+// runtime dispatch (host-side helpers: estimate_camera_fov, vlcal_camera_project)
+VL_HD void project_exact_dyn(const CameraParams& c, double px, double py, double pz, double* u, double* v) {
+  xd uu(NAN), vv(NAN);
+  switch (c.model) {
+    case CAM_PLUMB_BOB: project_exact<CAM_PLUMB_BOB>(c, px, py, pz, uu, vv); break;
+    case CAM_FISHEYE: project_exact<CAM_FISHEYE>(c, px, py, pz, uu, vv); break;
+    case CAM_ATAN: project_exact<CAM_ATAN>(c, px, py, pz, uu, vv); break;
+    case CAM_OMNIDIR: project_exact<CAM_OMNIDIR>(c, px, py, pz, uu, vv); break;
+    case CAM_EQUIRECTANGULAR: project_exact<CAM_EQUIRECTANGULAR>(c, px, py, pz, uu, vv); break;
+    case CAM_RATIONAL_POLYNOMIAL: project_exact<CAM_RATIONAL_POLYNOMIAL>(c, px, py, pz, uu, vv); break;
+    default: break;
+  }
+  *u = uu.v;
+  *v = vv.v;
+}
+
+}  // namespace vlcal

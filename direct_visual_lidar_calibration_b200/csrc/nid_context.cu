@@ -1,0 +1,685 @@
+// nid_context.cu -- cost-object lifecycle and batched evaluation behind the C ABI (include/vlcal_nid.h).
+//
+// Plays the role of vlcal::CostCalculatorNID (reference: include/vlcal/calib/cost_calculator_nid.hpp:16-29,
+// src/vlcal/calib/cost_calculator_nid.cpp:13-67): the constructor copies one bag (image + cloud) into HBM once,
+// calculate() becomes a batched kernel launch on the context's own stream.
+#include "nid_context.cuh"
+
+#include <omp.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "host_math.hpp"
+#include "nid_kernels.cuh"
+
+namespace vlcal {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) {
+  g_last_error = msg;
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[1024];
+  std::snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
+  set_last_error(buf);
+  cudaGetLastError();  // clear the sticky per-thread error
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) {
+    return VLCAL_ERR_NO_DEVICE;
+  }
+  return VLCAL_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera factory rules + estimate_camera_fov
+// ---------------------------------------------------------------------------------------------
+
+int make_camera(int model, const double* intr, int n_intr, const double* dist, int n_dist, CameraParams* out) {
+  int ni = 0, nd = 0;
+  if (!camera_num_params(model, &ni, &nd)) {
+    set_last_error("unknown camera model id " + std::to_string(model));  // create_camera.cpp:49-50
+    return VLCAL_ERR_UNKNOWN_CAMERA_MODEL;
+  }
+  if (n_intr != ni || (ni > 0 && intr == nullptr)) {
+    set_last_error("num of intrinsic parameters mismatch: model expects " + std::to_string(ni) + ", got " + std::to_string(n_intr));  // :19-22
+    return VLCAL_ERR_INTRINSIC_COUNT;
+  }
+  std::memset(out, 0, sizeof(*out));
+  out->model = model;
+  out->n_intr = ni;
+  out->n_dist = nd;
+  for (int i = 0; i < ni; i++) out->intr[i] = intr[i];
+  for (int i = 0; i < nd && i < n_dist && dist != nullptr; i++) out->dist[i] = dist[i];  // :24-27 zero-pad / truncate
+  return VLCAL_OK;
+}
+
+// to_dir(x) = AngleAxisd(x0, UnitX) * AngleAxisd(x1, UnitY) * UnitZ  (estimate_fov.cpp:18-20), evaluated the way
+// Eigen does: quaternion product, then Quaternion::_transformVector
+static void fov_to_dir(const double x[2], double dir[3]) {
+  const double ha = 0.5 * x[0], hb = 0.5 * x[1];
+  const double aw = std::cos(ha), ax = std::sin(ha);
+  const double bw = std::cos(hb), by = std::sin(hb);
+  const double qw = aw * bw - ax * 0.0 - 0.0 * by - 0.0 * 0.0;
+  const double qx = aw * 0.0 + ax * bw + 0.0 * 0.0 - 0.0 * by;
+  const double qy = aw * by + 0.0 * bw + 0.0 * 0.0 - ax * 0.0;
+  const double qz = aw * 0.0 + 0.0 * bw + ax * by - 0.0 * 0.0;
+  const double v[3] = {0.0, 0.0, 1.0};
+  double uv[3] = {qy * v[2] - qz * v[1], qz * v[0] - qx * v[2], qx * v[1] - qy * v[0]};
+  uv[0] += uv[0], uv[1] += uv[1], uv[2] += uv[2];
+  const double c[3] = {qy * uv[2] - qz * uv[1], qz * uv[0] - qx * uv[2], qx * uv[1] - qy * uv[0]};
+  for (int i = 0; i < 3; i++) dir[i] = v[i] + qw * uv[i] + c[i];
+}
+
+double estimate_camera_fov_host(const CameraParams& cam, int width, int height) {
+  // estimate_fov.cpp:37 (integer divisions), :39-48
+  const double corners[3][2] = {{0.0, 0.0}, {static_cast<double>(width / 2), 0.0}, {0.0, static_cast<double>(height / 2)}};
+  double max_fov = 0.0;
+  for (int k = 0; k < 3; k++) {
+    const double* target = corners[k];
+    auto f = [&](const double* xs, int count, double* ys) {  // :22-26
+      for (int i = 0; i < count; i++) {
+        double dir[3], u, v;
+        fov_to_dir(xs + 2 * i, dir);
+        project_exact_dyn(cam, dir[0], dir[1], dir[2], &u, &v);
+        const double ex = target[0] - u, ey = target[1] - v;
+        const double err = ex * ex + ey * ey;
+        ys[i] = std::isfinite(err) ? err : DBL_MAX;
+      }
+    };
+    auto observe = [](const double*, double) {};
+    const double x0[2] = {0.0, 0.0};
+    host::NelderMeadParams p;  // :29 defaults
+    const host::NelderMeadResult r = host::nelder_mead(2, f, observe, x0, p, /*speculate=*/false);
+    double dir[3];
+    fov_to_dir(r.x.data(), dir);  // :33
+    const double n2 = (dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2];
+    const double nz = n2 > 0.0 ? dir[2] / std::sqrt(n2) : dir[2];
+    const double fov = std::acos(nz);  // :43
+    if (fov > max_fov) max_fov = fov;
+  }
+  return max_fov;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device containers
+// ---------------------------------------------------------------------------------------------
+
+DeviceCloud::~DeviceCloud() {
+  if (d_points) {
+    cudaSetDevice(device);
+    cudaFree(d_points);
+  }
+}
+
+DeviceImage::~DeviceImage() {
+  if (d_raw) {
+    cudaSetDevice(device);
+    cudaFree(d_raw);
+  }
+}
+
+// process-wide pinned staging buffer (cudaHostAlloc costs milliseconds; contexts are rebuilt every outer iteration)
+struct PinnedStage {
+  std::mutex mu;
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return VLCAL_OK;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr, cap = 0;
+    const size_t want = std::max(bytes + bytes / 4, static_cast<size_t>(1) << 20);
+    VL_CUDA(cudaHostAlloc(&ptr, want, cudaHostAllocDefault));
+    cap = want;
+    return VLCAL_OK;
+  }
+};
+static PinnedStage g_stage;
+
+int upload_cloud(int device, const double* points_xyzw, const double* intensities, int64_t n, cudaStream_t stream, std::shared_ptr<DeviceCloud>* out) {
+  auto cloud = std::make_shared<DeviceCloud>();
+  cloud->device = device;
+  cloud->n = n;
+  cloud->f32 = true;
+  if (n == 0) {
+    *out = cloud;
+    return VLCAL_OK;
+  }
+  std::lock_guard<std::mutex> lock(g_stage.mu);
+  {
+    const int rc = g_stage.reserve(static_cast<size_t>(n) * 32);
+    if (rc != VLCAL_OK) return rc;
+  }
+  // float4 (x,y,z,intensity) is lossless when the doubles came from a float32 PLY and intensity = k/256
+  float4* stage = static_cast<float4*>(g_stage.ptr);
+  int lossless = 1, w_is_one = 1;
+#pragma omp parallel for schedule(static) reduction(&& : lossless, w_is_one)
+  for (int64_t i = 0; i < n; i++) {
+    const double* p = points_xyzw + 4 * i;
+    const float4 q = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(p[2]), static_cast<float>(intensities[i]));
+    stage[i] = q;
+    lossless = lossless && (static_cast<double>(q.x) == p[0] || p[0] != p[0]) && (static_cast<double>(q.y) == p[1] || p[1] != p[1]) &&
+               (static_cast<double>(q.z) == p[2] || p[2] != p[2]) && (static_cast<double>(q.w) == intensities[i] || intensities[i] != intensities[i]);
+    w_is_one = w_is_one && (p[3] == 1.0);
+  }
+  if (!w_is_one) {
+    set_last_error("points_xyzw: homogeneous coordinate w must be 1 for every point (Frame::points, frame.hpp:66)");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  cloud->f32 = lossless != 0;
+  if (!cloud->f32) {
+    double4* stage64 = static_cast<double4*>(g_stage.ptr);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+      const double* p = points_xyzw + 4 * i;
+      stage64[i] = make_double4(p[0], p[1], p[2], intensities[i]);
+    }
+  }
+  const size_t bytes = static_cast<size_t>(n) * cloud->bytes_per_point();
+  VL_CUDA(cudaMalloc(&cloud->d_points, bytes));
+  VL_CUDA(cudaMemcpyAsync(cloud->d_points, g_stage.ptr, bytes, cudaMemcpyHostToDevice, stream));
+  VL_CUDA(cudaStreamSynchronize(stream));  // staging buffer is shared
+  *out = cloud;
+  return VLCAL_OK;
+}
+
+int upload_image(int device, const uint8_t* image, int width, int height, int row_stride, cudaStream_t stream, std::shared_ptr<DeviceImage>* out) {
+  auto img = std::make_shared<DeviceImage>();
+  img->device = device;
+  img->width = width;
+  img->height = height;
+  const size_t bytes = static_cast<size_t>(width) * height;
+  VL_CUDA(cudaMalloc(&img->d_raw, bytes));
+  VL_CUDA(cudaMemcpy2DAsync(img->d_raw, width, image, row_stride, width, height, cudaMemcpyHostToDevice, stream));
+  VL_CUDA(cudaStreamSynchronize(stream));
+  *out = img;
+  return VLCAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------------
+
+using NidKernel = void (*)(const NidArgs);
+
+template <int MODEL>
+static NidKernel pick_layout(bool f32) {
+  return f32 ? nid_hist_exact_kernel<MODEL, true> : nid_hist_exact_kernel<MODEL, false>;
+}
+
+static NidKernel pick_kernel(int model, bool f32, int /*variant*/) {
+  switch (model) {
+    case CAM_PLUMB_BOB: return pick_layout<CAM_PLUMB_BOB>(f32);
+    case CAM_FISHEYE: return pick_layout<CAM_FISHEYE>(f32);
+    case CAM_ATAN: return pick_layout<CAM_ATAN>(f32);
+    case CAM_OMNIDIR: return pick_layout<CAM_OMNIDIR>(f32);
+    case CAM_EQUIRECTANGULAR: return pick_layout<CAM_EQUIRECTANGULAR>(f32);
+    case CAM_RATIONAL_POLYNOMIAL: return pick_layout<CAM_RATIONAL_POLYNOMIAL>(f32);
+    default: return nullptr;
+  }
+}
+
+constexpr size_t NID_SMEM_OPT_IN = 100 * 1024;  // dynamic shared memory ceiling we opt into
+constexpr size_t NID_SMEM_TARGET = 64 * 1024;   // privatised-copy budget per block
+
+struct LaunchGeom {
+  int copies;
+  size_t smem;
+  int blocks_per_sm;
+};
+
+static std::mutex g_geom_mu;
+static std::map<std::pair<const void*, size_t>, int> g_occupancy_cache;
+
+static int launch_geometry(NidKernel kernel, int n_poses, int nb, LaunchGeom* g) {
+  const size_t per_copy = static_cast<size_t>(n_poses) * nb * sizeof(int);
+  int copies = static_cast<int>(NID_SMEM_TARGET / per_copy);
+  copies = std::max(1, std::min(copies, NID_THREADS / 32));
+  g->copies = copies;
+  g->smem = per_copy * copies;
+  std::lock_guard<std::mutex> lock(g_geom_mu);
+  const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), g->smem);
+  auto it = g_occupancy_cache.find(key);
+  if (it == g_occupancy_cache.end()) {
+    VL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(NID_SMEM_OPT_IN)));
+    int nblk = 0;
+    VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kernel, NID_THREADS, g->smem));
+    it = g_occupancy_cache.emplace(key, std::max(1, nblk)).first;
+  }
+  g->blocks_per_sm = it->second;
+  return VLCAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+
+}  // namespace vlcal
+
+vlcal_nid_ctx::~vlcal_nid_ctx() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  for (auto& e : events) {
+    cudaEventDestroy(e.start);
+    cudaEventDestroy(e.stop);
+  }
+  if (d_bin_image) cudaFree(d_bin_image);
+  if (d_ghist) cudaFree(d_ghist);
+  if (d_counter) cudaFree(d_counter);
+  if (d_nid) cudaFree(d_nid);
+  if (d_hist_out) cudaFree(d_hist_out);
+  if (h_nid) cudaFreeHost(h_nid);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+namespace vlcal {
+
+int nid_ctx_create(
+  int device, int mode, const CameraParams& cam, std::shared_ptr<DeviceImage> image, std::shared_ptr<DeviceCloud> cloud, int bins, double max_fov, vlcal_nid_ctx** out) {
+  if (mode != VLCAL_NID_MODE_HISTOGRAM && mode != VLCAL_NID_MODE_BSPLINE) {
+    set_last_error("unknown NID mode");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  if (bins < 1 || bins > NID_MAX_BINS) {
+    set_last_error("bins must be in [1, " + std::to_string(NID_MAX_BINS) + "]");
+    return VLCAL_ERR_UNSUPPORTED;
+  }
+  VL_CUDA(cudaSetDevice(device));
+  std::unique_ptr<vlcal_nid_ctx> ctx(new vlcal_nid_ctx());
+  ctx->device = device;
+  ctx->mode = mode;
+  ctx->bins = bins;
+  ctx->cam = cam;
+  ctx->image = image;
+  ctx->cloud = cloud;
+  ctx->max_fov = max_fov;
+  ctx->cos_fov = std::cos(max_fov);  // cost_calculator_nid.cpp:32
+  VL_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
+  VL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+
+  const int nb = bins * bins;
+  ctx->max_poses = std::max(1, std::min<int>(NID_MAX_POSES, static_cast<int>((NID_SMEM_OPT_IN - 4096) / (static_cast<size_t>(nb) * sizeof(int)))));
+  VL_CUDA(cudaMalloc(&ctx->d_ghist, sizeof(int) * static_cast<size_t>(NID_MAX_POSES) * nb));
+  VL_CUDA(cudaMemsetAsync(ctx->d_ghist, 0, sizeof(int) * static_cast<size_t>(NID_MAX_POSES) * nb, ctx->stream));
+  VL_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+  VL_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
+
+  // image -> image-bin plane: image_bin = max(0, min(bins-1, int(u8/255.0 * bins)))  (cost_calculator_nid.cpp:43,46)
+  uint8_t lut[256];
+  for (int v = 0; v < 256; v++) {
+    const double pixel = v / 255.0;
+    int b = cast_int_x86(pixel * bins);
+    b = b < bins - 1 ? b : bins - 1;
+    b = b > 0 ? b : 0;
+    lut[v] = static_cast<uint8_t>(b);
+  }
+  uint8_t* d_lut = nullptr;
+  VL_CUDA(cudaMalloc(&d_lut, 256));
+  VL_CUDA(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t npix = static_cast<size_t>(image->width) * image->height;
+  VL_CUDA(cudaMalloc(&ctx->d_bin_image, std::max<size_t>(npix, 1)));
+  if (npix > 0) {
+    const dim3 grid((image->width + 255) / 256, image->height);
+    apply_lut_kernel<<<grid, 256, 0, ctx->stream>>>(image->d_raw, image->width, ctx->d_bin_image, image->width, image->height, d_lut);
+    VL_CUDA(cudaGetLastError());
+  }
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  VL_CUDA(cudaFree(d_lut));
+  *out = ctx.release();
+  return VLCAL_OK;
+}
+
+static int ensure_outputs(vlcal_nid_ctx* ctx, int n_poses, bool want_hist) {
+  if (n_poses > ctx->d_nid_cap) {
+    if (ctx->d_nid) cudaFree(ctx->d_nid);
+    if (ctx->h_nid) cudaFreeHost(ctx->h_nid);
+    ctx->d_nid = nullptr, ctx->h_nid = nullptr, ctx->d_nid_cap = 0;
+    const int cap = std::max(n_poses, 64);
+    VL_CUDA(cudaMalloc(&ctx->d_nid, sizeof(double) * cap));
+    VL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nid), sizeof(double) * cap, cudaHostAllocDefault));
+    ctx->d_nid_cap = cap;
+    ctx->h_nid_cap = cap;
+  }
+  if (want_hist) {
+    const size_t need = static_cast<size_t>(n_poses) * ctx->bins * ctx->bins;
+    if (need > ctx->d_hist_out_cap) {
+      if (ctx->d_hist_out) cudaFree(ctx->d_hist_out);
+      ctx->d_hist_out = nullptr, ctx->d_hist_out_cap = 0;
+      VL_CUDA(cudaMalloc(&ctx->d_hist_out, sizeof(int) * need));
+      ctx->d_hist_out_cap = need;
+    }
+  }
+  return VLCAL_OK;
+}
+
+int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses, bool want_hist) {
+  if (ctx->in_flight) {
+    set_last_error("an evaluation is already in flight on this context");
+    return VLCAL_ERR_BUSY;
+  }
+  if (ctx->mode != VLCAL_NID_MODE_HISTOGRAM) {
+    set_last_error("context was created in B-spline mode; use vlcal_nid_evaluate_bspline");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  VL_CUDA(cudaSetDevice(ctx->device));
+  {
+    const int rc = ensure_outputs(ctx, n_poses, want_hist);
+    if (rc != VLCAL_OK) return rc;
+  }
+  const int nb = ctx->bins * ctx->bins;
+  NidKernel kernel = pick_kernel(ctx->cam.model, ctx->cloud->f32, ctx->variant);
+  for (int p0 = 0; p0 < n_poses; p0 += ctx->max_poses) {
+    const int pc = std::min(ctx->max_poses, n_poses - p0);
+    NidArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.points = ctx->cloud->d_points;
+    a.bin_image = ctx->d_bin_image;
+    a.n = ctx->cloud->n;
+    a.width = ctx->image->width;
+    a.height = ctx->image->height;
+    a.bins = ctx->bins;
+    a.nb = nb;
+    a.n_poses = pc;
+    a.cos_fov = ctx->cos_fov;
+    a.cam = ctx->cam;
+    for (int p = 0; p < pc; p++) {
+      const double* T = T_colmajor + 16 * static_cast<size_t>(p0 + p);
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) a.pose[p][4 * r + c] = T[r + 4 * c];
+    }
+    a.ghist = ctx->d_ghist;
+    a.counter = ctx->d_counter;
+    a.nid_out = ctx->d_nid + p0;
+    a.hist_out = want_hist ? ctx->d_hist_out + static_cast<size_t>(p0) * nb : nullptr;
+
+    LaunchGeom g{1, 0, 1};
+    {
+      const int rc = launch_geometry(kernel, pc, nb, &g);
+      if (rc != VLCAL_OK) return rc;
+    }
+    a.copies = g.copies;
+    const long long want_blocks = (a.n + NID_THREADS - 1) / NID_THREADS;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want_blocks, static_cast<long long>(ctx->num_sms) * g.blocks_per_sm)));
+
+    ProfileEvents* ev = nullptr;
+    if (ctx->profiling) {
+      if (ctx->events_used == ctx->events.size()) {
+        ProfileEvents e;
+        VL_CUDA(cudaEventCreate(&e.start));
+        VL_CUDA(cudaEventCreate(&e.stop));
+        e.poses = 0;
+        ctx->events.push_back(e);
+      }
+      ev = &ctx->events[ctx->events_used++];
+      ev->poses = pc;
+      VL_CUDA(cudaEventRecord(ev->start, ctx->stream));
+    }
+    kernel<<<grid, NID_THREADS, g.smem, ctx->stream>>>(a);
+    VL_CUDA(cudaGetLastError());
+    if (ev) VL_CUDA(cudaEventRecord(ev->stop, ctx->stream));
+    ctx->launches++;
+    ctx->poses_total += pc;
+  }
+  VL_CUDA(cudaMemcpyAsync(ctx->h_nid, ctx->d_nid, sizeof(double) * n_poses, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->in_flight = true;
+  ctx->in_flight_poses = n_poses;
+  return VLCAL_OK;
+}
+
+static int drain_profile(vlcal_nid_ctx* ctx) {
+  for (size_t i = 0; i < ctx->events_used; i++) {
+    float ms = 0.f;
+    VL_CUDA(cudaEventElapsedTime(&ms, ctx->events[i].start, ctx->events[i].stop));
+    ctx->kernel_ms_accum += ms;
+  }
+  ctx->events_used = 0;
+  return VLCAL_OK;
+}
+
+int nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out) {
+  if (!ctx->in_flight) {
+    set_last_error("no evaluation in flight on this context");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  VL_CUDA(cudaSetDevice(ctx->device));
+  ctx->in_flight = false;
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->events_used > 256) {
+    const int rc = drain_profile(ctx);
+    if (rc != VLCAL_OK) return rc;
+  }
+  const int n_poses = ctx->in_flight_poses;
+  if (nid_out) std::memcpy(nid_out, ctx->h_nid, sizeof(double) * n_poses);
+  if (hist_out) {
+    if (!ctx->d_hist_out) {
+      set_last_error("histograms were not requested for the evaluation in flight");
+      return VLCAL_ERR_INVALID_ARGUMENT;
+    }
+    VL_CUDA(cudaMemcpy(hist_out, ctx->d_hist_out, sizeof(int) * static_cast<size_t>(n_poses) * ctx->bins * ctx->bins, cudaMemcpyDeviceToHost));
+  }
+  return VLCAL_OK;
+}
+
+}  // namespace vlcal
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+
+using namespace vlcal;
+
+extern "C" {
+
+const char* vlcal_nid_version(void) {
+  return "0.1.0";
+}
+
+const char* vlcal_nid_last_error(void) {
+  return g_last_error.c_str();
+}
+
+int vlcal_nid_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int vlcal_camera_model_id(const char* camera_model) {
+  if (camera_model == nullptr) {
+    set_last_error("camera_model is NULL");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  const std::string m(camera_model);  // create_camera.cpp:35-46
+  if (m == "plumb_bob") return VLCAL_CAMERA_PLUMB_BOB;
+  if (m == "fisheye" || m == "equidistant") return VLCAL_CAMERA_FISHEYE;
+  if (m == "atan") return VLCAL_CAMERA_ATAN;
+  if (m == "omnidir") return VLCAL_CAMERA_OMNIDIR;
+  if (m == "equirectangular") return VLCAL_CAMERA_EQUIRECTANGULAR;
+  if (m == "rational_polynomial") return VLCAL_CAMERA_RATIONAL_POLYNOMIAL;
+  set_last_error("error: unknown camera model " + m);  // :49
+  return VLCAL_ERR_UNKNOWN_CAMERA_MODEL;
+}
+
+int vlcal_camera_num_params(int camera_model, int* n_intrinsics, int* n_distortion) {
+  int ni = 0, nd = 0;
+  if (!camera_num_params(camera_model, &ni, &nd)) {
+    set_last_error("unknown camera model id");
+    return VLCAL_ERR_UNKNOWN_CAMERA_MODEL;
+  }
+  if (n_intrinsics) *n_intrinsics = ni;
+  if (n_distortion) *n_distortion = nd;
+  return VLCAL_OK;
+}
+
+int vlcal_camera_project(int camera_model, const double* intrinsics, int n_intrinsics, const double* distortion, int n_distortion, const double point_3d[3], double uv[2]) {
+  CameraParams cam;
+  const int rc = make_camera(camera_model, intrinsics, n_intrinsics, distortion, n_distortion, &cam);
+  if (rc != VLCAL_OK) return rc;
+  project_exact_dyn(cam, point_3d[0], point_3d[1], point_3d[2], &uv[0], &uv[1]);
+  return VLCAL_OK;
+}
+
+int vlcal_se3_expmap_gtsam(const double x[6], double T_colmajor[16]) {
+  if (!x || !T_colmajor) {
+    set_last_error("NULL argument");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  host::se3_expmap_gtsam(x, T_colmajor);
+  return VLCAL_OK;
+}
+
+int vlcal_estimate_camera_fov(int camera_model, const double* intrinsics, int n_intrinsics, const double* distortion, int n_distortion, int width, int height, double* max_fov_rad) {
+  CameraParams cam;
+  const int rc = make_camera(camera_model, intrinsics, n_intrinsics, distortion, n_distortion, &cam);
+  if (rc != VLCAL_OK) return rc;
+  *max_fov_rad = estimate_camera_fov_host(cam, width, height);
+  return VLCAL_OK;
+}
+
+int vlcal_nid_create(
+  vlcal_nid_ctx** ctx,
+  int device,
+  int mode,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  const uint8_t* image,
+  int width,
+  int height,
+  int row_stride_bytes,
+  const double* points_xyzw,
+  const double* intensities,
+  int64_t n_points,
+  int bins,
+  double max_fov_rad) {
+  if (!ctx) {
+    set_last_error("ctx is NULL");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  *ctx = nullptr;
+  if (width <= 0 || height <= 0 || !image || row_stride_bytes < width || n_points < 0 || (n_points > 0 && (!points_xyzw || !intensities))) {
+    set_last_error("invalid image / point buffers");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  CameraParams cam;
+  int rc = make_camera(camera_model, intrinsics, n_intrinsics, distortion, n_distortion, &cam);
+  if (rc != VLCAL_OK) return rc;
+  if (vlcal_nid_device_count() == 0) {
+    set_last_error("no CUDA device available: this library has no CPU fallback");
+    return VLCAL_ERR_NO_DEVICE;
+  }
+  if (device < 0) VL_CUDA(cudaGetDevice(&device));
+  VL_CUDA(cudaSetDevice(device));
+  if (max_fov_rad < 0.0) {
+    max_fov_rad = estimate_camera_fov_host(cam, width, height);  // cost_calculator_nid.cpp:17
+  }
+  std::shared_ptr<DeviceCloud> cloud;
+  std::shared_ptr<DeviceImage> img;
+  rc = upload_cloud(device, points_xyzw, intensities, n_points, /*stream=*/nullptr, &cloud);
+  if (rc != VLCAL_OK) return rc;
+  rc = upload_image(device, image, width, height, row_stride_bytes, /*stream=*/nullptr, &img);
+  if (rc != VLCAL_OK) return rc;
+  return nid_ctx_create(device, mode, cam, img, cloud, bins, max_fov_rad, ctx);
+}
+
+void vlcal_nid_destroy(vlcal_nid_ctx* ctx) {
+  delete ctx;
+}
+
+int vlcal_nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses) {
+  if (!ctx || !T_camera_lidar || n_poses <= 0) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  return nid_evaluate_async(ctx, T_camera_lidar, n_poses, /*want_hist=*/false);
+}
+
+int vlcal_nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out) {
+  if (!ctx) {
+    set_last_error("ctx is NULL");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  return nid_wait(ctx, nid_out, hist_out);
+}
+
+int vlcal_nid_evaluate(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double* nid_out, int32_t* hist_out) {
+  if (!ctx || !T_camera_lidar || n_poses <= 0) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  const int rc = nid_evaluate_async(ctx, T_camera_lidar, n_poses, hist_out != nullptr);
+  if (rc != VLCAL_OK) return rc;
+  return nid_wait(ctx, nid_out, hist_out);
+}
+
+int64_t vlcal_nid_num_points(const vlcal_nid_ctx* ctx) {
+  return ctx ? ctx->cloud->n : 0;
+}
+int vlcal_nid_bins(const vlcal_nid_ctx* ctx) {
+  return ctx ? ctx->bins : 0;
+}
+double vlcal_nid_max_fov(const vlcal_nid_ctx* ctx) {
+  return ctx ? ctx->max_fov : 0.0;
+}
+int vlcal_nid_points_are_f32(const vlcal_nid_ctx* ctx) {
+  return ctx && ctx->cloud->f32 ? 1 : 0;
+}
+int vlcal_nid_max_poses_per_launch(void) {
+  return NID_MAX_POSES;
+}
+
+int vlcal_nid_set_profiling(vlcal_nid_ctx* ctx, int enable) {
+  if (!ctx) return VLCAL_ERR_INVALID_ARGUMENT;
+  ctx->profiling = enable != 0;
+  return VLCAL_OK;
+}
+
+int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* kernel_ms_total, int64_t* poses_total) {
+  if (!ctx) return VLCAL_ERR_INVALID_ARGUMENT;
+  VL_CUDA(cudaSetDevice(ctx->device));
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int rc = drain_profile(ctx);
+  if (rc != VLCAL_OK) return rc;
+  if (kernel_launches) *kernel_launches = ctx->launches;
+  if (kernel_ms_total) *kernel_ms_total = ctx->kernel_ms_accum;
+  if (poses_total) *poses_total = ctx->poses_total;
+  return VLCAL_OK;
+}
+
+int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
+  if (!ctx) return VLCAL_ERR_INVALID_ARGUMENT;
+  VL_CUDA(cudaSetDevice(ctx->device));
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->events_used = 0;
+  ctx->launches = 0;
+  ctx->poses_total = 0;
+  ctx->kernel_ms_accum = 0.0;
+  return VLCAL_OK;
+}
+
+int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 1) return VLCAL_ERR_INVALID_ARGUMENT;
+  ctx->variant = variant;
+  return VLCAL_OK;
+}
+
+int vlcal_nid_evaluate_bspline(vlcal_nid_ctx* ctx, const double* T_params, int n_poses, double* nid_out, int32_t* ok_out, double* hist_out) {
+  (void)ctx, (void)T_params, (void)n_poses, (void)nid_out, (void)ok_out, (void)hist_out;
+  set_last_error("mode B (B-spline NIDCost) kernel is not built yet");
+  return VLCAL_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

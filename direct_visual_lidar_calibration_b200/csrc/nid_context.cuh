@@ -1,0 +1,107 @@
+// nid_context.cuh -- internal C++ types behind the C ABI (include/vlcal_nid.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "camera_models.cuh"
+#include "vlcal_nid.h"
+
+namespace vlcal {
+
+void set_last_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define VL_CUDA(expr)                                                   \
+  do {                                                                  \
+    cudaError_t e__ = (expr);                                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+// validated camera (create_camera.cpp:17-32 rules)
+int make_camera(int model, const double* intr, int n_intr, const double* dist, int n_dist, CameraParams* out);
+// estimate_camera_fov (estimate_fov.cpp:36-51)
+double estimate_camera_fov_host(const CameraParams& cam, int width, int height);
+
+// a cloud resident in HBM: float4 (x,y,z,intensity) when lossless, double4 otherwise
+struct DeviceCloud {
+  void* d_points = nullptr;
+  int64_t n = 0;
+  bool f32 = true;
+  int device = 0;
+  ~DeviceCloud();
+  size_t bytes_per_point() const { return f32 ? 16 : 32; }
+};
+
+// a grayscale image resident in HBM (tight rows)
+struct DeviceImage {
+  uint8_t* d_raw = nullptr;  // H x W u8
+  int width = 0, height = 0;
+  int device = 0;
+  ~DeviceImage();
+};
+
+int upload_cloud(int device, const double* points_xyzw, const double* intensities, int64_t n, cudaStream_t stream, std::shared_ptr<DeviceCloud>* out);
+int upload_image(int device, const uint8_t* image, int width, int height, int row_stride, cudaStream_t stream, std::shared_ptr<DeviceImage>* out);
+
+// GPU ViewCulling (view_culling.cpp:21-92): returns a compacted cloud and/or the kept indices
+int view_cull_device(
+  const CameraParams& cam, int width, int height, double max_fov, bool depth_culling, const DeviceCloud& cloud, const double T[16], cudaStream_t stream,
+  std::shared_ptr<DeviceCloud>* culled_out, int32_t* indices_host_out, int64_t* n_kept);
+
+struct ProfileEvents {
+  cudaEvent_t start, stop;
+  int poses;
+};
+
+}  // namespace vlcal
+
+struct vlcal_nid_ctx {
+  int device = 0;
+  int mode = 0;
+  int bins = 16;
+  int variant = 0;
+  double max_fov = 0.0;
+  double cos_fov = 0.0;
+  vlcal::CameraParams cam{};
+  std::shared_ptr<vlcal::DeviceCloud> cloud;
+  std::shared_ptr<vlcal::DeviceImage> image;
+  uint8_t* d_bin_image = nullptr;
+  cudaStream_t stream = nullptr;
+  // accumulators / outputs
+  int* d_ghist = nullptr;
+  unsigned int* d_counter = nullptr;
+  double* d_nid = nullptr;
+  int d_nid_cap = 0;
+  int* d_hist_out = nullptr;
+  size_t d_hist_out_cap = 0;
+  double* h_nid = nullptr;  // pinned
+  int h_nid_cap = 0;
+  // launch geometry
+  int max_poses = 1;
+  int num_sms = 148;
+  // async state
+  bool in_flight = false;
+  int in_flight_poses = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<vlcal::ProfileEvents> events;
+  size_t events_used = 0;
+  int64_t launches = 0;
+  int64_t poses_total = 0;
+  double kernel_ms_accum = 0.0;
+
+  ~vlcal_nid_ctx();
+};
+
+namespace vlcal {
+int nid_ctx_create(
+  int device, int mode, const CameraParams& cam, std::shared_ptr<DeviceImage> image, std::shared_ptr<DeviceCloud> cloud, int bins, double max_fov, vlcal_nid_ctx** out);
+int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses, bool want_hist);
+int nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out);
+}  // namespace vlcal

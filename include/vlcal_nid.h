@@ -1,0 +1,299 @@
+/*
+ * vlcal_nid.h -- C ABI of the B200-native NID registration engine (libvlcal_nid.so).
+ *
+ * This is the drop-in boundary for ONE hot path of koide3/direct_visual_lidar_calibration:
+ * the per-evaluation NID cost and the Nelder-Mead solve that drives it.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference repo root).
+ * Plain pointers and sizes only; no C++/torch types.  All matrices are 4x4 double,
+ * COLUMN-MAJOR (the memory of Eigen::Isometry3d::matrix().data()).
+ *
+ * Error convention (reference: I/O failure -> abort(), src/calibrate.cpp:31-34; unknown camera
+ * model -> nullptr, src/camera/create_camera.cpp:49-50): every function returns an int status,
+ * 0 = OK, < 0 = error; nothing throws or aborts across this boundary.  vlcal_nid_last_error()
+ * returns a thread-local message for the last failure.  There is NO CPU fallback: without a
+ * usable CUDA device the create/evaluate functions fail with VLCAL_ERR_CUDA / VLCAL_ERR_NO_DEVICE.
+ *
+ * Threading (reference: calculate() is called from OpenMP workers, one cost object per bag,
+ * never re-entered; src/vlcal/calib/visual_camera_calibration.cpp:107-110): contexts may be
+ * created / used from any host thread; different contexts may be used concurrently; one context
+ * must not be used from two threads at once.
+ */
+#ifndef VLCAL_NID_H
+#define VLCAL_NID_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLCAL_OK 0
+#define VLCAL_ERR_INVALID_ARGUMENT (-1)
+#define VLCAL_ERR_UNKNOWN_CAMERA_MODEL (-2) /* create_camera.cpp:49-50 (nullptr) */
+#define VLCAL_ERR_INTRINSIC_COUNT (-3)      /* create_camera.cpp:19-22 (nullptr) */
+#define VLCAL_ERR_CUDA (-4)
+#define VLCAL_ERR_NO_DEVICE (-5)
+#define VLCAL_ERR_UNSUPPORTED (-6)
+#define VLCAL_ERR_BUSY (-7)
+
+/* camera model ids, in the order of the string switch at src/camera/create_camera.cpp:35-46 */
+#define VLCAL_CAMERA_PLUMB_BOB 0           /* "plumb_bob"            include/camera/pinhole.hpp */
+#define VLCAL_CAMERA_FISHEYE 1             /* "fisheye"|"equidistant" include/camera/fisheye.hpp */
+#define VLCAL_CAMERA_ATAN 2                /* "atan"                 include/camera/atan.hpp */
+#define VLCAL_CAMERA_OMNIDIR 3             /* "omnidir"              include/camera/omnidir.hpp */
+#define VLCAL_CAMERA_EQUIRECTANGULAR 4     /* "equirectangular"      include/camera/equirectangular.hpp */
+#define VLCAL_CAMERA_RATIONAL_POLYNOMIAL 5 /* "rational_polynomial"  include/camera/rational_polynomial.hpp */
+
+/* cost modes */
+#define VLCAL_NID_MODE_HISTOGRAM 0 /* "mode A": CostCalculatorNID::calculate, integer joint histogram, nearest pixel
+                                      src/vlcal/calib/cost_calculator_nid.cpp:21-67 (what dfo::NelderMead scores) */
+#define VLCAL_NID_MODE_BSPLINE 1   /* "mode B": NIDCost::operator()<double>, 4x4 cubic-B-spline soft histogram (value only)
+                                      include/vlcal/costs/nid_cost.hpp:36-107 */
+
+typedef struct vlcal_nid_ctx vlcal_nid_ctx;
+
+/* ---- library / errors ------------------------------------------------------------------ */
+
+/* "major.minor.patch" of this library */
+const char* vlcal_nid_version(void);
+/* message of the last error on the calling thread ("" if none) */
+const char* vlcal_nid_last_error(void);
+/* number of visible CUDA devices (0 if none / no driver); never fails */
+int vlcal_nid_device_count(void);
+
+/* ---- camera factory facts (src/camera/create_camera.cpp:17-50) ----------------------- */
+
+/* model string -> id; VLCAL_ERR_UNKNOWN_CAMERA_MODEL where the reference returns nullptr */
+int vlcal_camera_model_id(const char* camera_model);
+/* CameraModelTraits<>::num_intrinsic_params / num_distortion_params of a model id */
+int vlcal_camera_num_params(int camera_model, int* n_intrinsics, int* n_distortion);
+/* GenericCameraBase::project(point_3d) for one point (host, double) -- include/camera/generic_camera.hpp:21-28.
+ * Intrinsic count must match the model (else VLCAL_ERR_INTRINSIC_COUNT); distortion is zero-padded/truncated. */
+int vlcal_camera_project(int camera_model, const double* intrinsics, int n_intrinsics, const double* distortion, int n_distortion, const double point_3d[3], double uv[2]);
+
+/* ---- host math shared by callers ----------------------------------------------------- */
+
+/* gtsam::Pose3::Expmap(x).matrix(), x = (wx,wy,wz,vx,vy,vz) -- call sites visual_camera_calibration.cpp:104,129 */
+int vlcal_se3_expmap_gtsam(const double x[6], double T_colmajor[16]);
+/* vlcal::estimate_camera_fov(proj, image_size) -- src/vlcal/common/estimate_fov.cpp:36-51 */
+int vlcal_estimate_camera_fov(int camera_model, const double* intrinsics, int n_intrinsics, const double* distortion, int n_distortion, int width, int height, double* max_fov_rad);
+
+/* ---- the cost object: CostCalculatorNID(proj, data, NIDCostParams{bins}) ---------------
+ * replaces the constructor at src/vlcal/calib/cost_calculator_nid.cpp:13-17 (one per bag per outer
+ * iteration, visual_camera_calibration.cpp:82-84).  Copies image and points host -> device (caller keeps
+ * ownership).  points_xyzw = Eigen::Vector4d[n] (x,y,z,1), intensities = double[n]
+ * (include/vlcal/common/frame.hpp:66,69).  max_fov_rad: pass a negative value to have the library compute
+ * estimate_camera_fov(camera, {width,height}) exactly as the reference constructor does (:17).
+ * device: CUDA ordinal, or -1 for the current device. */
+int vlcal_nid_create(
+  vlcal_nid_ctx** ctx,
+  int device,
+  int mode,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  const uint8_t* image,
+  int width,
+  int height,
+  int row_stride_bytes,
+  const double* points_xyzw,
+  const double* intensities,
+  int64_t n_points,
+  int bins,
+  double max_fov_rad);
+
+/* CostCalculatorNID::~CostCalculatorNID; frees device memory; NULL is a no-op */
+void vlcal_nid_destroy(vlcal_nid_ctx* ctx);
+
+/* CostCalculator::calculate(T_camera_lidar) for P poses in ONE pass over the cloud
+ * (include/vlcal/calib/cost_calculator.hpp:17; src/vlcal/calib/cost_calculator_nid.cpp:21-67).
+ * T_camera_lidar: P x 16 doubles (column-major 4x4 each).  nid_out: P doubles (NaN where the reference returns
+ * NaN, i.e. no inliers).  hist_out: optional P x bins x bins int32, index = image_bin + lidar_bin*bins
+ * (the storage of Eigen::MatrixXi hist(image_bin, lidar_bin)); pass NULL to skip.  Synchronous. */
+int vlcal_nid_evaluate(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double* nid_out, int32_t* hist_out);
+
+/* same, split so that several contexts (bags) overlap on the GPU: _async enqueues on the context's stream and
+ * returns; _wait blocks until that evaluation is done and delivers the results. One evaluation in flight per
+ * context (VLCAL_ERR_BUSY otherwise). */
+int vlcal_nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses);
+int vlcal_nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out);
+
+/* mode B evaluation with the reference's parameterisation: T_params = P x 7 doubles [qx qy qz qw tx ty tz]
+ * (Sophus::SE3d storage, include/vlcal/costs/nid_cost.hpp:38).  ok_out[p] = 0 where the reference functor returns
+ * false (non-finite NID, :98-102).  hist_out: optional P x bins x bins doubles (un-normalised). */
+int vlcal_nid_evaluate_bspline(vlcal_nid_ctx* ctx, const double* T_params, int n_poses, double* nid_out, int32_t* ok_out, double* hist_out);
+
+/* introspection */
+int64_t vlcal_nid_num_points(const vlcal_nid_ctx* ctx);
+int vlcal_nid_bins(const vlcal_nid_ctx* ctx);
+double vlcal_nid_max_fov(const vlcal_nid_ctx* ctx);
+/* 1 if the cloud is stored as float4 (x,y,z,intensity) = 16 B/point (lossless: inputs were float32-representable,
+ * SURVEY D9), 0 if the 32 B/point double layout had to be used */
+int vlcal_nid_points_are_f32(const vlcal_nid_ctx* ctx);
+/* max poses one kernel launch carries (larger batches are split into several launches) */
+int vlcal_nid_max_poses_per_launch(void);
+
+/* measurement hooks (bench.py): with profiling on, every histogram-kernel launch is bracketed by CUDA events on the
+ * context's stream. get_profile returns totals since the last reset. */
+int vlcal_nid_set_profiling(vlcal_nid_ctx* ctx, int enable);
+int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* kernel_ms_total, int64_t* poses_total);
+int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
+/* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck), 1 = exact fp64 only */
+int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
+
+/* ---- view culling: ViewCulling::cull (src/vlcal/calib/view_culling.cpp:21-92) ------------
+ * GPU z-buffer hidden-point removal at pose T.  indices_out: capacity n_points int32, receives the kept
+ * original indices in ascending order; *n_kept their count.  max_fov_rad < 0 -> estimate_camera_fov. */
+int vlcal_view_cull(
+  int device,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  int width,
+  int height,
+  double max_fov_rad,
+  int enable_depth_buffer_culling,
+  const double* points_xyzw,
+  int64_t n_points,
+  const double T_camera_lidar[16],
+  int32_t* indices_out,
+  int64_t* n_kept);
+
+/* ---- solver surface ------------------------------------------------------------------ */
+
+/* dfo::NelderMead<N>::Params (include/dfo/nelder_mead.hpp:11-22) */
+typedef struct {
+  double init_step;              /* 0.1  */
+  double alpha;                  /* 1.0  */
+  double gamma;                  /* 2.0  */
+  double rho;                    /* 0.5  */
+  double sigma;                  /* 0.5 (unused by the reference) */
+  int max_iterations;            /* 1024 */
+  double convergence_var_thresh; /* 1e-5 */
+} vlcal_nm_params;
+
+/* dfo::OptimizationResult<N> (include/dfo/optimizer.hpp:8-20) + evaluation counters */
+typedef struct {
+  int converged;
+  int num_iterations;
+  double x[8];
+  double y;
+  int num_evaluations;           /* evaluations the reference's serial NelderMead would have requested */
+  int num_batches;               /* batched objective calls issued */
+  int num_evaluations_computed;  /* poses actually scored (incl. speculative ones) */
+} vlcal_nm_result;
+
+void vlcal_nm_default_params(vlcal_nm_params* p);
+
+/* batch objective: ys[i] = f(xs + i*n) for i < count */
+typedef void (*vlcal_nm_batch_fn)(const double* xs, int count, int n, double* ys, void* user);
+/* observer called once per evaluation THE REFERENCE WOULD HAVE MADE, in the reference's order (this is where the
+ * objective's side effects -- best-cost bookkeeping / params.callback, visual_camera_calibration.cpp:112-116 -- go) */
+typedef void (*vlcal_nm_observe_fn)(const double* x, int n, double y, void* user);
+
+/* dfo::NelderMead<N>::optimize with the exact trajectory of the serial reference (include/dfo/nelder_mead.hpp:32-101),
+ * but asking for all candidates of an iteration {xo, xr, xe, xc} (or the shrink set) in one batch call. n <= 8. */
+int vlcal_nelder_mead_batched(int n, vlcal_nm_batch_fn f, vlcal_nm_observe_fn observe, void* user, const double* x0, const vlcal_nm_params* params, vlcal_nm_result* result);
+
+/* VisualCameraCalibrationParams (include/vlcal/calib/visual_camera_calibration.hpp:10-40) -- Nelder-Mead branch */
+typedef struct {
+  int max_outer_iterations;                /* 10 */
+  int max_inner_iterations;                /* 256 */
+  double delta_trans_thresh;               /* 0.1 [m] */
+  double delta_rot_thresh;                 /* 0.5 deg in rad */
+  int disable_z_buffer_culling;            /* 0 */
+  int nid_bins;                            /* 16 */
+  double nelder_mead_init_step;            /* 1e-3 */
+  double nelder_mead_convergence_criteria; /* 1e-8 */
+} vlcal_calib_params;
+void vlcal_calib_default_params(vlcal_calib_params* p);
+
+/* params.callback(T_camera_lidar) (visual_camera_calibration.hpp:38) -- fired on each best-cost improvement */
+typedef void (*vlcal_pose_callback)(const double T_camera_lidar[16], double cost, void* user);
+/* optional cross-process reduction of the per-pose partial sums over LOCAL bags (multi-GPU bag sharding):
+ * must replace vals[0..count) by the sum over all ranks, identically on every rank. NULL = single process. */
+typedef void (*vlcal_allreduce_fn)(double* vals, int count, void* user);
+
+/* one bag as the reference's VisualLiDARData (include/vlcal/common/visual_lidar_data.hpp:10-23): host buffers */
+typedef struct {
+  const uint8_t* image; /* CV_8UC1 */
+  int width, height, row_stride_bytes;
+  const double* points_xyzw; /* Eigen::Vector4d[n] */
+  const double* intensities; /* double[n] */
+  int64_t n_points;
+} vlcal_bag;
+
+typedef struct {
+  int outer_iterations;
+  int total_evaluations;          /* reference-equivalent objective evaluations */
+  int total_evaluations_computed; /* poses actually scored per bag */
+  int total_batches;
+  int inner_iterations[16];
+  double inner_final_cost[16];
+  int64_t culled_points[16]; /* points kept by view culling in bag 0 per outer iteration */
+  int64_t kernel_launches;
+  double kernel_ms_total; /* only if profiling != 0 */
+} vlcal_calib_stats;
+
+/* the objective of estimate_pose_nelder_mead (visual_camera_calibration.cpp:103-119) over already-built cost
+ * objects: T = init_T * Expmap(x), sum over ctxs of calculate(T), Nelder-Mead with the calibration parameters
+ * (:122-127), result pose init_T * Expmap(result.x) (:129).  The contexts play the role of `costs` (:75-84). */
+int vlcal_estimate_pose_nelder_mead_ctx(
+  vlcal_nid_ctx* const* ctxs,
+  int n_ctxs,
+  const vlcal_calib_params* params,
+  const double init_T_camera_lidar[16],
+  vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce,
+  void* user,
+  double T_out[16],
+  vlcal_nm_result* nm_result);
+
+/* VisualCameraCalibration::estimate_pose_nelder_mead (visual_camera_calibration.cpp:70-139) from host data:
+ * view culling at init_T (GPU), one cost context per bag, Nelder-Mead, pose out. */
+int vlcal_estimate_pose_nelder_mead(
+  int device,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  const vlcal_bag* bags,
+  int n_bags,
+  const vlcal_calib_params* params,
+  const double init_T_camera_lidar[16],
+  vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce,
+  void* user,
+  int profiling,
+  double T_out[16],
+  vlcal_nm_result* nm_result,
+  vlcal_calib_stats* stats);
+
+/* VisualCameraCalibration::calibrate, NID_NELDER_MEAD branch (visual_camera_calibration.cpp:35-68) */
+int vlcal_calibrate_nelder_mead(
+  int device,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  const vlcal_bag* bags,
+  int n_bags,
+  const vlcal_calib_params* params,
+  const double init_T_camera_lidar[16],
+  vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce,
+  void* user,
+  int profiling,
+  double T_out[16],
+  vlcal_calib_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLCAL_NID_H */

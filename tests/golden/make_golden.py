@@ -1,0 +1,66 @@
+"""Generates the golden fixtures in this directory FROM THE ORACLE (oracle/vlcal_oracle.c).
+
+The reference ships no golden vectors, so these pins are ours: they freeze the oracle's answers on
+seeded inputs so that (a) a later edit of the oracle that changes behaviour is caught by the CPU suite and (b) the
+GPU suite can compare against committed numbers, not only against a checker built in the same run.
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import oracle as O  # noqa: E402
+import util  # noqa: E402
+
+
+def main():
+    # 1. hand-derived known-answer vectors for the entropy/NID tail (cost_calculator_nid.cpp:54-64), SURVEY.md 8c,
+    #    computed independently in float64 with numpy (not with the oracle)
+    def nid_np(h):
+        h = np.asarray(h, dtype=np.float64)
+        s = h.sum()
+        H = lambda p: -(p * np.log(p + 1e-6)).sum()  # noqa: E731
+        Hr, Hs, Hrs = H(h.sum(1) / s), H(h.sum(0) / s), H(h / s)
+        MI = Hr + Hs - Hrs
+        return {"Hr": Hr, "Hs": Hs, "Hrs": Hrs, "MI": MI, "NID": (Hrs - MI) / Hrs}
+
+    kats = []
+    for name, h in [("diag2", [[2, 0], [0, 2]]), ("ones2", [[1, 1], [1, 1]]), ("mixed2", [[3, 1], [0, 4]]), ("10I16", (10 * np.eye(16, dtype=int)).tolist()), ("ones16", np.ones((16, 16), dtype=int).tolist())]:
+        kats.append({"name": name, "hist": h, **nid_np(h)})
+    with open(os.path.join(HERE, "nid_kat.json"), "w") as f:
+        json.dump(kats, f, indent=1)
+
+    # 2. per-camera-model mode-A fixtures: small seeded problem, 3 poses, oracle histograms + NID
+    for model in util.MODELS:
+        pr = util.random_problem(model, n=3000, seed=100 + util.MODELS.index(model), size=(160, 120) if model != "equirectangular" else (160, 80))
+        intr = list(pr["intrinsics"])
+        if model == "equirectangular":
+            intr = [160.0, 80.0]
+        else:
+            intr = [v * 0.25 for v in intr]
+        cam = O.create_camera(model, intr, pr["distortion"])
+        fov = O.estimate_camera_fov(cam, pr["W"], pr["H"])
+        Ts = util.random_poses(pr["T"], 3, seed=7)
+        nids, hists = [], []
+        for T in Ts:
+            nid, h = O.nid_calculate(cam, pr["image"], pr["points"], pr["intensities"], 16, fov, T)
+            nids.append(nid)
+            hists.append(h)
+        idx = O.view_cull(cam, pr["W"], pr["H"], fov, True, pr["points"], Ts[0])
+        np.savez_compressed(
+            os.path.join(HERE, f"mode_a_{model}.npz"),
+            intrinsics=np.array(intr), distortion=np.array(pr["distortion"], dtype=np.float64), image=pr["image"],
+            points=pr["points"].astype(np.float32), intensities=pr["intensities"].astype(np.float32), poses=Ts, max_fov=fov,
+            nid=np.array(nids), hist=np.stack(hists).astype(np.int32), cull_indices=idx.astype(np.int32),
+        )
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

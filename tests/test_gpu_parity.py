@@ -1,0 +1,269 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the committed golden
+fixtures.  Bar: integer histograms bit-exact (0 differing counts); NID within 1e-12 of the oracle (the required
+tolerance of BASELINE.json's north_star is 1e-6) -- the only non-identical arithmetic is log() in the entropy tail
+(CUDA libdevice vs glibc, <= 1 ulp each) and the fixed-tree summation order."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NID_TOL = 1e-12
+
+
+def _cost(V, pr, bins=16, **kw):
+    cam = V.create_camera(pr["model"], pr["intrinsics"], pr["distortion"])
+    data = V.VisualLiDARData(pr["image"], pr["points"], pr["intensities"])
+    return V.CostCalculatorNID(cam, data, V.NIDCostParams(bins), **kw)
+
+
+def _oracle_eval(O, pr, Ts, bins=16):
+    cam = O.create_camera(pr["model"], pr["intrinsics"], pr["distortion"])
+    fov = O.estimate_camera_fov(cam, pr["W"], pr["H"])
+    out = [O.nid_calculate(cam, pr["image"], pr["points"], pr["intensities"], bins, fov, T) for T in Ts]
+    return np.array([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+def _assert_close_nid(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(a)
+    assert np.all(np.abs(a[m] - b[m]) < NID_TOL), np.abs(a[m] - b[m]).max()
+
+
+@pytest.mark.parametrize("model", util.MODELS)
+def test_golden_fixtures(gpu, model):
+    V = gpu
+    g = np.load(os.path.join(GOLDEN, f"mode_a_{model}.npz"))
+    cam = V.create_camera(model, g["intrinsics"], g["distortion"])
+    data = V.VisualLiDARData(g["image"], np.concatenate([g["points"][:, :3].astype(np.float64), np.ones((g["points"].shape[0], 1))], axis=1), g["intensities"].astype(np.float64))
+    cost = V.CostCalculatorNID(cam, data)
+    assert cost.max_fov == float(g["max_fov"])
+    nid, hist = cost.calculate_batch(g["poses"], return_hist=True)
+    assert np.array_equal(hist, g["hist"])
+    _assert_close_nid(nid, g["nid"])
+    idx = V.ViewCulling(cam, (g["image"].shape[1], g["image"].shape[0])).cull_indices(data.points, g["poses"][0])
+    assert np.array_equal(idx, g["cull_indices"])
+
+
+@pytest.mark.parametrize("model", util.MODELS)
+def test_histograms_bit_exact_vs_oracle(gpu, oracle, model):
+    pr = util.random_problem(model, n=60000, seed=21)
+    Ts = util.random_poses(pr["T"], 5, seed=4)
+    cost = _cost(gpu, pr)
+    assert cost.points_are_f32
+    nid, hist = cost.calculate_batch(Ts, return_hist=True)
+    ref_nid, ref_hist = _oracle_eval(oracle, pr, Ts)
+    assert int(np.abs(hist - ref_hist).sum()) == 0
+    assert hist.sum() > 10000
+    _assert_close_nid(nid, ref_nid)
+    # reference surface: calculate(T) == batch entry, bit for bit
+    assert cost.calculate(Ts[2]) == nid[2]
+
+
+def test_batch_equals_singles_and_chunking(gpu, oracle):
+    pr = util.random_problem("plumb_bob", n=30000, seed=5)
+    Ts = util.random_poses(pr["T"], 21, seed=8)  # > 2 launches of 8 poses
+    cost = _cost(gpu, pr)
+    nid, hist = cost.calculate_batch(Ts, return_hist=True)
+    for p in (0, 7, 8, 20):
+        n1, h1 = cost.calculate_batch(Ts[p : p + 1], return_hist=True)
+        assert n1[0] == nid[p] and np.array_equal(h1[0], hist[p])
+    ref_nid, ref_hist = _oracle_eval(oracle, pr, Ts)
+    assert np.array_equal(hist, ref_hist)
+    _assert_close_nid(nid, ref_nid)
+    # repeated evaluation is deterministic and the self-cleaning accumulators leave no residue
+    nid2, hist2 = cost.calculate_batch(Ts, return_hist=True)
+    assert np.array_equal(nid, nid2) and np.array_equal(hist, hist2)
+
+
+@pytest.mark.parametrize("bins", [1, 4, 32, 64, 128])
+def test_other_bin_counts(gpu, oracle, bins):
+    pr = util.random_problem("plumb_bob", n=20000, seed=6)
+    Ts = util.random_poses(pr["T"], 3, seed=1)
+    nid, hist = _cost(gpu, pr, bins).calculate_batch(Ts, return_hist=True)
+    ref_nid, ref_hist = _oracle_eval(oracle, pr, Ts, bins)
+    assert np.array_equal(hist, ref_hist)
+    _assert_close_nid(nid, ref_nid)
+
+
+def test_unsupported_bins_is_an_error_not_a_fallback(gpu):
+    pr = util.random_problem("plumb_bob", n=100, seed=6)
+    with pytest.raises(gpu.VlcalError) as e:
+        _cost(gpu, pr, 256)
+    assert e.value.code == -6
+
+
+def test_double_layout_when_points_are_not_float32(gpu, oracle):
+    pr = util.random_problem("rational_polynomial", n=20000, seed=7, f32=False)
+    Ts = util.random_poses(pr["T"], 4, seed=2)
+    cost = _cost(gpu, pr)
+    assert not cost.points_are_f32
+    nid, hist = cost.calculate_batch(Ts, return_hist=True)
+    ref_nid, ref_hist = _oracle_eval(oracle, pr, Ts)
+    assert np.array_equal(hist, ref_hist)
+    _assert_close_nid(nid, ref_nid)
+
+
+def test_edge_cases(gpu, oracle):
+    V = gpu
+    cam = V.create_camera("plumb_bob", [100.0, 100.0, 2.0, 2.0], [])
+    img = (np.arange(16, dtype=np.uint8).reshape(4, 4) * 16).copy()
+    T = np.eye(4)
+
+    def inliers(x, y, z=1.0):
+        data = V.VisualLiDARData(img, np.array([[x, y, z, 1.0]]), np.array([0.5]))
+        c = V.CostCalculatorNID(cam, data, max_fov=1.4)
+        return int(c.calculate_batch(T[None], return_hist=True)[1].sum())
+
+    assert inliers(-0.025, 0.0) == 1  # u = -0.5 truncates to column 0 and is accepted
+    assert inliers(-0.0301, 0.0) == 0 and inliers(0.0199, 0.0) == 1 and inliers(0.02, 0.0) == 0
+    assert inliers(0.0, -0.025) == 1 and inliers(0.0, 0.0201) == 0
+    assert inliers(0.0, 0.0, -1.0) == 0  # behind the camera
+    assert inliers(float("nan"), 0.0) == 0
+    # no inliers -> NaN, as the reference (no guard, cost_calculator_nid.cpp:54-64)
+    data = V.VisualLiDARData(img, np.array([[0.0, 0.0, -1.0, 1.0]]), np.array([0.5]))
+    assert math.isnan(V.CostCalculatorNID(cam, data, max_fov=1.4).calculate(T))
+    # empty cloud -> NaN
+    data = V.VisualLiDARData(img, np.zeros((0, 4)), np.zeros(0))
+    assert math.isnan(V.CostCalculatorNID(cam, data, max_fov=1.4).calculate(T))
+    # padded image rows (row_stride > width)
+    big = np.random.default_rng(0).integers(0, 256, (48, 80), dtype=np.uint8)
+    view = big[:, :64]
+    pr = util.random_problem("plumb_bob", n=5000, seed=3, size=(64, 48))
+    cam2 = V.create_camera("plumb_bob", [40.0, 41.0, 32.0, 24.0], pr["distortion"])
+    ocam = oracle.create_camera("plumb_bob", [40.0, 41.0, 32.0, 24.0], pr["distortion"])
+
+    class _D:  # VisualLiDARData would make the view contiguous; build the strided case by hand
+        image, points, intensities = view, pr["points"], pr["intensities"]
+
+        @staticmethod
+        def size():
+            return pr["points"].shape[0]
+
+    c = V.CostCalculatorNID(cam2, _D)
+    _, h = c.calculate_batch(pr["T"][None], return_hist=True)
+    fov = oracle.estimate_camera_fov(ocam, 64, 48)
+    _, href = oracle.nid_calculate(ocam, np.ascontiguousarray(view), pr["points"], pr["intensities"], 16, fov, pr["T"])
+    assert np.array_equal(h[0], href)
+    # w != 1 is rejected loudly
+    bad = V.VisualLiDARData(img, np.array([[0.0, 0.0, 1.0, 2.0]]), np.array([0.5]))
+    with pytest.raises(V.VlcalError):
+        V.CostCalculatorNID(cam, bad)
+
+
+def test_permutation_invariance(gpu):
+    pr = util.random_problem("fisheye", n=40000, seed=12)
+    perm = np.random.default_rng(1).permutation(40000)
+    a = _cost(gpu, pr).calculate_batch(pr["T"][None], return_hist=True)
+    pr2 = dict(pr, points=pr["points"][perm], intensities=pr["intensities"][perm])
+    b = _cost(gpu, pr2).calculate_batch(pr["T"][None], return_hist=True)
+    assert np.array_equal(a[1], b[1]) and a[0][0] == b[0][0]
+
+
+@pytest.mark.parametrize("model", util.MODELS)
+@pytest.mark.parametrize("depth", [True, False])
+def test_view_culling_indices_identical(gpu, oracle, model, depth):
+    pr = util.random_problem(model, n=80000, seed=31)
+    cam = gpu.create_camera(model, pr["intrinsics"], pr["distortion"])
+    ocam = oracle.create_camera(model, pr["intrinsics"], pr["distortion"])
+    fov = oracle.estimate_camera_fov(ocam, pr["W"], pr["H"])
+    ref = oracle.view_cull(ocam, pr["W"], pr["H"], fov, depth, pr["points"], pr["T"])
+    idx = gpu.ViewCulling(cam, (pr["W"], pr["H"]), gpu.ViewCullingParams(depth)).cull_indices(pr["points"], pr["T"])
+    assert np.array_equal(idx, ref) and len(ref) > 1000
+
+
+def _synthetic_bag(n, cfg=3, scale=0.5):
+    from direct_visual_lidar_calibration_b200 import synthetic as S
+
+    bag = S.make_bag("pinhole_640x480", "frustum", n, config_index=cfg, scale=scale)
+    bag["T_init"] = S.perturb(bag["T_gt"], (0.3, -0.3, 0.3), (0.01, -0.01, 0.01))
+    return bag
+
+
+def test_inner_solve_follows_oracle_evaluation_by_evaluation(gpu, oracle):
+    V = gpu
+    bag = _synthetic_bag(40000)
+    cam = V.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    ocam = oracle.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    data = V.VisualLiDARData(bag["image"], bag["points"], bag["intensities"])
+    params = V.VisualCameraCalibrationParams()
+    params.max_inner_iterations = 80
+    calib = V.VisualCameraCalibration(cam, [data], params)
+    T, r = calib.estimate_pose_nelder_mead(bag["T_init"])
+    op = oracle.default_calib_params()
+    op.max_inner_iterations = 80
+    ref = oracle.estimate_pose_nelder_mead(ocam, [(bag["image"], bag["points"], bag["intensities"])], bag["T_init"], op)
+    assert r["num_iterations"] == ref["num_iterations"] and r["converged"] == ref["converged"]
+    assert r["num_evaluations"] == ref["num_evaluations"]
+    assert np.array_equal(r["x"], ref["x"])  # identical decisions -> identical simplex arithmetic
+    assert abs(r["y"] - ref["y"]) < NID_TOL
+    assert np.abs(T - ref["T"]).max() == 0.0
+    # best-cost callback sequence == prefix minima of the oracle's evaluation trace
+    tr = ref["trace"][:, 6]
+    best, expect = float("inf"), []
+    for c in tr:
+        if c < best:
+            best = c
+            expect.append(c)
+    got = [c for _, c in calib.trace]
+    assert len(got) == len(expect) and np.allclose(got, expect, atol=NID_TOL)
+    assert calib.stats["total_batches"] < ref["num_evaluations"]  # batched: fewer launches than evaluations
+
+
+def test_full_calibrate_matches_oracle_two_bags(gpu, oracle):
+    V = gpu
+    b1, b2 = _synthetic_bag(30000, cfg=4), _synthetic_bag(25000, cfg=5)
+    cam = V.create_camera(b1["camera_model"], b1["intrinsics"], b1["distortion"])
+    ocam = oracle.create_camera(b1["camera_model"], b1["intrinsics"], b1["distortion"])
+    params = V.VisualCameraCalibrationParams()
+    params.max_inner_iterations = 40
+    params.max_outer_iterations = 3
+    params.delta_trans_thresh = 1e-4  # force more than one outer iteration
+    params.delta_rot_thresh = 1e-5
+    ds = [V.VisualLiDARData(b["image"], b["points"], b["intensities"]) for b in (b1, b2)]
+    calib = V.VisualCameraCalibration(cam, ds, params)
+    T = calib.calibrate(b1["T_init"])
+    op = oracle.default_calib_params()
+    op.max_inner_iterations, op.max_outer_iterations, op.delta_trans_thresh, op.delta_rot_thresh = 40, 3, 1e-4, 1e-5
+    ref = oracle.calibrate(ocam, [(b["image"], b["points"], b["intensities"]) for b in (b1, b2)], b1["T_init"], op)
+    assert calib.stats["outer_iterations"] == ref["outer_iterations"]
+    assert calib.stats["inner_iterations"] == ref["inner_iterations"]
+    assert calib.stats["total_evaluations"] == ref["total_evaluations"]
+    assert np.abs(T - ref["T"]).max() < 1e-15
+    assert np.allclose(calib.stats["inner_final_cost"], ref["inner_final_cost"], atol=2 * NID_TOL)
+
+
+def test_full_size_properties_c2(gpu):
+    """BASELINE.json configs[1] size (1M points, 1920x1080): size-independent properties instead of the oracle."""
+    V = gpu
+    from direct_visual_lidar_calibration_b200 import synthetic as S
+
+    rng = np.random.default_rng(77)
+    n = 1_000_000
+    dirs = S.lidar_directions("os1_64", n, rng)
+    pts = (dirs * rng.uniform(1.0, 20.0, (n, 1))).astype(np.float32).astype(np.float64)
+    inten = rng.integers(0, 256, n) / 256.0
+    image = rng.integers(0, 256, (1080, 1920), dtype=np.uint8)
+    model, intr, dist, W, H = S.CAMERAS["pinhole_1920x1080"]
+    cam = V.create_camera(model, intr, dist)
+    xyzw = np.concatenate([pts, np.ones((n, 1))], axis=1)
+    T = S.gt_T_camera_lidar()
+    Ts = util.random_poses(T, 4, seed=3, rot_deg=0.5, trans=0.02)
+    full = V.CostCalculatorNID(cam, V.VisualLiDARData(image, xyzw, inten))
+    nid, hist = full.calculate_batch(Ts, return_hist=True)
+    # additivity: histogram of the whole cloud == sum of the histograms of its two halves (integer, exact)
+    h1 = V.CostCalculatorNID(cam, V.VisualLiDARData(image, xyzw[: n // 2], inten[: n // 2])).calculate_batch(Ts, return_hist=True)[1]
+    h2 = V.CostCalculatorNID(cam, V.VisualLiDARData(image, xyzw[n // 2 :], inten[n // 2 :])).calculate_batch(Ts, return_hist=True)[1]
+    assert np.array_equal(hist, h1 + h2)
+    # lidar marginal of the inliers is bounded by the cloud's own intensity histogram
+    lb = np.minimum((inten * 16).astype(int), 15)
+    assert np.all(hist.sum(axis=1) <= np.bincount(lb, minlength=16)[None, :])
+    assert hist.sum() > 0 and np.all((nid >= 0) & (nid <= 1 + 1e-9))
+    # inliers never exceed the points that survive bounds-only culling at the same pose
+    kept = V.ViewCulling(cam, (W, H), V.ViewCullingParams(False)).cull_indices(xyzw, Ts[0])
+    assert hist[0].sum() <= len(kept)
