@@ -264,6 +264,9 @@ def test_full_size_properties_c2(gpu):
     lb = np.minimum((inten * 16).astype(int), 15)
     assert np.all(hist.sum(axis=1) <= np.bincount(lb, minlength=16)[None, :])
     assert hist.sum() > 0 and np.all((nid >= 0) & (nid <= 1 + 1e-9))
-    # inliers never exceed the points that survive bounds-only culling at the same pose
+    # bounds-only culling keeps a subset of the cost's inliers at the same pose: its FoV test divides z by the norm of
+    # the homogeneous 4-vector (view_culling.cpp:45), which is stricter than the cost's z/|xyz| (cost_calculator_nid.cpp:32)
     kept = V.ViewCulling(cam, (W, H), V.ViewCullingParams(False)).cull_indices(xyzw, Ts[0])
-    assert hist[0].sum() <= len(kept)
+    assert 0 < len(kept) <= hist[0].sum()
+    sub = V.CostCalculatorNID(cam, V.VisualLiDARData(image, xyzw[kept], inten[kept])).calculate_batch(Ts[:1], return_hist=True)[1]
+    assert sub[0].sum() == len(kept)  # every culled-in point is an inlier of the cost at that pose
