@@ -97,6 +97,18 @@ class CostCalculatorNID:
         return bool(self._L.vlcal_nid_points_are_f32(self._ctx))
 
     @property
+    def filter_enabled(self) -> bool:
+        return bool(self._L.vlcal_nid_filter_enabled(self._ctx))
+
+    def debug_filter_check(self, Ts):
+        """Test hook: (point_poses, deferred_to_exact, mismatches, max |uv32-uv64|/bound)."""
+        Tc = T_to_colmajor(Ts)
+        counts = (C.c_uint64 * 3)()
+        ratio = C.c_double()
+        _lib.check(self._L.vlcal_nid_debug_filter_check(self._ctx, _dp(Tc), Tc.shape[0], counts, C.byref(ratio)))
+        return int(counts[0]), int(counts[1]), int(counts[2]), float(ratio.value)
+
+    @property
     def handle(self):
         return self._ctx
 

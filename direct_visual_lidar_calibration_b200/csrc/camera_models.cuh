@@ -165,6 +165,63 @@ VL_HD void project_exact(const CameraParams& c, xd px, xd py, xd pz, xd& u, xd& 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 filter projections
+//
+// The filter never decides a point on its own authority near a decision edge: every fast projection comes with a
+// rigorous bound E (pixels) on |uv_fp32 - uv_reference|, assembled from
+//   rho    = delta / depth, delta >= |pc_fp32 - pc_exact| per component (5u(|x|+|y|+|z|+max|t|), u = 2^-24)
+//   k_rho  = f * L * (1 + Rmax): L bounds the Jacobian norm of the distortion map over the part of the normalised
+//            plane the FoV test lets through (r <= Rmax = tan(max_fov)), so it turns input error into pixel error
+//   k0     = rounding of the fp32 evaluation itself (division, polynomial, intrinsics)
+// all evaluated on the host in double (fast_filter.hpp) with a safety factor.  A verdict is accepted only when the
+// fp32 pixel is farther than E from every integer (truncation edge) and outside the +-E band around the image
+// border; everything else is re-decided by project_exact.  DESIGN.md has the derivation.
+// ---------------------------------------------------------------------------------------------
+
+struct FastCam {
+  int enabled;    // 0: this camera / FoV combination has no fp32 filter -> exact kernel only
+  float cos_fov;  // float(cos(max_fov))
+  float fx, fy, cx, cy, xi;
+  float d[8];
+  float k_rho_u, k_rho_v;  // pixels per unit rho
+  float k0_u, k0_v;        // pixels
+  float aux0, aux1;        // model specific (see fast_filter.hpp)
+};
+
+constexpr float F32_U = 5.9604644775390625e-08f;  // 2^-24, unit roundoff of binary32
+
+// returns true when (u, v, Eu, Ev) are valid; false -> the caller must use the exact path
+template <int MODEL>
+__device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float pcy, float pcz, float nrm, float delta, float& u, float& v, float& Eu, float& Ev) {
+  if constexpr (MODEL == CAM_PLUMB_BOB || MODEL == CAM_RATIONAL_POLYNOMIAL) {
+    // enabled only when cos_fov >= 0.05: a certain FoV pass then implies pcz >= 0.05*|pc| > 0 and r <= Rmax
+    const float inv = __frcp_rn(pcz);
+    const float x = pcx * inv, y = pcy * inv;
+    const float x2 = x * x, y2 = y * y, xy = x * y;
+    const float r2 = x2 + y2;
+    float rc;
+    if constexpr (MODEL == CAM_PLUMB_BOB) {
+      rc = fmaf(r2, fmaf(r2, fmaf(r2, c.d[4], c.d[1]), c.d[0]), 1.0f);  // 1 + k1 r2 + k2 r4 + k3 r6
+    } else {
+      const float num = fmaf(r2, fmaf(r2, fmaf(r2, c.d[4], c.d[1]), c.d[0]), 1.0f);
+      const float den = fmaf(r2, fmaf(r2, fmaf(r2, c.d[7], c.d[6]), c.d[5]), 1.0f);
+      rc = num * __frcp_rn(den);  // host guarantees den >= aux0 > 0 on r <= Rmax
+    }
+    const float p1 = c.d[2], p2 = c.d[3];
+    const float xd = fmaf(x, rc, fmaf(2.0f * p1, xy, p2 * fmaf(2.0f, x2, r2)));
+    const float yd = fmaf(y, rc, fmaf(2.0f * p2, xy, p1 * fmaf(2.0f, y2, r2)));
+    u = fmaf(c.fx, xd, c.cx);
+    v = fmaf(c.fy, yd, c.cy);
+    const float rho = delta * inv;
+    Eu = fmaf(c.k_rho_u, rho, c.k0_u);
+    Ev = fmaf(c.k_rho_v, rho, c.k0_v);
+    return true;
+  } else {
+    return false;
+  }
+}
+
 // runtime dispatch (host-side helpers: estimate_camera_fov, vlcal_camera_project)
 VL_HD void project_exact_dyn(const CameraParams& c, double px, double py, double pz, double* u, double* v) {
   xd uu(NAN), vv(NAN);

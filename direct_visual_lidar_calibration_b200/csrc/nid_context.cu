@@ -8,12 +8,15 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
 
+#include "fast_filter.hpp"
 #include "host_math.hpp"
+#include "mem_pool.hpp"
 #include "nid_kernels.cuh"
 
 namespace vlcal {
@@ -114,17 +117,11 @@ double estimate_camera_fov_host(const CameraParams& cam, int width, int height) 
 // ---------------------------------------------------------------------------------------------
 
 DeviceCloud::~DeviceCloud() {
-  if (d_points) {
-    cudaSetDevice(device);
-    cudaFree(d_points);
-  }
+  MemPool::instance().device_free(device, d_points);
 }
 
 DeviceImage::~DeviceImage() {
-  if (d_raw) {
-    cudaSetDevice(device);
-    cudaFree(d_raw);
-  }
+  MemPool::instance().device_free(device, d_raw);
 }
 
 // process-wide pinned staging buffer (cudaHostAlloc costs milliseconds; contexts are rebuilt every outer iteration)
@@ -134,10 +131,10 @@ struct PinnedStage {
   size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return VLCAL_OK;
-    if (ptr) cudaFreeHost(ptr);
+    MemPool::instance().pinned_free(ptr);
     ptr = nullptr, cap = 0;
     const size_t want = std::max(bytes + bytes / 4, static_cast<size_t>(1) << 20);
-    VL_CUDA(cudaHostAlloc(&ptr, want, cudaHostAllocDefault));
+    VL_CUDA(MemPool::instance().pinned_alloc(want, &ptr));
     cap = want;
     return VLCAL_OK;
   }
@@ -184,7 +181,7 @@ int upload_cloud(int device, const double* points_xyzw, const double* intensitie
     }
   }
   const size_t bytes = static_cast<size_t>(n) * cloud->bytes_per_point();
-  VL_CUDA(cudaMalloc(&cloud->d_points, bytes));
+  VL_CUDA(MemPool::instance().device_alloc(device, bytes, &cloud->d_points));
   VL_CUDA(cudaMemcpyAsync(cloud->d_points, g_stage.ptr, bytes, cudaMemcpyHostToDevice, stream));
   VL_CUDA(cudaStreamSynchronize(stream));  // staging buffer is shared
   *out = cloud;
@@ -197,7 +194,7 @@ int upload_image(int device, const uint8_t* image, int width, int height, int ro
   img->width = width;
   img->height = height;
   const size_t bytes = static_cast<size_t>(width) * height;
-  VL_CUDA(cudaMalloc(&img->d_raw, bytes));
+  VL_CUDA(MemPool::instance().device_alloc(device, bytes, reinterpret_cast<void**>(&img->d_raw)));
   VL_CUDA(cudaMemcpy2DAsync(img->d_raw, width, image, row_stride, width, height, cudaMemcpyHostToDevice, stream));
   VL_CUDA(cudaStreamSynchronize(stream));
   *out = img;
@@ -210,19 +207,22 @@ int upload_image(int device, const uint8_t* image, int width, int height, int ro
 
 using NidKernel = void (*)(const NidArgs);
 
+// kind: 0 = fp32 filter + exact recheck (float4 layout only), 1 = exact fp64, 2 = verify (debug)
 template <int MODEL>
-static NidKernel pick_layout(bool f32) {
+static NidKernel pick_layout(bool f32, int kind) {
+  if (f32 && kind == 0) return nid_hist_filter_kernel<MODEL, true>;
+  if (f32 && kind == 2) return nid_filter_verify_kernel<MODEL, true>;
   return f32 ? nid_hist_exact_kernel<MODEL, true> : nid_hist_exact_kernel<MODEL, false>;
 }
 
-static NidKernel pick_kernel(int model, bool f32, int /*variant*/) {
+static NidKernel pick_kernel(int model, bool f32, int kind) {
   switch (model) {
-    case CAM_PLUMB_BOB: return pick_layout<CAM_PLUMB_BOB>(f32);
-    case CAM_FISHEYE: return pick_layout<CAM_FISHEYE>(f32);
-    case CAM_ATAN: return pick_layout<CAM_ATAN>(f32);
-    case CAM_OMNIDIR: return pick_layout<CAM_OMNIDIR>(f32);
-    case CAM_EQUIRECTANGULAR: return pick_layout<CAM_EQUIRECTANGULAR>(f32);
-    case CAM_RATIONAL_POLYNOMIAL: return pick_layout<CAM_RATIONAL_POLYNOMIAL>(f32);
+    case CAM_PLUMB_BOB: return pick_layout<CAM_PLUMB_BOB>(f32, kind);
+    case CAM_FISHEYE: return pick_layout<CAM_FISHEYE>(f32, kind);
+    case CAM_ATAN: return pick_layout<CAM_ATAN>(f32, kind);
+    case CAM_OMNIDIR: return pick_layout<CAM_OMNIDIR>(f32, kind);
+    case CAM_EQUIRECTANGULAR: return pick_layout<CAM_EQUIRECTANGULAR>(f32, kind);
+    case CAM_RATIONAL_POLYNOMIAL: return pick_layout<CAM_RATIONAL_POLYNOMIAL>(f32, kind);
     default: return nullptr;
   }
 }
@@ -271,12 +271,14 @@ vlcal_nid_ctx::~vlcal_nid_ctx() {
     cudaEventDestroy(e.start);
     cudaEventDestroy(e.stop);
   }
-  if (d_bin_image) cudaFree(d_bin_image);
-  if (d_ghist) cudaFree(d_ghist);
-  if (d_counter) cudaFree(d_counter);
-  if (d_nid) cudaFree(d_nid);
-  if (d_hist_out) cudaFree(d_hist_out);
-  if (h_nid) cudaFreeHost(h_nid);
+  auto& pool = vlcal::MemPool::instance();
+  pool.device_free(device, d_bin_image);
+  pool.device_free(device, d_ghist);
+  pool.device_free(device, d_counter);
+  pool.device_free(device, d_nid);
+  pool.device_free(device, d_hist_out);
+  pool.pinned_free(h_nid);
+  pool.pinned_free(h_flag);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -302,14 +304,15 @@ int nid_ctx_create(
   ctx->cloud = cloud;
   ctx->max_fov = max_fov;
   ctx->cos_fov = std::cos(max_fov);  // cost_calculator_nid.cpp:32
+  ctx->fast = make_fast_cam(cam, image->width, image->height, max_fov);
   VL_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
   VL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 
   const int nb = bins * bins;
   ctx->max_poses = std::max(1, std::min<int>(NID_MAX_POSES, static_cast<int>((NID_SMEM_OPT_IN - 4096) / (static_cast<size_t>(nb) * sizeof(int)))));
-  VL_CUDA(cudaMalloc(&ctx->d_ghist, sizeof(int) * static_cast<size_t>(NID_MAX_POSES) * nb));
+  VL_CUDA(MemPool::instance().device_alloc(device, sizeof(int) * static_cast<size_t>(NID_MAX_POSES) * nb, reinterpret_cast<void**>(&ctx->d_ghist)));
   VL_CUDA(cudaMemsetAsync(ctx->d_ghist, 0, sizeof(int) * static_cast<size_t>(NID_MAX_POSES) * nb, ctx->stream));
-  VL_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+  VL_CUDA(MemPool::instance().device_alloc(device, sizeof(unsigned int), reinterpret_cast<void**>(&ctx->d_counter)));
   VL_CUDA(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), ctx->stream));
 
   // image -> image-bin plane: image_bin = max(0, min(bins-1, int(u8/255.0 * bins)))  (cost_calculator_nid.cpp:43,46)
@@ -322,42 +325,62 @@ int nid_ctx_create(
     lut[v] = static_cast<uint8_t>(b);
   }
   uint8_t* d_lut = nullptr;
-  VL_CUDA(cudaMalloc(&d_lut, 256));
+  VL_CUDA(MemPool::instance().device_alloc(device, 256, reinterpret_cast<void**>(&d_lut)));
   VL_CUDA(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, ctx->stream));
   const size_t npix = static_cast<size_t>(image->width) * image->height;
-  VL_CUDA(cudaMalloc(&ctx->d_bin_image, std::max<size_t>(npix, 1)));
+  VL_CUDA(MemPool::instance().device_alloc(device, std::max<size_t>(npix, 1), reinterpret_cast<void**>(&ctx->d_bin_image)));
   if (npix > 0) {
     const dim3 grid((image->width + 255) / 256, image->height);
     apply_lut_kernel<<<grid, 256, 0, ctx->stream>>>(image->d_raw, image->width, ctx->d_bin_image, image->width, image->height, d_lut);
     VL_CUDA(cudaGetLastError());
   }
   VL_CUDA(cudaStreamSynchronize(ctx->stream));
-  VL_CUDA(cudaFree(d_lut));
+  MemPool::instance().device_free(device, d_lut);
   *out = ctx.release();
   return VLCAL_OK;
 }
 
 static int ensure_outputs(vlcal_nid_ctx* ctx, int n_poses, bool want_hist) {
   if (n_poses > ctx->d_nid_cap) {
-    if (ctx->d_nid) cudaFree(ctx->d_nid);
-    if (ctx->h_nid) cudaFreeHost(ctx->h_nid);
+    auto& pool = MemPool::instance();
+    pool.device_free(ctx->device, ctx->d_nid);
+    pool.pinned_free(ctx->h_nid);
     ctx->d_nid = nullptr, ctx->h_nid = nullptr, ctx->d_nid_cap = 0;
     const int cap = std::max(n_poses, 64);
-    VL_CUDA(cudaMalloc(&ctx->d_nid, sizeof(double) * cap));
-    VL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_nid), sizeof(double) * cap, cudaHostAllocDefault));
+    VL_CUDA(pool.device_alloc(ctx->device, sizeof(double) * cap, reinterpret_cast<void**>(&ctx->d_nid)));
+    VL_CUDA(pool.pinned_alloc(sizeof(double) * cap, reinterpret_cast<void**>(&ctx->h_nid)));
+    if (!ctx->h_flag) {
+      VL_CUDA(pool.pinned_alloc(sizeof(unsigned long long), reinterpret_cast<void**>(&ctx->h_flag)));
+      *ctx->h_flag = 0;
+    }
     ctx->d_nid_cap = cap;
     ctx->h_nid_cap = cap;
   }
   if (want_hist) {
     const size_t need = static_cast<size_t>(n_poses) * ctx->bins * ctx->bins;
     if (need > ctx->d_hist_out_cap) {
-      if (ctx->d_hist_out) cudaFree(ctx->d_hist_out);
+      MemPool::instance().device_free(ctx->device, ctx->d_hist_out);
       ctx->d_hist_out = nullptr, ctx->d_hist_out_cap = 0;
-      VL_CUDA(cudaMalloc(&ctx->d_hist_out, sizeof(int) * need));
+      VL_CUDA(MemPool::instance().device_alloc(ctx->device, sizeof(int) * need, reinterpret_cast<void**>(&ctx->d_hist_out)));
       ctx->d_hist_out_cap = need;
     }
   }
   return VLCAL_OK;
+}
+
+// float copy of the poses for the fp32 filter: R, t rounded to nearest; max|t| rounded up
+static void fill_pose32(NidArgs& a, int pc) {
+  for (int p = 0; p < pc; p++) {
+    const double* T = a.pose[p];
+    float* P = a.pose32[p];
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) P[3 * r + c] = static_cast<float>(T[4 * r + c]);
+      P[9 + r] = static_cast<float>(T[4 * r + 3]);
+    }
+    const double tmax = std::max(std::fabs(T[3]), std::max(std::fabs(T[7]), std::fabs(T[11])));
+    P[12] = std::nextafter(static_cast<float>(tmax), INFINITY);
+    P[13] = P[14] = P[15] = 0.f;
+  }
 }
 
 int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses, bool want_hist) {
@@ -375,7 +398,9 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
     if (rc != VLCAL_OK) return rc;
   }
   const int nb = ctx->bins * ctx->bins;
-  NidKernel kernel = pick_kernel(ctx->cam.model, ctx->cloud->f32, ctx->variant);
+  // the fp32 filter needs the float4 layout, a camera/FoV it has bounds for, and 32-bit point indices
+  const bool use_filter = ctx->variant == 0 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
+  NidKernel kernel = pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? 0 : 1);
   for (int p0 = 0; p0 < n_poses; p0 += ctx->max_poses) {
     const int pc = std::min(ctx->max_poses, n_poses - p0);
     NidArgs a;
@@ -395,9 +420,15 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 4; c++) a.pose[p][4 * r + c] = T[r + 4 * c];
     }
+    fill_pose32(a, pc);
+    a.fast = ctx->fast;
     a.ghist = ctx->d_ghist;
     a.counter = ctx->d_counter;
     a.nid_out = ctx->d_nid + p0;
+    a.nid_host = ctx->h_nid + p0;  // UVA: pinned host memory is directly addressable from the device
+    const bool last_chunk = p0 + pc >= n_poses;
+    a.done_flag = last_chunk ? ctx->h_flag : nullptr;
+    a.done_seq = ctx->seq + 1;
     a.hist_out = want_hist ? ctx->d_hist_out + static_cast<size_t>(p0) * nb : nullptr;
 
     LaunchGeom g{1, 0, 1};
@@ -428,7 +459,7 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
     ctx->launches++;
     ctx->poses_total += pc;
   }
-  VL_CUDA(cudaMemcpyAsync(ctx->h_nid, ctx->d_nid, sizeof(double) * n_poses, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->seq += 1;
   ctx->in_flight = true;
   ctx->in_flight_poses = n_poses;
   return VLCAL_OK;
@@ -451,8 +482,32 @@ int nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out) {
   }
   VL_CUDA(cudaSetDevice(ctx->device));
   ctx->in_flight = false;
-  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  {
+    // the last block of the last launch writes the scores into mapped host memory and then bumps the flag: poll it
+    // (a few microseconds) instead of paying a D2H copy + stream synchronisation per Nelder-Mead batch; fall back to
+    // the stream (which also surfaces launch / execution errors) if the flag does not arrive promptly.
+    volatile unsigned long long* flag = ctx->h_flag;
+    bool done = false;
+    for (int spin = 0; spin < 4000000; spin++) {
+      if (*flag == ctx->seq) {
+        done = true;
+        break;
+      }
+      if ((spin & 0x3fff) == 0x3fff && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;
+      __builtin_ia32_pause();
+    }
+    if (!done) VL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*flag != ctx->seq) {
+      VL_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (*flag != ctx->seq) {
+        set_last_error("evaluation finished without publishing its results");
+        return VLCAL_ERR_CUDA;
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
   if (ctx->events_used > 256) {
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));
     const int rc = drain_profile(ctx);
     if (rc != VLCAL_OK) return rc;
   }
@@ -463,6 +518,7 @@ int nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out) {
       set_last_error("histograms were not requested for the evaluation in flight");
       return VLCAL_ERR_INVALID_ARGUMENT;
     }
+    VL_CUDA(cudaStreamSynchronize(ctx->stream));  // the flag only orders the scores; histograms come from device memory
     VL_CUDA(cudaMemcpy(hist_out, ctx->d_hist_out, sizeof(int) * static_cast<size_t>(n_poses) * ctx->bins * ctx->bins, cudaMemcpyDeviceToHost));
   }
   return VLCAL_OK;
@@ -673,6 +729,70 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant) {
   if (!ctx || variant < 0 || variant > 1) return VLCAL_ERR_INVALID_ARGUMENT;
   ctx->variant = variant;
+  return VLCAL_OK;
+}
+
+int vlcal_nid_trim_memory(void) {
+  MemPool::instance().trim();
+  return VLCAL_OK;
+}
+
+int vlcal_nid_filter_enabled(const vlcal_nid_ctx* ctx) {
+  return ctx && ctx->fast.enabled && ctx->cloud->f32 ? 1 : 0;
+}
+
+int vlcal_nid_debug_filter_check(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, uint64_t counts[3], double* max_bound_ratio) {
+  if (!ctx || !T_camera_lidar || n_poses <= 0 || !counts) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  if (!vlcal_nid_filter_enabled(ctx) || ctx->mode != VLCAL_NID_MODE_HISTOGRAM) {
+    set_last_error("the fp32 filter is not enabled for this context (camera model / FoV / point layout)");
+    return VLCAL_ERR_UNSUPPORTED;
+  }
+  VL_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long* d_dbg = nullptr;
+  VL_CUDA(MemPool::instance().device_alloc(ctx->device, 4 * sizeof(unsigned long long), reinterpret_cast<void**>(&d_dbg)));
+  VL_CUDA(cudaMemsetAsync(d_dbg, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  NidKernel kernel = pick_kernel(ctx->cam.model, true, 2);
+  for (int p0 = 0; p0 < n_poses; p0 += NID_MAX_POSES) {
+    const int pc = std::min(NID_MAX_POSES, n_poses - p0);
+    NidArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.points = ctx->cloud->d_points;
+    a.bin_image = ctx->d_bin_image;
+    a.n = ctx->cloud->n;
+    a.width = ctx->image->width;
+    a.height = ctx->image->height;
+    a.bins = ctx->bins;
+    a.nb = ctx->bins * ctx->bins;
+    a.n_poses = pc;
+    a.cos_fov = ctx->cos_fov;
+    a.cam = ctx->cam;
+    for (int p = 0; p < pc; p++) {
+      const double* T = T_camera_lidar + 16 * static_cast<size_t>(p0 + p);
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) a.pose[p][4 * r + c] = T[r + 4 * c];
+    }
+    fill_pose32(a, pc);
+    a.fast = ctx->fast;
+    a.dbg = d_dbg;
+    const long long want_blocks = (a.n + NID_THREADS - 1) / NID_THREADS;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want_blocks, static_cast<long long>(ctx->num_sms) * 4)));
+    kernel<<<grid, NID_THREADS, 0, ctx->stream>>>(a);
+    VL_CUDA(cudaGetLastError());
+  }
+  unsigned long long h[4];
+  VL_CUDA(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  MemPool::instance().device_free(ctx->device, d_dbg);
+  counts[0] = h[0], counts[1] = h[1], counts[2] = h[2];
+  if (max_bound_ratio) {
+    const unsigned int bits = static_cast<unsigned int>(h[3] & 0xffffffffu);
+    float f;
+    std::memcpy(&f, &bits, sizeof(f));
+    *max_bound_ratio = f;
+  }
   return VLCAL_OK;
 }
 

@@ -69,6 +69,7 @@ struct vlcal_nid_ctx {
   double max_fov = 0.0;
   double cos_fov = 0.0;
   vlcal::CameraParams cam{};
+  vlcal::FastCam fast{};
   std::shared_ptr<vlcal::DeviceCloud> cloud;
   std::shared_ptr<vlcal::DeviceImage> image;
   uint8_t* d_bin_image = nullptr;
@@ -80,8 +81,10 @@ struct vlcal_nid_ctx {
   int d_nid_cap = 0;
   int* d_hist_out = nullptr;
   size_t d_hist_out_cap = 0;
-  double* h_nid = nullptr;  // pinned
+  double* h_nid = nullptr;  // pinned + mapped: the finalize block writes the scores here directly (zero-copy)
   int h_nid_cap = 0;
+  unsigned long long* h_flag = nullptr;  // pinned + mapped completion word polled by nid_wait
+  unsigned long long seq = 0;
   // launch geometry
   int max_poses = 1;
   int num_sms = 148;

@@ -34,15 +34,21 @@ struct NidArgs {
   double cos_fov;             // cos(max_fov)  (:32)
   CameraParams cam;
   double pose[NID_MAX_POSES][12];  // row-major 3x4 [R|t] of T_camera_lidar
+  float pose32[NID_MAX_POSES][16]; // fp32 filter copy: R (9, row-major), t (3), max|t| (1), pad
+  FastCam fast;                    // fp32 filter constants (fast.enabled == 0 -> exact kernel only)
+  unsigned long long* dbg;         // verify kernel only: {point-poses, uncertain, mismatches, max ratio bits}
   int* ghist;                 // [NID_MAX_POSES][nb] global accumulators, zero on entry, zero on exit
   unsigned int* counter;      // block ticket, zero on entry, zero on exit
   double* nid_out;            // [n_poses]
+  double* nid_host;           // optional zero-copy mirror of nid_out in mapped pinned host memory
+  unsigned long long* done_flag;  // optional mapped host word; receives done_seq after the results are visible
+  unsigned long long done_seq;
   int* hist_out;              // optional [n_poses][nb], index = image_bin + lidar_bin*bins
 };
 
-// ---- exact classification of one (point, pose): returns image_bin (>= 0) or -1 if the reference skips the point
+// ---- exact decision for one (point, pose): pixel index iy*W+ix (>= 0), or -1 if the reference skips the point
 template <int MODEL>
-__device__ __forceinline__ int classify_exact(const NidArgs& a, const double* __restrict__ T, double x, double y, double z) {
+__device__ __forceinline__ int exact_pixel(const NidArgs& a, const double* __restrict__ T, double x, double y, double z, double* u_out = nullptr, double* v_out = nullptr) {
   // :31 pt_camera = T * p  -> ((m0*x + m1*y) + m2*z) + m3
   const xd X(x), Y(y), Z(z);
   const xd pcx = ((xd(T[0]) * X + xd(T[1]) * Y) + xd(T[2]) * Z) + xd(T[3]);
@@ -57,13 +63,61 @@ __device__ __forceinline__ int classify_exact(const NidArgs& a, const double* __
   // :37 project + cast<int> (truncation; NaN -> INT_MIN)
   xd u, v;
   project_exact<MODEL>(a.cam, pcx, pcy, pcz, u, v);
+  if (u_out) *u_out = u.v;
+  if (v_out) *v_out = v.v;
   const int ix = cast_int_x86(u.v);
   const int iy = cast_int_x86(v.v);
   // :38
   if (ix < 0 || iy < 0 || ix >= a.width || iy >= a.height) {
     return -1;
   }
-  return static_cast<int>(__ldg(a.bin_image + static_cast<size_t>(iy) * a.width + ix));
+  return iy * a.width + ix;
+}
+
+template <int MODEL>
+__device__ __forceinline__ int classify_exact(const NidArgs& a, const double* __restrict__ T, double x, double y, double z) {
+  const int pix = exact_pixel<MODEL>(a, T, x, y, z);
+  return pix < 0 ? -1 : static_cast<int>(__ldg(a.bin_image + pix));  // :43,:46 via the pre-binned image
+}
+
+// ---- fp32 filter --------------------------------------------------------------------------------------------
+constexpr int VERDICT_REJECT = -1;     // certainly skipped by the reference
+constexpr int VERDICT_UNCERTAIN = -2;  // within the error bound of a decision edge: ask the exact path
+
+// one image coordinate: 0 = certainly outside, 1 = certainly inside with pixel index `ip`, 2 = uncertain
+__device__ __forceinline__ int coord_verdict(float c, float E, int size, int& ip) {
+  if (!(E < 0.25f)) return 2;                // bound useless (or NaN)
+  if (c < -1.0f - E) return 0;               // reference coordinate < -1 -> truncates to <= -1
+  if (c > static_cast<float>(size) + E) return 0;  // reference coordinate > size -> index >= size
+  const float r = rintf(c);
+  if (!(fabsf(c - r) > E)) return 2;         // an integer (truncation edge, image border) lies within the bound; NaN lands here
+  ip = static_cast<int>(c);                  // truncation toward zero, like cast<int>()
+  return (ip >= 0 && ip < size) ? 1 : 0;
+}
+
+// returns pixel index (>= 0), VERDICT_REJECT or VERDICT_UNCERTAIN
+template <int MODEL>
+__device__ __forceinline__ int classify_fast(const NidArgs& a, const float* __restrict__ P, float x, float y, float z, float a_p) {
+  const float pcx = fmaf(P[0], x, fmaf(P[1], y, fmaf(P[2], z, P[9])));
+  const float pcy = fmaf(P[3], x, fmaf(P[4], y, fmaf(P[5], z, P[10])));
+  const float pcz = fmaf(P[6], x, fmaf(P[7], y, fmaf(P[8], z, P[11])));
+  const float n2 = fmaf(pcx, pcx, fmaf(pcy, pcy, pcz * pcz));
+  const float nrm = n2 * rsqrtf(n2);
+  const float delta = (5.25f * F32_U) * (a_p + P[12]);
+  // FoV: sign of g = pcz - cos_fov*|pc| with |g_fp32 - g_exact| <= 2.8 delta + 8.5 u |pc|
+  const float g = fmaf(-a.fast.cos_fov, nrm, pcz);
+  const float mf = fmaf(3.0f, delta, (12.0f * F32_U) * nrm);
+  if (!(fabsf(g) > mf)) return VERDICT_UNCERTAIN;  // also catches NaN / n2 == 0
+  if (g < 0.0f) return VERDICT_REJECT;
+  float u, v, Eu, Ev;
+  if (!project_fast<MODEL>(a.fast, pcx, pcy, pcz, nrm, delta, u, v, Eu, Ev)) return VERDICT_UNCERTAIN;
+  int ix = 0, iy = 0;
+  const int vu = coord_verdict(u, Eu, a.width, ix);
+  if (vu == 0) return VERDICT_REJECT;
+  const int vv = coord_verdict(v, Ev, a.height, iy);
+  if (vv == 0) return VERDICT_REJECT;
+  if (vu == 2 || vv == 2) return VERDICT_UNCERTAIN;
+  return iy * a.width + ix;
 }
 
 __device__ __forceinline__ int lidar_bin_of(double intensity, int bins) {
@@ -139,7 +193,9 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
     const double Hs = -block_sum(t_s, scratch);
     if (threadIdx.x == 0) {
       const double MI = Hr + Hs - Hrs;    // :63
-      a.nid_out[p] = (Hrs - MI) / Hrs;    // :64 (NaN when there are no inliers, as in the reference)
+      const double nid = (Hrs - MI) / Hrs;  // :64 (NaN when there are no inliers, as in the reference)
+      a.nid_out[p] = nid;
+      if (a.nid_host) a.nid_host[p] = nid;
     }
     // export + self-clean
     for (int k = threadIdx.x; k < a.nb; k += blockDim.x) {
@@ -148,7 +204,34 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *a.counter = 0u;
+  if (threadIdx.x == 0) {
+    *a.counter = 0u;
+    if (a.done_flag) {  // publish to the polling host thread: results first, then the sequence number
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
+    }
+  }
+}
+
+// block epilogue shared by the histogram kernels: merge copies -> global accumulators -> last block finalizes
+__device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, int* smem_hist, bool* s_is_last) {
+  const int per_copy = a.n_poses * a.nb;
+  __syncthreads();
+  for (int k = threadIdx.x; k < per_copy; k += blockDim.x) {
+    int s = 0;
+    for (int c = 0; c < a.copies; c++) s += smem_hist[c * per_copy + k];
+    if (s) atomicAdd(a.ghist + k, s);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(a.counter, 1u);
+    *s_is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!*s_is_last) return;
+  __threadfence();
+  nid_finalize(a, smem_hist);
 }
 
 template <int MODEL, bool F32>
@@ -178,24 +261,124 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __gri
       }
     }
   }
-  __syncthreads();
+  nid_block_epilogue(a, smem_hist, &s_is_last);
+}
 
-  // merge the block's copies into the global accumulators
-  for (int k = threadIdx.x; k < per_copy; k += blockDim.x) {
-    int s = 0;
-    for (int c = 0; c < a.copies; c++) s += smem_hist[c * per_copy + k];
-    if (s) atomicAdd(a.ghist + k, s);
-  }
-  __threadfence();
+constexpr int NID_QUEUE = 64;  // per-warp queue of (point, pose) pairs waiting for the exact path
+
+// K1 (default): fp32 filter + exact fp64 recheck.
+// Every (point, pose) is first classified in fp32 together with a rigorous error bound; verdicts that are farther
+// than the bound from every decision edge (FoV cone, integer pixel boundaries, image border) are final.  The rest
+// (~1-3 %) are pushed on a per-warp shared-memory queue and re-decided 32 at a time by the exact double path, so
+// the fp64 pipe runs with full warps instead of diverging inside the hot loop.  The histogram is therefore
+// bit-identical to the all-fp64 kernel (tests/test_gpu_parity.py::test_filter_kernel_*).
+template <int MODEL, bool F32>
+__global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __grid_constant__ NidArgs a) {
+  extern __shared__ int smem_hist[];
+  __shared__ bool s_is_last;
+  __shared__ unsigned int q_idx[NID_THREADS / 32][NID_QUEUE];
+  __shared__ unsigned char q_pose[NID_THREADS / 32][NID_QUEUE];
+  static_assert(F32, "the fp32 filter runs on the float4 cloud layout");
+  const int per_copy = a.n_poses * a.nb;
+  for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int ticket = atomicAdd(a.counter, 1u);
-    s_is_last = (ticket == gridDim.x - 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  int* my_hist = smem_hist + (warp % a.copies) * per_copy;
+  const float4* __restrict__ pts = static_cast<const float4*>(a.points);
+  int qn = 0;  // queue fill, warp-uniform
+
+  auto drain32 = [&](int first, int count) {  // entries [first, first+count), count <= 32
+    if (lane < count) {
+      const unsigned int i = q_idx[warp][first + lane];
+      const int p = q_pose[warp][first + lane];
+      const float4 q = __ldg(pts + i);
+      const int ib = classify_exact<MODEL>(a, a.pose[p], q.x, q.y, q.z);
+      if (ib >= 0) atomicAdd(&my_hist[p * a.nb + ib + lidar_bin_of(q.w, a.bins) * a.bins], 1);
+    }
+  };
+
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long warp_base = static_cast<long long>(blockIdx.x) * blockDim.x + warp * 32;
+  for (long long base = warp_base; base < a.n; base += stride) {  // trip count is warp-uniform
+    const long long i = base + lane;
+    const bool valid = i < a.n;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) q = __ldg(pts + i);
+    const float a_p = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
+    const int lb_off = lidar_bin_of(q.w, a.bins) * a.bins;
+    for (int p = 0; p < a.n_poses; p++) {
+      int verdict = VERDICT_REJECT;
+      if (valid) verdict = classify_fast<MODEL>(a, a.pose32[p], q.x, q.y, q.z, a_p);
+      if (verdict >= 0) {
+        const int ib = __ldg(a.bin_image + verdict);
+        atomicAdd(&my_hist[p * a.nb + ib + lb_off], 1);  // :49 hist(image_bin, lidar_bin)++
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, verdict == VERDICT_UNCERTAIN);
+      if (m) {
+        if (verdict == VERDICT_UNCERTAIN) {
+          const int pos = qn + __popc(m & lt_mask);
+          q_idx[warp][pos] = static_cast<unsigned int>(i);
+          q_pose[warp][pos] = static_cast<unsigned char>(p);
+        }
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+          drain32(qn - 32, 32);
+          qn -= 32;
+          __syncwarp();
+        }
+      }
+    }
   }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  nid_finalize(a, smem_hist);
+  if (qn > 0) drain32(0, qn);
+  nid_block_epilogue(a, smem_hist, &s_is_last);
+}
+
+// debug / test kernel: runs BOTH paths on every (point, pose) and counts, in a.dbg:
+//   [0] point-poses, [1] uncertain verdicts, [2] certain verdicts that disagree with the exact path (must be 0),
+//   [3] max over certain in-image verdicts of |uv_fp32 - uv_exact| / E, as float bits scaled (atomicMax)
+template <int MODEL, bool F32>
+__global__ void __launch_bounds__(NID_THREADS) nid_filter_verify_kernel(const __grid_constant__ NidArgs a) {
+  static_assert(F32, "the fp32 filter runs on the float4 cloud layout");
+  const float4* __restrict__ pts = static_cast<const float4*>(a.points);
+  unsigned long long total = 0, uncertain = 0, mismatch = 0;
+  float max_ratio = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const float4 q = __ldg(pts + i);
+    const float a_p = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
+    for (int p = 0; p < a.n_poses; p++) {
+      total++;
+      const int vf = classify_fast<MODEL>(a, a.pose32[p], q.x, q.y, q.z, a_p);
+      double ue = 0.0, ve = 0.0;
+      const int pe = exact_pixel<MODEL>(a, a.pose[p], q.x, q.y, q.z, &ue, &ve);
+      if (vf == VERDICT_UNCERTAIN) {
+        uncertain++;
+      } else if (vf != pe) {  // both -1, or the same pixel
+        mismatch++;
+      } else if (vf >= 0) {
+        // recompute the fp32 projection to measure how much of the bound is used
+        const float* P = a.pose32[p];
+        const float pcx = fmaf(P[0], q.x, fmaf(P[1], q.y, fmaf(P[2], q.z, P[9])));
+        const float pcy = fmaf(P[3], q.x, fmaf(P[4], q.y, fmaf(P[5], q.z, P[10])));
+        const float pcz = fmaf(P[6], q.x, fmaf(P[7], q.y, fmaf(P[8], q.z, P[11])));
+        const float n2 = fmaf(pcx, pcx, fmaf(pcy, pcy, pcz * pcz));
+        const float nrm = n2 * rsqrtf(n2);
+        const float delta = (5.25f * F32_U) * (a_p + P[12]);
+        float u, v, Eu, Ev;
+        if (project_fast<MODEL>(a.fast, pcx, pcy, pcz, nrm, delta, u, v, Eu, Ev)) {
+          const float ru = static_cast<float>(fabs(static_cast<double>(u) - ue)) / Eu;
+          const float rv = static_cast<float>(fabs(static_cast<double>(v) - ve)) / Ev;
+          max_ratio = fmaxf(max_ratio, fmaxf(ru, rv));
+        }
+      }
+    }
+  }
+  atomicAdd(a.dbg + 0, total);
+  atomicAdd(a.dbg + 1, uncertain);
+  atomicAdd(a.dbg + 2, mismatch);
+  atomicMax(reinterpret_cast<unsigned int*>(a.dbg + 3), __float_as_uint(max_ratio));  // non-negative floats order like uints
 }
 
 // image -> image-bin LUT pass (:43,:46), once per context

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "mem_pool.hpp"
 #include "nid_context.cuh"
 
 namespace vlcal {
@@ -174,11 +175,14 @@ static CullProjectKernel pick_cull_kernel(int model, bool f32) {
   }
 }
 
-struct DevBuf {
+struct DevBuf {  // pooled scratch; returned to the pool after the culling pass has synchronised its stream
   void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
+  int device = 0;
+  cudaError_t alloc(int dev, size_t bytes) {
+    device = dev;
+    return MemPool::instance().device_alloc(dev, bytes, &p);
   }
+  ~DevBuf() { MemPool::instance().device_free(device, p); }
 };
 
 int view_cull_device(
@@ -202,11 +206,11 @@ int view_cull_device(
   const int num_blocks = static_cast<int>((n + CULL_THREADS - 1) / CULL_THREADS);
   const size_t npix = static_cast<size_t>(width) * height;
   DevBuf zbuf, pix, dist, counts, total, idx;
-  VL_CUDA(cudaMalloc(&zbuf.p, sizeof(unsigned int) * npix));
-  VL_CUDA(cudaMalloc(&pix.p, sizeof(int) * n));
-  VL_CUDA(cudaMalloc(&dist.p, sizeof(double) * n));
-  VL_CUDA(cudaMalloc(&counts.p, sizeof(int) * num_blocks));
-  VL_CUDA(cudaMalloc(&total.p, sizeof(long long)));
+  VL_CUDA(zbuf.alloc(cloud.device, sizeof(unsigned int) * npix));
+  VL_CUDA(pix.alloc(cloud.device, sizeof(int) * n));
+  VL_CUDA(dist.alloc(cloud.device, sizeof(double) * n));
+  VL_CUDA(counts.alloc(cloud.device, sizeof(int) * num_blocks));
+  VL_CUDA(total.alloc(cloud.device, sizeof(long long)));
   // :40 dist_map filled with cv::Scalar(DBL_MAX) -> saturates to +inf in CV_32F
   fill_u32_kernel<<<static_cast<unsigned int>((npix + 255) / 256), 256, 0, stream>>>(static_cast<unsigned int*>(zbuf.p), npix, 0x7f800000u);
   VL_CUDA(cudaGetLastError());
@@ -243,9 +247,9 @@ int view_cull_device(
     culled->device = cloud.device;
     culled->f32 = cloud.f32;
     culled->n = kept;
-    if (kept > 0) VL_CUDA(cudaMalloc(&culled->d_points, static_cast<size_t>(kept) * culled->bytes_per_point()));
+    if (kept > 0) VL_CUDA(MemPool::instance().device_alloc(cloud.device, static_cast<size_t>(kept) * culled->bytes_per_point(), &culled->d_points));
   }
-  if (indices_host_out && kept > 0) VL_CUDA(cudaMalloc(&idx.p, sizeof(int) * kept));
+  if (indices_host_out && kept > 0) VL_CUDA(idx.alloc(cloud.device, sizeof(int) * kept));
   if (kept > 0 && (culled_out || indices_host_out)) {
     if (cloud.f32) {
       cull_scatter_kernel<true><<<num_blocks, CULL_THREADS, 0, stream>>>(a, static_cast<int*>(counts.p), static_cast<int*>(idx.p), culled ? culled->d_points : nullptr);

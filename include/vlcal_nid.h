@@ -143,6 +143,16 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
 /* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck), 1 = exact fp64 only */
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
 
+/* device / pinned buffers of destroyed contexts are cached for reuse (contexts are rebuilt every outer iteration);
+ * this releases the cache back to the CUDA driver */
+int vlcal_nid_trim_memory(void);
+/* 1 if evaluations of this context run the fp32-filter kernel (camera model / FoV / float32-representable cloud) */
+int vlcal_nid_filter_enabled(const vlcal_nid_ctx* ctx);
+/* test hook: runs the fp32 filter AND the exact path on every (point, pose) and reports counts[0] = point-poses,
+ * counts[1] = verdicts the filter deferred to the exact path, counts[2] = filter verdicts it kept that disagree with the
+ * exact path (MUST be 0), *max_bound_ratio = max |uv_fp32 - uv_exact| / error-bound over kept in-image verdicts (< 1). */
+int vlcal_nid_debug_filter_check(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, uint64_t counts[3], double* max_bound_ratio);
+
 /* ---- view culling: ViewCulling::cull (src/vlcal/calib/view_culling.cpp:21-92) ------------
  * GPU z-buffer hidden-point removal at pose T.  indices_out: capacity n_points int32, receives the kept
  * original indices in ascending order; *n_kept their count.  max_fov_rad < 0 -> estimate_camera_fov. */

@@ -9,6 +9,9 @@ import numpy as np
 import pytest
 
 import util
+from direct_visual_lidar_calibration_b200 import synthetic as _S
+
+util.S = _S
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -270,3 +273,80 @@ def test_full_size_properties_c2(gpu):
     assert 0 < len(kept) <= hist[0].sum()
     sub = V.CostCalculatorNID(cam, V.VisualLiDARData(image, xyzw[kept], inten[kept])).calculate_batch(Ts[:1], return_hist=True)[1]
     assert sub[0].sum() == len(kept)  # every culled-in point is an inlier of the cost at that pose
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32 filter + exact recheck (default kernel for pinhole-type cameras on float32-representable clouds)
+# ---------------------------------------------------------------------------------------------------------------
+
+FILTER_MODELS = ["plumb_bob", "rational_polynomial"]
+
+
+def _adversarial_problem(model, n, seed):
+    """Clouds that stress the filter's error bound: far points, points skimming the FoV cone and the image border,
+    tiny depths, large lever arms."""
+    rng = np.random.default_rng(seed)
+    pr = util.random_problem(model, n=n, seed=seed)
+    pts = pr["points"][:, :3].copy()
+    k = n // 4
+    pts[:k] *= rng.uniform(5.0, 40.0, (k, 1))  # far (up to ~1 km): |p| large vs depth
+    pts[k : 2 * k] = util.S.lidar_directions("frustum", k, rng) * rng.uniform(0.05, 0.5, (k, 1))  # very close to the sensor
+    pr["points"][:, :3] = pts.astype(np.float32).astype(np.float64)
+    return pr
+
+
+@pytest.mark.parametrize("model", FILTER_MODELS)
+def test_filter_kernel_is_bit_identical_to_exact_kernel(gpu, oracle, model):
+    pr = _adversarial_problem(model, 200000, seed=41)
+    Ts = util.random_poses(pr["T"], 16, seed=9, rot_deg=5.0, trans=0.5)
+    cost = _cost(gpu, pr)
+    assert cost.filter_enabled
+    nid_f, hist_f = cost.calculate_batch(Ts, return_hist=True)
+    cost.set_kernel_variant(1)  # exact fp64 kernel
+    nid_e, hist_e = cost.calculate_batch(Ts, return_hist=True)
+    assert int(np.abs(hist_f - hist_e).sum()) == 0 and hist_f.sum() > 100000
+    assert np.array_equal(nid_f, nid_e, equal_nan=True)
+    ref_nid, ref_hist = _oracle_eval(oracle, pr, Ts[:3])
+    assert np.array_equal(hist_f[:3], ref_hist)
+    _assert_close_nid(nid_f[:3], ref_nid)
+
+
+@pytest.mark.parametrize("model", FILTER_MODELS)
+def test_filter_error_bound_is_sound(gpu, model):
+    """Every verdict the filter keeps must equal the exact verdict; the measured fp32 error must stay inside the bound."""
+    total_pp = 0
+    for seed, rot, trans in [(51, 3.0, 0.3), (52, 20.0, 2.0), (53, 0.2, 0.01)]:
+        pr = _adversarial_problem(model, 400000, seed=seed)
+        Ts = util.random_poses(pr["T"], 24, seed=seed, rot_deg=rot, trans=trans)
+        cost = _cost(gpu, pr)
+        n_pp, deferred, mismatches, ratio = cost.debug_filter_check(Ts)
+        assert n_pp == 400000 * 24
+        assert mismatches == 0
+        assert ratio < 0.5, ratio  # observed error uses less than half of the (already x2) bound
+        assert deferred / n_pp < 0.15
+        total_pp += n_pp
+    assert total_pp > 2e7
+
+
+def test_filter_on_c2_like_geometry_defers_few_points(gpu):
+    from direct_visual_lidar_calibration_b200 import synthetic as S
+
+    bag = S.make_bag("pinhole_1920x1080", "os1_64", 300000, config_index=1)
+    cam = gpu.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    cost = gpu.CostCalculatorNID(cam, gpu.VisualLiDARData(bag["image"], bag["points"], bag["intensities"]))
+    Ts = util.random_poses(bag["T_gt"], 8, seed=1, rot_deg=0.5, trans=0.02)
+    n_pp, deferred, mismatches, ratio = cost.debug_filter_check(Ts)
+    assert mismatches == 0 and ratio < 0.5
+    assert deferred / n_pp < 0.05, deferred / n_pp
+
+
+def test_filter_disabled_cases_fall_back_to_the_exact_kernel_not_to_cpu(gpu, oracle):
+    # non-float32 cloud -> double layout -> exact kernel; wide FoV camera -> exact kernel; both still bit-exact
+    pr = util.random_problem("plumb_bob", n=20000, seed=7, f32=False)
+    assert not _cost(gpu, pr).filter_enabled
+    pr = util.random_problem("fisheye", n=20000, seed=7)
+    cost = _cost(gpu, pr)
+    assert not cost.filter_enabled
+    Ts = util.random_poses(pr["T"], 2, seed=1)
+    _, hist = cost.calculate_batch(Ts, return_hist=True)
+    assert np.array_equal(hist, _oracle_eval(oracle, pr, Ts)[1])
