@@ -184,39 +184,65 @@ struct FastCam {
   float cos_fov;  // float(cos(max_fov))
   float fx, fy, cx, cy, xi;
   float d[8];
-  float k_rho_u, k_rho_v;  // pixels per unit rho
-  float k0_u, k0_v;        // pixels
-  float aux0, aux1;        // model specific (see fast_filter.hpp)
+  // error-bound constants (fast_filter.hpp), SAFETY folded in
+  float a1, a2, a3;      // |k1|, |k2|, |k3|  (numerator of the radial factor)
+  float b1, b2, b3;      // |k4|, |k5|, |k6|  (denominator, rational model)
+  float p3, p4;          // 3(|p1|+|p2|), 4(|p1|+|p2|)
+  float sfx, sfy;        // SAFETY * |fx|, SAFETY * |fy|
+  float cu, cv;          // SAFETY * rounding of the intrinsics step, pixels
+  float aux0, aux1;      // model specific
 };
 
 constexpr float F32_U = 5.9604644775390625e-08f;  // 2^-24, unit roundoff of binary32
 
-// returns true when (u, v, Eu, Ev) are valid; false -> the caller must use the exact path
+// fp32 projection + per-point error bounds; returns false if this point must take the exact path regardless
 template <int MODEL>
 __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float pcy, float pcz, float nrm, float delta, float& u, float& v, float& Eu, float& Ev) {
   if constexpr (MODEL == CAM_PLUMB_BOB || MODEL == CAM_RATIONAL_POLYNOMIAL) {
-    // enabled only when cos_fov >= 0.05: a certain FoV pass then implies pcz >= 0.05*|pc| > 0 and r <= Rmax
-    const float inv = __frcp_rn(pcz);
+    // enabled only when cos_fov >= 0.05: a certain FoV pass then implies pcz >= 0.05*|pc| > 0
+    const float inv = __fdividef(1.0f, pcz);  // MUFU.RCP, <= 1 ulp
     const float x = pcx * inv, y = pcy * inv;
     const float x2 = x * x, y2 = y * y, xy = x * y;
     const float r2 = x2 + y2;
-    float rc;
+    // bounds are monotone in r2; r2b >= (true r)^2 because |x_fp32 - x| ~ 1e-6
+    const float r2b = fmaf(r2, 1.001f, 1e-6f);
+    const float num_a = fmaf(r2b, fmaf(r2b, fmaf(r2b, c.a3, c.a2), c.a1), 1.0f);      // >= |numerator|
+    const float qn_a = fmaf(r2b, fmaf(r2b, 3.0f * c.a3, 2.0f * c.a2), c.a1);          // >= |d numerator / d r2|
+    float rc, RC, Q, m_extra = 0.0f;
+    bool ok = true;
     if constexpr (MODEL == CAM_PLUMB_BOB) {
       rc = fmaf(r2, fmaf(r2, fmaf(r2, c.d[4], c.d[1]), c.d[0]), 1.0f);  // 1 + k1 r2 + k2 r4 + k3 r6
+      RC = num_a;
+      Q = qn_a;
     } else {
       const float num = fmaf(r2, fmaf(r2, fmaf(r2, c.d[4], c.d[1]), c.d[0]), 1.0f);
       const float den = fmaf(r2, fmaf(r2, fmaf(r2, c.d[7], c.d[6]), c.d[5]), 1.0f);
-      rc = num * __frcp_rn(den);  // host guarantees den >= aux0 > 0 on r <= Rmax
+      const float den_a = fmaf(r2b, fmaf(r2b, fmaf(r2b, c.b3, c.b2), c.b1), 1.0f);
+      const float qd_a = fmaf(r2b, fmaf(r2b, 3.0f * c.b3, 2.0f * c.b2), c.b1);
+      // lower bound of the true denominator on the segment between the fp32 and the exact normalised point
+      const float den_lb = den - fmaf(qd_a, 2.0f * (r2b - r2), (8.0f * F32_U) * den_a);
+      ok = den_lb > 0.1f;  // far from the reference's 1e-8 guard (rational_polynomial.hpp:33) and from a pole
+      const float dinv = __fdividef(1.0f, den_lb);
+      rc = num * __fdividef(1.0f, den);
+      RC = num_a * dinv;
+      Q = (qn_a + RC * qd_a) * dinv;
+      m_extra = RC * den_a * dinv;
     }
     const float p1 = c.d[2], p2 = c.d[3];
     const float xd = fmaf(x, rc, fmaf(2.0f * p1, xy, p2 * fmaf(2.0f, x2, r2)));
     const float yd = fmaf(y, rc, fmaf(2.0f * p2, xy, p1 * fmaf(2.0f, y2, r2)));
     u = fmaf(c.fx, xd, c.cx);
     v = fmaf(c.fy, yd, c.cy);
+    // |J_distortion| <= L, sum|terms| <= M on the disc of radius sqrt(r2b);  r <= (1 + r2)/2 =: mh
+    const float mh = fmaf(0.5f, r2b, 0.5f);
+    const float L = fmaf(r2b, fmaf(3.0f, Q, c.p4), RC + c.p4);
+    const float M = fmaf(mh, RC + m_extra, c.p3 * r2b);
     const float rho = delta * inv;
-    Eu = fmaf(c.k_rho_u, rho, c.k0_u);
-    Ev = fmaf(c.k_rho_v, rho, c.k0_v);
-    return true;
+    const float exy = fmaf(rho, 1.0f + mh, (4.0f * F32_U) * mh);  // |(x,y)_fp32 - (x,y)| <= rho (1 + r) + 4u r
+    const float e = fmaf(L, exy, (16.0f * F32_U) * M);
+    Eu = fmaf(c.sfx, e, c.cu);
+    Ev = fmaf(c.sfy, e, c.cv);
+    return ok;
   } else {
     return false;
   }

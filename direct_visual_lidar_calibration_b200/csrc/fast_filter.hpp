@@ -6,13 +6,13 @@
 //   delta    = 5u (|x|+|y|+|z| + max|t|)     [1u rounding of R and t, 3u for the three FMAs, 1u slack]
 // Pinhole-type models (plumb_bob, rational_polynomial), enabled when cos(max_fov) >= 0.05:
 //   a point that certainly passes the FoV test has z >= cos(max_fov)|pc| > 0 and r = |(x/z, y/z)| <= Rmax = tan(max_fov)
-//   e_xy = |(x/z)_fp32 - (x/z)_exact| <= rho (1 + Rmax) + 4u Rmax,  rho = delta / z
-//   distortion D(x,y): |J_D| <= L on r <= Rmax with
-//       L = RC + 3 Rmax^2 Q + 8 (|p1|+|p2|) Rmax,   RC >= |r_coeff|, Q >= |d r_coeff / d r^2|
-//   fp32 evaluation of D rounds by at most 16u M,   M = Rmax RC + 3 (|p1|+|p2|) Rmax^2
-//   pixel error  E = f (L e_xy + 16u M) + 4u (size + |c|)  =  k_rho * rho + k0
-// SAFETY multiplies everything (the constants are already worst case; the factor also covers the rounding of the
-// fp32 evaluation of E itself).  The verify kernel (vlcal_nid_debug_filter_check) measures max |uv_fp32-uv_exact|/E.
+//   e_xy = |(x/z)_fp32 - (x/z)_exact| <= rho (1 + r) + 4u r,  rho = delta / z,  r = |(x/z, y/z)|
+//   distortion D(x,y): |J_D| <= L(r) = RC + 3 r^2 Q + 8 (|p1|+|p2|) r,   RC >= |r_coeff|, Q >= |d r_coeff / d r^2|
+//       (polynomials with absolute coefficients, monotone in r^2, evaluated PER POINT in the kernel at r^2 * 1.001 + 1e-6;
+//        a global bound at Rmax = tan(max_fov) would be 5x looser on a distorted wide lens and defer 15 % of the points)
+//   fp32 evaluation of D rounds by at most 16u M(r),   M = r RC + 3 (|p1|+|p2|) r^2
+//   pixel error  E = SAFETY * ( f (L e_xy + 16u M) + 4u (size + |c| + 1) )
+// SAFETY = 2 (the constants are already worst case; the factor also covers the rounding of the fp32 evaluation of E).  The verify kernel (vlcal_nid_debug_filter_check) measures max |uv_fp32-uv_exact|/E.
 #pragma once
 
 #include <algorithm>
@@ -35,53 +35,26 @@ inline FastCam make_fast_cam(const CameraParams& cam, int width, int height, dou
   f.cy = static_cast<float>(cam.intr[3]);
   f.xi = static_cast<float>(cam.intr[4]);
   for (int i = 0; i < 8; i++) f.d[i] = static_cast<float>(cam.dist[i]);
-  auto finite_all = [&]() {
-    for (int i = 0; i < 5; i++)
-      if (!std::isfinite(cam.intr[i])) return false;
-    for (int i = 0; i < 8; i++)
-      if (!std::isfinite(cam.dist[i])) return false;
-    return std::isfinite(max_fov);
-  };
-  if (!finite_all()) return f;
+  for (int i = 0; i < 5; i++)
+    if (!std::isfinite(cam.intr[i])) return f;
+  for (int i = 0; i < 8; i++)
+    if (!std::isfinite(cam.dist[i])) return f;
+  if (!std::isfinite(max_fov)) return f;
+  auto up = [](double v) { return std::nextafter(static_cast<float>(v), INFINITY); };  // round the bound constants up
 
   if (cam.model == CAM_PLUMB_BOB || cam.model == CAM_RATIONAL_POLYNOMIAL) {
-    if (!(cos_fov >= 0.05)) return f;
+    if (!(cos_fov >= 0.05)) return f;  // the pinhole division needs z > 0 for every point that passes the FoV test
     const double* d = cam.dist;
-    const double R = std::tan(max_fov) * 1.001 + 1e-6;
-    const double R2 = R * R, R4 = R2 * R2, R6 = R4 * R2;
-    const double NUM = 1.0 + std::fabs(d[0]) * R2 + std::fabs(d[1]) * R4 + std::fabs(d[4]) * R6;
-    const double QN = std::fabs(d[0]) + 2.0 * std::fabs(d[1]) * R2 + 3.0 * std::fabs(d[4]) * R4;
-    double RC = NUM, Q = QN, M_extra = 0.0;
-    f.aux0 = 1.0f;
-    if (cam.model == CAM_RATIONAL_POLYNOMIAL) {
-      // denominator 1 + k4 r2 + k5 r4 + k6 r6 must stay clear of the reference's 1e-8 guard and of zero
-      double dmin = 1.0;
-      for (int i = 0; i <= 4096; i++) {
-        const double r2 = R2 * i / 4096.0;
-        dmin = std::min(dmin, 1.0 + d[5] * r2 + d[6] * r2 * r2 + d[7] * r2 * r2 * r2);
-      }
-      const double QD = std::fabs(d[5]) + 2.0 * std::fabs(d[6]) * R2 + 3.0 * std::fabs(d[7]) * R4;
-      dmin -= QD * R2 / 4096.0;  // grid spacing slack
-      if (!(dmin >= 0.1)) return f;
-      RC = NUM / dmin;
-      Q = QN / dmin + NUM * QD / (dmin * dmin);
-      const double DEN = 1.0 + std::fabs(d[5]) * R2 + std::fabs(d[6]) * R4 + std::fabs(d[7]) * R6;
-      M_extra = R * NUM * DEN / (dmin * dmin);  // rounding of the denominator polynomial, amplified by the division
-      f.aux0 = static_cast<float>(dmin);
-    }
     const double P = std::fabs(d[2]) + std::fabs(d[3]);
-    const double L = RC + 3.0 * R2 * Q + 8.0 * P * R;
-    const double M = R * RC + 3.0 * P * R2 + M_extra;
-    const double fxa = std::fabs(cam.intr[0]), fya = std::fabs(cam.intr[1]);
-    const double k_rho_u = SAFETY * fxa * L * (1.0 + R);
-    const double k_rho_v = SAFETY * fya * L * (1.0 + R);
-    const double k0_u = SAFETY * (fxa * (4.0 * U * L * R + 16.0 * U * M) + 4.0 * U * (width + std::fabs(cam.intr[2]) + 1.0));
-    const double k0_v = SAFETY * (fya * (4.0 * U * L * R + 16.0 * U * M) + 4.0 * U * (height + std::fabs(cam.intr[3]) + 1.0));
-    if (!(std::isfinite(k_rho_u) && std::isfinite(k_rho_v)) || k0_u > 0.2 || k0_v > 0.2) return f;  // bound too loose to be useful
-    f.k_rho_u = static_cast<float>(k_rho_u * (1.0 + 1e-6));
-    f.k_rho_v = static_cast<float>(k_rho_v * (1.0 + 1e-6));
-    f.k0_u = static_cast<float>(k0_u * (1.0 + 1e-6));
-    f.k0_v = static_cast<float>(k0_v * (1.0 + 1e-6));
+    f.a1 = up(std::fabs(d[0])), f.a2 = up(std::fabs(d[1])), f.a3 = up(std::fabs(d[4]));
+    f.b1 = up(std::fabs(d[5])), f.b2 = up(std::fabs(d[6])), f.b3 = up(std::fabs(d[7]));
+    f.p3 = up(3.0 * P), f.p4 = up(4.0 * P);
+    f.sfx = up(SAFETY * std::fabs(cam.intr[0]));
+    f.sfy = up(SAFETY * std::fabs(cam.intr[1]));
+    // u = fma(fx, xd, cx): one rounding of the result (|u| <= size + 1 wherever the verdict matters), rounding of the
+    // float copies of fx (folded into the 16u M term) and cx
+    f.cu = up(SAFETY * 4.0 * U * (width + std::fabs(cam.intr[2]) + 1.0));
+    f.cv = up(SAFETY * 4.0 * U * (height + std::fabs(cam.intr[3]) + 1.0));
     f.enabled = 1;
   }
   return f;

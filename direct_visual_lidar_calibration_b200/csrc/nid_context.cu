@@ -207,10 +207,12 @@ int upload_image(int device, const uint8_t* image, int width, int height, int ro
 
 using NidKernel = void (*)(const NidArgs);
 
-// kind: 0 = fp32 filter + exact recheck (float4 layout only), 1 = exact fp64, 2 = verify (debug)
+// kind: 0 = fp32 filter + exact recheck (float4 layout only; 4 points/thread), 1 = exact fp64, 2 = verify (debug),
+//       3 = fp32 filter with 2 points/thread (A/B measurement)
 template <int MODEL>
 static NidKernel pick_layout(bool f32, int kind) {
-  if (f32 && kind == 0) return nid_hist_filter_kernel<MODEL, true>;
+  if (f32 && kind == 0) return nid_hist_filter_kernel<MODEL, true, 4>;
+  if (f32 && kind == 3) return nid_hist_filter_kernel<MODEL, true, 2>;
   if (f32 && kind == 2) return nid_filter_verify_kernel<MODEL, true>;
   return f32 ? nid_hist_exact_kernel<MODEL, true> : nid_hist_exact_kernel<MODEL, false>;
 }
@@ -399,8 +401,8 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
   }
   const int nb = ctx->bins * ctx->bins;
   // the fp32 filter needs the float4 layout, a camera/FoV it has bounds for, and 32-bit point indices
-  const bool use_filter = ctx->variant == 0 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
-  NidKernel kernel = pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? 0 : 1);
+  const bool use_filter = ctx->variant != 1 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
+  NidKernel kernel = pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? (ctx->variant == 2 ? 3 : 0) : 1);
   for (int p0 = 0; p0 < n_poses; p0 += ctx->max_poses) {
     const int pc = std::min(ctx->max_poses, n_poses - p0);
     NidArgs a;
@@ -727,7 +729,7 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
 }
 
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 1) return VLCAL_ERR_INVALID_ARGUMENT;
+  if (!ctx || variant < 0 || variant > 2) return VLCAL_ERR_INVALID_ARGUMENT;
   ctx->variant = variant;
   return VLCAL_OK;
 }

@@ -84,18 +84,9 @@ __device__ __forceinline__ int classify_exact(const NidArgs& a, const double* __
 constexpr int VERDICT_REJECT = -1;     // certainly skipped by the reference
 constexpr int VERDICT_UNCERTAIN = -2;  // within the error bound of a decision edge: ask the exact path
 
-// one image coordinate: 0 = certainly outside, 1 = certainly inside with pixel index `ip`, 2 = uncertain
-__device__ __forceinline__ int coord_verdict(float c, float E, int size, int& ip) {
-  if (!(E < 0.25f)) return 2;                // bound useless (or NaN)
-  if (c < -1.0f - E) return 0;               // reference coordinate < -1 -> truncates to <= -1
-  if (c > static_cast<float>(size) + E) return 0;  // reference coordinate > size -> index >= size
-  const float r = rintf(c);
-  if (!(fabsf(c - r) > E)) return 2;         // an integer (truncation edge, image border) lies within the bound; NaN lands here
-  ip = static_cast<int>(c);                  // truncation toward zero, like cast<int>()
-  return (ip >= 0 && ip < size) ? 1 : 0;
-}
-
-// returns pixel index (>= 0), VERDICT_REJECT or VERDICT_UNCERTAIN
+// fp32 classification of one (point, pose), written without data-dependent branches (predicate logic only).
+// P = pose32 row: R (9, row-major), t (3), max|t|.  Returns pixel index (>= 0), VERDICT_REJECT or VERDICT_UNCERTAIN.
+// Decision order mirrors the reference: FoV (:32), then the two truncated coordinates against the image (:37-38).
 template <int MODEL>
 __device__ __forceinline__ int classify_fast(const NidArgs& a, const float* __restrict__ P, float x, float y, float z, float a_p) {
   const float pcx = fmaf(P[0], x, fmaf(P[1], y, fmaf(P[2], z, P[9])));
@@ -107,17 +98,24 @@ __device__ __forceinline__ int classify_fast(const NidArgs& a, const float* __re
   // FoV: sign of g = pcz - cos_fov*|pc| with |g_fp32 - g_exact| <= 2.8 delta + 8.5 u |pc|
   const float g = fmaf(-a.fast.cos_fov, nrm, pcz);
   const float mf = fmaf(3.0f, delta, (12.0f * F32_U) * nrm);
-  if (!(fabsf(g) > mf)) return VERDICT_UNCERTAIN;  // also catches NaN / n2 == 0
-  if (g < 0.0f) return VERDICT_REJECT;
+  const bool fov_unc = !(fabsf(g) > mf);  // also catches NaN / n2 == 0
+  const bool fov_rej = g < 0.0f;
   float u, v, Eu, Ev;
-  if (!project_fast<MODEL>(a.fast, pcx, pcy, pcz, nrm, delta, u, v, Eu, Ev)) return VERDICT_UNCERTAIN;
-  int ix = 0, iy = 0;
-  const int vu = coord_verdict(u, Eu, a.width, ix);
-  if (vu == 0) return VERDICT_REJECT;
-  const int vv = coord_verdict(v, Ev, a.height, iy);
-  if (vv == 0) return VERDICT_REJECT;
-  if (vu == 2 || vv == 2) return VERDICT_UNCERTAIN;
-  return iy * a.width + ix;
+  const bool proj_ok = project_fast<MODEL>(a.fast, pcx, pcy, pcz, nrm, delta, u, v, Eu, Ev);
+  const float wf = static_cast<float>(a.width), hf = static_cast<float>(a.height);
+  const bool bad = !proj_ok || !(Eu < 0.25f) || !(Ev < 0.25f);       // bound useless (or NaN)
+  const bool out = (u < -1.0f - Eu) || (u > wf + Eu) || (v < -1.0f - Ev) || (v > hf + Ev);  // certainly truncates outside
+  // an integer (truncation edge / image border) within the bound of either coordinate; NaN lands here
+  const bool edge = !(fabsf(u - rintf(u)) > Eu) || !(fabsf(v - rintf(v)) > Ev);
+  const int ix = __float2int_rz(u), iy = __float2int_rz(v);          // truncation toward zero, like cast<int>()
+  const bool inside = ix >= 0 && ix < a.width && iy >= 0 && iy < a.height;
+  int verdict = inside ? iy * a.width + ix : VERDICT_REJECT;
+  verdict = edge ? VERDICT_UNCERTAIN : verdict;
+  verdict = out ? VERDICT_REJECT : verdict;
+  verdict = bad ? VERDICT_UNCERTAIN : verdict;
+  verdict = fov_rej ? VERDICT_REJECT : verdict;
+  verdict = fov_unc ? VERDICT_UNCERTAIN : verdict;
+  return verdict;
 }
 
 __device__ __forceinline__ int lidar_bin_of(double intensity, int bins) {
@@ -269,10 +267,13 @@ constexpr int NID_QUEUE = 64;  // per-warp queue of (point, pose) pairs waiting 
 // K1 (default): fp32 filter + exact fp64 recheck.
 // Every (point, pose) is first classified in fp32 together with a rigorous error bound; verdicts that are farther
 // than the bound from every decision edge (FoV cone, integer pixel boundaries, image border) are final.  The rest
-// (~1-3 %) are pushed on a per-warp shared-memory queue and re-decided 32 at a time by the exact double path, so
-// the fp64 pipe runs with full warps instead of diverging inside the hot loop.  The histogram is therefore
-// bit-identical to the all-fp64 kernel (tests/test_gpu_parity.py::test_filter_kernel_*).
-template <int MODEL, bool F32>
+// (~2 %) are pushed on a per-warp shared-memory queue and re-decided 32 at a time by the exact double path, so the
+// fp64 pipe runs with full warps instead of diverging inside the hot loop.  The histogram is therefore bit-identical
+// to the all-fp64 kernel (tests/test_gpu_parity.py::test_filter_kernel_*).
+// Loop structure: each thread keeps NID_KPT points in registers (warp-coalesced 512-byte rows) and sweeps the P poses
+// over them, so the pose constants are fetched once per NID_KPT points and NID_KPT independent chains are in flight.
+// NID_KPT = points held in registers per thread while the poses are swept.
+template <int MODEL, bool F32, int NID_KPT>
 __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __grid_constant__ NidArgs a) {
   extern __shared__ int smem_hist[];
   __shared__ bool s_is_last;
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   const unsigned int lt_mask = (1u << lane) - 1u;
   int* my_hist = smem_hist + (warp % a.copies) * per_copy;
   const float4* __restrict__ pts = static_cast<const float4*>(a.points);
-  int qn = 0;  // queue fill, warp-uniform
+  const unsigned int n = static_cast<unsigned int>(a.n);  // host guarantees n < 2^31 for this kernel
+  int qn = 0;                                             // queue fill, warp-uniform
 
   auto drain32 = [&](int first, int count) {  // entries [first, first+count), count <= 32
     if (lane < count) {
@@ -298,35 +300,58 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
     }
   };
 
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long warp_base = static_cast<long long>(blockIdx.x) * blockDim.x + warp * 32;
-  for (long long base = warp_base; base < a.n; base += stride) {  // trip count is warp-uniform
-    const long long i = base + lane;
-    const bool valid = i < a.n;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) q = __ldg(pts + i);
-    const float a_p = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
-    const int lb_off = lidar_bin_of(q.w, a.bins) * a.bins;
+  constexpr unsigned int TILE = 32 * NID_KPT;
+  const unsigned int warps_total = gridDim.x * (NID_THREADS / 32);
+  const unsigned int warp_global = blockIdx.x * (NID_THREADS / 32) + warp;
+  for (unsigned long long tile = static_cast<unsigned long long>(warp_global) * TILE; tile < n; tile += static_cast<unsigned long long>(warps_total) * TILE) {
+    float px[NID_KPT], py[NID_KPT], pz[NID_KPT], pa[NID_KPT];
+    int lboff[NID_KPT];
+    unsigned int idx[NID_KPT];
+    unsigned int valid_bits = 0;
+#pragma unroll
+    for (int j = 0; j < NID_KPT; j++) {
+      idx[j] = static_cast<unsigned int>(tile) + j * 32 + lane;
+      const bool valid = idx[j] < n;
+      float4 q = make_float4(0.f, 0.f, -1.f, 0.f);
+      if (valid) q = __ldg(pts + idx[j]);
+      valid_bits |= (valid ? 1u : 0u) << j;
+      px[j] = q.x, py[j] = q.y, pz[j] = q.z;
+      pa[j] = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
+      lboff[j] = lidar_bin_of(q.w, a.bins) * a.bins;
+    }
     for (int p = 0; p < a.n_poses; p++) {
-      int verdict = VERDICT_REJECT;
-      if (valid) verdict = classify_fast<MODEL>(a, a.pose32[p], q.x, q.y, q.z, a_p);
-      if (verdict >= 0) {
-        const int ib = __ldg(a.bin_image + verdict);
-        atomicAdd(&my_hist[p * a.nb + ib + lb_off], 1);  // :49 hist(image_bin, lidar_bin)++
-      }
-      const unsigned int m = __ballot_sync(0xffffffffu, verdict == VERDICT_UNCERTAIN);
-      if (m) {
-        if (verdict == VERDICT_UNCERTAIN) {
-          const int pos = qn + __popc(m & lt_mask);
-          q_idx[warp][pos] = static_cast<unsigned int>(i);
-          q_pose[warp][pos] = static_cast<unsigned char>(p);
+      const float* __restrict__ P = a.pose32[p];
+      int* hist_p = my_hist + p * a.nb;
+      unsigned int unc_bits = 0;
+#pragma unroll
+      for (int j = 0; j < NID_KPT; j++) {
+        int verdict = classify_fast<MODEL>(a, P, px[j], py[j], pz[j], pa[j]);
+        verdict = ((valid_bits >> j) & 1u) ? verdict : VERDICT_REJECT;
+        if (verdict >= 0) {
+          const int ib = __ldg(a.bin_image + verdict);
+          atomicAdd(&hist_p[ib + lboff[j]], 1);  // :49 hist(image_bin, lidar_bin)++
         }
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-          drain32(qn - 32, 32);
-          qn -= 32;
-          __syncwarp();
+        unc_bits |= (verdict == VERDICT_UNCERTAIN ? 1u : 0u) << j;
+      }
+      if (__any_sync(0xffffffffu, unc_bits != 0)) {  // some lane deferred a point: queue it for the exact path
+#pragma unroll
+        for (int j = 0; j < NID_KPT; j++) {
+          const bool mine = (unc_bits >> j) & 1u;
+          const unsigned int m = __ballot_sync(0xffffffffu, mine);
+          if (m) {
+            if (mine) {
+              const int pos = qn + __popc(m & lt_mask);
+              q_idx[warp][pos] = idx[j];
+              q_pose[warp][pos] = static_cast<unsigned char>(p);
+            }
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+              drain32(qn - 32, 32);
+              qn -= 32;
+              __syncwarp();
+            }
+          }
         }
       }
     }

@@ -140,7 +140,8 @@ int vlcal_nid_max_poses_per_launch(void);
 int vlcal_nid_set_profiling(vlcal_nid_ctx* ctx, int enable);
 int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* kernel_ms_total, int64_t* poses_total);
 int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
-/* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck), 1 = exact fp64 only */
+/* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck, 4 points/thread),
+ * 1 = exact fp64 only, 2 = fp32 filter with 2 points/thread */
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
 
 /* device / pinned buffers of destroyed contexts are cached for reuse (contexts are rebuilt every outer iteration);
