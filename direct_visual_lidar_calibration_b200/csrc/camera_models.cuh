@@ -190,6 +190,8 @@ struct FastCam {
   float p3, p4;          // 3(|p1|+|p2|), 4(|p1|+|p2|)
   float sfx, sfy;        // SAFETY * |fx|, SAFETY * |fy|
   float cu, cv;          // SAFETY * rounding of the intrinsics step, pixels
+  float l0, l1, l2, l3;      // plumb_bob: L(r2) = sum l_i r2^i  >= |J_distortion|
+  float m0, m1, m2, m3, m4;  // plumb_bob: 16u * M(r2), M = sum m_i r2^i >= sum |terms of the distortion polynomial|
   float aux0, aux1;      // model specific
 };
 
@@ -235,11 +237,17 @@ __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float 
     v = fmaf(c.fy, yd, c.cy);
     // |J_distortion| <= L, sum|terms| <= M on the disc of radius sqrt(r2b);  r <= (1 + r2)/2 =: mh
     const float mh = fmaf(0.5f, r2b, 0.5f);
-    const float L = fmaf(r2b, fmaf(3.0f, Q, c.p4), RC + c.p4);
-    const float M = fmaf(mh, RC + m_extra, c.p3 * r2b);
+    float L, M16;
+    if constexpr (MODEL == CAM_PLUMB_BOB) {  // same L and M, pre-expanded into polynomials of r2b on the host
+      L = fmaf(r2b, fmaf(r2b, fmaf(r2b, c.l3, c.l2), c.l1), c.l0);
+      M16 = fmaf(r2b, fmaf(r2b, fmaf(r2b, fmaf(r2b, c.m4, c.m3), c.m2), c.m1), c.m0);
+    } else {
+      L = fmaf(r2b, fmaf(3.0f, Q, c.p4), RC + c.p4);
+      M16 = (16.0f * F32_U) * fmaf(mh, RC + m_extra, c.p3 * r2b);
+    }
     const float rho = delta * inv;
     const float exy = fmaf(rho, 1.0f + mh, (4.0f * F32_U) * mh);  // |(x,y)_fp32 - (x,y)| <= rho (1 + r) + 4u r
-    const float e = fmaf(L, exy, (16.0f * F32_U) * M);
+    const float e = fmaf(L, exy, M16);
     Eu = fmaf(c.sfx, e, c.cu);
     Ev = fmaf(c.sfy, e, c.cv);
     return ok;

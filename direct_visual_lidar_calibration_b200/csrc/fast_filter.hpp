@@ -55,6 +55,12 @@ inline FastCam make_fast_cam(const CameraParams& cam, int width, int height, dou
     // float copies of fx (folded into the 16u M term) and cx
     f.cu = up(SAFETY * 4.0 * U * (width + std::fabs(cam.intr[2]) + 1.0));
     f.cv = up(SAFETY * 4.0 * U * (height + std::fabs(cam.intr[3]) + 1.0));
+    {  // plumb_bob: L = RC + r2 (3Q + 4P) + 4P and M = (1+r2)/2 RC + 3P r2 expanded in powers of r2 (see project_fast)
+      const double a1 = f.a1, a2 = f.a2, a3 = f.a3, p3 = f.p3, p4 = f.p4;
+      f.l0 = up(1.0 + p4), f.l1 = up(4.0 * a1 + p4), f.l2 = up(7.0 * a2), f.l3 = up(10.0 * a3);
+      const double s = 16.0 * U;
+      f.m0 = up(s * 0.5), f.m1 = up(s * (0.5 + 0.5 * a1 + p3)), f.m2 = up(s * 0.5 * (a1 + a2)), f.m3 = up(s * 0.5 * (a2 + a3)), f.m4 = up(s * 0.5 * a3);
+    }
     f.enabled = 1;
   }
   return f;

@@ -131,77 +131,64 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// deterministic block-wide sum (fixed tree), result valid in thread 0; `scratch` holds >= 32 doubles
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  double s = 0.0;
-  if (threadIdx.x == 0) {
-    for (int w = 0; w < (blockDim.x >> 5); w++) s += scratch[w];
-  }
-  return s;
-}
-
-// entropies + NID for every pose of the launch; run by the last block only (:54-64)
+// entropies + NID for every pose of the launch; run by the last block only (:54-64).
+// One warp per pose (the serial tail of the launch is one pose deep, not P): lane l owns joint bins l, l+32, ...;
+// marginals are the row / column sums of the joint (the reference increments all three together, :49-51).
+// Summation order is a fixed function of (bins, lane), independent of P and of the pose's slot.
 static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
-  __shared__ double scratch[32];
-  __shared__ int s_sum;
-  int* h_image = smem_i;            // [bins]
-  int* h_points = smem_i + a.bins;  // [bins]
-  for (int p = 0; p < a.n_poses; p++) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  int* h_image = smem_i + warp * 2 * a.bins;  // [bins] per warp
+  int* h_points = h_image + a.bins;           // [bins]
+  for (int p = warp; p < a.n_poses; p += n_warps) {
     int* g = a.ghist + static_cast<size_t>(p) * a.nb;
-    for (int i = threadIdx.x; i < 2 * a.bins; i += blockDim.x) smem_i[i] = 0;
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
-    // marginals = row / column sums of the joint (the reference increments all three together, :49-51)
-    for (int k = threadIdx.x; k < a.nb; k += blockDim.x) {
+    for (int i = lane; i < 2 * a.bins; i += 32) h_image[i] = 0;
+    __syncwarp();
+    int part = 0;
+    for (int k = lane; k < a.nb; k += 32) {
       const int c = __ldcg(g + k);
       if (c) {
         atomicAdd(&h_image[k % a.bins], c);
         atomicAdd(&h_points[k / a.bins], c);
+        part += c;
       }
     }
-    __syncthreads();
-    if (threadIdx.x < 32) {  // :54 sum = hist_image.sum()
-      int s = 0;
-      for (int i = threadIdx.x; i < a.bins; i += 32) s += h_image[i];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if (threadIdx.x == 0) s_sum = s;
-    }
-    __syncthreads();
-    const double sum = static_cast<double>(s_sum);
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncwarp();
+    const double sum = static_cast<double>(part);  // :54 sum = hist_image.sum()
     // :59-61  H = -sum p*log(p + 1e-6)
     double t_rs = 0.0, t_r = 0.0, t_s = 0.0;
-    for (int k = threadIdx.x; k < a.nb; k += blockDim.x) {
+    for (int k = lane; k < a.nb; k += 32) {
       const double pr = static_cast<double>(__ldcg(g + k)) / sum;
       t_rs += pr * log(pr + 1e-6);
     }
-    for (int k = threadIdx.x; k < a.bins; k += blockDim.x) {
+    for (int k = lane; k < a.bins; k += 32) {
       const double pi = static_cast<double>(h_image[k]) / sum;
       const double pp = static_cast<double>(h_points[k]) / sum;
       t_r += pi * log(pi + 1e-6);
       t_s += pp * log(pp + 1e-6);
     }
-    const double Hrs = -block_sum(t_rs, scratch);
-    const double Hr = -block_sum(t_r, scratch);
-    const double Hs = -block_sum(t_s, scratch);
-    if (threadIdx.x == 0) {
-      const double MI = Hr + Hs - Hrs;    // :63
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t_rs += __shfl_xor_sync(0xffffffffu, t_rs, o);
+      t_r += __shfl_xor_sync(0xffffffffu, t_r, o);
+      t_s += __shfl_xor_sync(0xffffffffu, t_s, o);
+    }
+    if (lane == 0) {
+      const double Hrs = -t_rs, Hr = -t_r, Hs = -t_s;
+      const double MI = Hr + Hs - Hrs;      // :63
       const double nid = (Hrs - MI) / Hrs;  // :64 (NaN when there are no inliers, as in the reference)
       a.nid_out[p] = nid;
       if (a.nid_host) a.nid_host[p] = nid;
     }
     // export + self-clean
-    for (int k = threadIdx.x; k < a.nb; k += blockDim.x) {
+    for (int k = lane; k < a.nb; k += 32) {
       if (a.hist_out) a.hist_out[static_cast<size_t>(p) * a.nb + k] = __ldcg(g + k);
       g[k] = 0;
     }
-    __syncthreads();
+    __syncwarp();
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     *a.counter = 0u;
     if (a.done_flag) {  // publish to the polling host thread: results first, then the sequence number
@@ -319,37 +306,52 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
       pa[j] = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
       lboff[j] = lidar_bin_of(q.w, a.bins) * a.bins;
     }
-    for (int p = 0; p < a.n_poses; p++) {
-      const float* __restrict__ P = a.pose32[p];
-      int* hist_p = my_hist + p * a.nb;
-      unsigned int unc_bits = 0;
-#pragma unroll
-      for (int j = 0; j < NID_KPT; j++) {
-        int verdict = classify_fast<MODEL>(a, P, px[j], py[j], pz[j], pa[j]);
-        verdict = ((valid_bits >> j) & 1u) ? verdict : VERDICT_REJECT;
-        if (verdict >= 0) {
-          const int ib = __ldg(a.bin_image + verdict);
-          atomicAdd(&hist_p[ib + lboff[j]], 1);  // :49 hist(image_bin, lidar_bin)++
-        }
-        unc_bits |= (verdict == VERDICT_UNCERTAIN ? 1u : 0u) << j;
-      }
-      if (__any_sync(0xffffffffu, unc_bits != 0)) {  // some lane deferred a point: queue it for the exact path
+    // software pipeline over the poses: the image-bin gathers of pose p are issued unconditionally (clamped address),
+    // stay in flight while pose p+1 is classified, and are consumed by the histogram atomics one iteration later
+    int pend_bin[NID_KPT];
+    unsigned int pend_ok = 0;
+    int* pend_hist = my_hist;
+    for (int p = 0; p <= a.n_poses; p++) {
+      int verdict[NID_KPT];
+      unsigned int unc_bits = 0, ok_bits = 0;
+      if (p < a.n_poses) {
+        const float* __restrict__ P = a.pose32[p];
 #pragma unroll
         for (int j = 0; j < NID_KPT; j++) {
-          const bool mine = (unc_bits >> j) & 1u;
-          const unsigned int m = __ballot_sync(0xffffffffu, mine);
-          if (m) {
-            if (mine) {
-              const int pos = qn + __popc(m & lt_mask);
-              q_idx[warp][pos] = idx[j];
-              q_pose[warp][pos] = static_cast<unsigned char>(p);
-            }
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-              drain32(qn - 32, 32);
-              qn -= 32;
+          int vd = classify_fast<MODEL>(a, P, px[j], py[j], pz[j], pa[j]);
+          vd = ((valid_bits >> j) & 1u) ? vd : VERDICT_REJECT;
+          verdict[j] = vd;
+          ok_bits |= (vd >= 0 ? 1u : 0u) << j;
+          unc_bits |= (vd == VERDICT_UNCERTAIN ? 1u : 0u) << j;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NID_KPT; j++) {  // consume the previous pose's gathers
+        if ((pend_ok >> j) & 1u) atomicAdd(&pend_hist[pend_bin[j] + lboff[j]], 1);  // :49 hist(image_bin, lidar_bin)++
+      }
+      pend_ok = ok_bits;
+      if (p < a.n_poses) {
+        pend_hist = my_hist + p * a.nb;
+#pragma unroll
+        for (int j = 0; j < NID_KPT; j++) pend_bin[j] = __ldg(a.bin_image + max(verdict[j], 0));
+        if (__any_sync(0xffffffffu, unc_bits != 0)) {  // some lane deferred a point: queue it for the exact path
+#pragma unroll
+          for (int j = 0; j < NID_KPT; j++) {
+            const bool mine = (unc_bits >> j) & 1u;
+            const unsigned int m = __ballot_sync(0xffffffffu, mine);
+            if (m) {
+              if (mine) {
+                const int pos = qn + __popc(m & lt_mask);
+                q_idx[warp][pos] = idx[j];
+                q_pose[warp][pos] = static_cast<unsigned char>(p);
+              }
+              qn += __popc(m);
               __syncwarp();
+              if (qn >= 32) {
+                drain32(qn - 32, 32);
+                qn -= 32;
+                __syncwarp();
+              }
             }
           }
         }
