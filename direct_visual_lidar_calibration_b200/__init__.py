@@ -6,6 +6,7 @@ this package is the thin host-side mirror of the reference's interface for that 
   create_camera                 <- camera::create_camera             (src/camera/create_camera.cpp:34-50)
   VisualLiDARData               <- vlcal::VisualLiDARData            (include/vlcal/common/visual_lidar_data.hpp)
   NIDCostParams, CostCalculatorNID <- vlcal::CostCalculatorNID       (include/vlcal/calib/cost_calculator_nid.hpp)
+  NIDCost                       <- vlcal::NIDCost (value only)        (include/vlcal/costs/nid_cost.hpp)
   ViewCullingParams, ViewCulling   <- vlcal::ViewCulling             (include/vlcal/calib/view_culling.hpp)
   NelderMead                    <- dfo::NelderMead<N>                (include/dfo/nelder_mead.hpp)
   VisualCameraCalibrationParams, VisualCameraCalibration <- vlcal::VisualCameraCalibration
@@ -15,7 +16,7 @@ There is no CPU fallback: without the built library or without a CUDA device eve
 """
 from ._lib import VlcalError, build_library, device_count, library_path, load_library
 from .camera import GenericCamera, create_camera
-from .cost import CostCalculatorNID, NIDCostParams, VisualLiDARData
+from .cost import CostCalculatorNID, NIDCost, NIDCostParams, VisualLiDARData
 from .culling import ViewCulling, ViewCullingParams
 from .nelder_mead import NelderMead, NelderMeadParams
 from .calibration import RegistrationType, VisualCameraCalibration, VisualCameraCalibrationParams, estimate_camera_fov, se3_expmap
@@ -23,7 +24,7 @@ from .calibration import RegistrationType, VisualCameraCalibration, VisualCamera
 __all__ = [
     "VlcalError", "build_library", "device_count", "library_path", "load_library",
     "GenericCamera", "create_camera",
-    "CostCalculatorNID", "NIDCostParams", "VisualLiDARData",
+    "CostCalculatorNID", "NIDCost", "NIDCostParams", "VisualLiDARData",
     "ViewCulling", "ViewCullingParams",
     "NelderMead", "NelderMeadParams",
     "RegistrationType", "VisualCameraCalibration", "VisualCameraCalibrationParams", "estimate_camera_fov", "se3_expmap",

@@ -122,6 +122,7 @@ def load_library():
     L.vlcal_nid_get_profile.argtypes = [vp, C.POINTER(C.c_int64), dp, C.POINTER(C.c_int64)]
     L.vlcal_nid_reset_profile.argtypes = [vp]
     L.vlcal_nid_set_kernel_variant.argtypes = [vp, C.c_int]
+    L.vlcal_nid_debug_timeline.argtypes = [vp, dp, C.c_int, dp]
     L.vlcal_nid_filter_enabled.argtypes = [vp]
     L.vlcal_nid_debug_filter_check.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_uint64), dp]
     L.vlcal_view_cull.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int64, dp, vp, C.POINTER(C.c_int64)]

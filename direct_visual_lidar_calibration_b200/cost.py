@@ -96,6 +96,13 @@ class CostCalculatorNID:
     def points_are_f32(self) -> bool:
         return bool(self._L.vlcal_nid_points_are_f32(self._ctx))
 
+    def debug_timeline(self, Ts):
+        Tc = T_to_colmajor(Ts)
+        out = np.zeros(8)
+        _lib.check(self._L.vlcal_nid_debug_timeline(self._ctx, _dp(Tc), Tc.shape[0], _dp(out)))
+        keys = ["main_done", "merged", "ticket", "finalize_done", "published", "host_launch_call", "host_total"]
+        return dict(zip(keys, out[:7]))
+
     @property
     def filter_enabled(self) -> bool:
         return bool(self._L.vlcal_nid_filter_enabled(self._ctx))
@@ -125,6 +132,54 @@ class CostCalculatorNID:
         launches, poses, ms = C.c_int64(), C.c_int64(), C.c_double()
         _lib.check(self._L.vlcal_nid_get_profile(self._ctx, C.byref(launches), C.byref(ms), C.byref(poses)))
         return {"kernel_launches": launches.value, "kernel_ms_total": ms.value, "poses_total": poses.value}
+
+    def close(self):
+        if self._ctx:
+            self._L.vlcal_nid_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NIDCost:
+    """vlcal::NIDCost(proj, normalized_image, points, bins) -- value of operator()<double> (nid_cost.hpp:23-107), the
+    B-spline soft-histogram NID of the BFGS branch.  `image` is the uint8 image; the reference's CV_64F image is
+    image * (1/255.0) (visual_camera_calibration.cpp:203-204), which is what the kernel's bin plane is built from.
+
+    evaluate(T_params) with T_params = (P,7) [qx qy qz qw tx ty tz] (Sophus::SE3d storage) -> (ok[P], nid[P])."""
+
+    def __init__(self, proj: GenericCamera, data: VisualLiDARData, bins: int = 16, device: int = -1):
+        L = _lib.load_library()
+        self._L = L
+        self._ctx = C.c_void_p()
+        self.bins = bins
+        self.data = data
+        h, w = data.image.shape
+        _lib.check(
+            L.vlcal_nid_create(
+                C.byref(self._ctx), device, _lib.MODE_BSPLINE, proj.model_id, _dp(proj.intrinsics), proj.intrinsics.size, _dp(proj.distortion), proj.distortion.size,
+                data.image.ctypes.data, w, h, data.image.strides[0], data.points.ctypes.data, data.intensities.ctypes.data, data.size(), bins, 0.0,
+            )
+        )
+
+    def evaluate(self, T_params, return_hist: bool = False):
+        tp = np.ascontiguousarray(np.asarray(T_params, dtype=np.float64)).reshape(-1, 7)
+        P = tp.shape[0]
+        nid = np.empty(P)
+        ok = np.empty(P, dtype=np.int32)
+        hist = np.empty((P, self.bins * self.bins)) if return_hist else None
+        _lib.check(self._L.vlcal_nid_evaluate_bspline(self._ctx, _dp(tp), P, _dp(nid), ok.ctypes.data, hist.ctypes.data if return_hist else None))
+        if return_hist:
+            return ok.astype(bool), nid, np.swapaxes(hist.reshape(P, self.bins, self.bins), 1, 2).copy()
+        return ok.astype(bool), nid
+
+    def __call__(self, T_params7):
+        ok, nid = self.evaluate(np.asarray(T_params7).reshape(1, 7))
+        return bool(ok[0]), float(nid[0])
 
     def close(self):
         if self._ctx:

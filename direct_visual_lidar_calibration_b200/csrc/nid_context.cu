@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <map>
 
 #include "fast_filter.hpp"
@@ -281,6 +282,7 @@ vlcal_nid_ctx::~vlcal_nid_ctx() {
   pool.device_free(device, d_hist_out);
   pool.pinned_free(h_nid);
   pool.pinned_free(h_flag);
+  pool.pinned_free(h_timeline);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -320,10 +322,17 @@ int nid_ctx_create(
   // image -> image-bin plane: image_bin = max(0, min(bins-1, int(u8/255.0 * bins)))  (cost_calculator_nid.cpp:43,46)
   uint8_t lut[256];
   for (int v = 0; v < 256; v++) {
-    const double pixel = v / 255.0;
-    int b = cast_int_x86(pixel * bins);
-    b = b < bins - 1 ? b : bins - 1;
-    b = b > 0 ? b : 0;
+    int b;
+    if (mode == VLCAL_NID_MODE_HISTOGRAM) {
+      const double pixel = v / 255.0;  // image.at<uint8_t>() / 255.0  (cost_calculator_nid.cpp:43)
+      b = cast_int_x86(pixel * bins);
+      b = b < bins - 1 ? b : bins - 1;
+      b = b > 0 ? b : 0;
+    } else {
+      const double pix = v * (1.0 / 255.0);  // image.convertTo(CV_64FC1, 1.0 / 255.0)  (visual_camera_calibration.cpp:203-204)
+      b = cast_int_x86(pix * bins);          // std::min<int>(pix * bins, bins - 1)  (nid_cost.hpp:79)
+      b = b < bins - 1 ? b : bins - 1;
+    }
     lut[v] = static_cast<uint8_t>(b);
   }
   uint8_t* d_lut = nullptr;
@@ -424,6 +433,7 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
     }
     fill_pose32(a, pc);
     a.fast = ctx->fast;
+    a.timeline = ctx->h_timeline;
     a.ghist = ctx->d_ghist;
     a.counter = ctx->d_counter;
     a.nid_out = ctx->d_nid + p0;
@@ -734,6 +744,38 @@ int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant) {
   return VLCAL_OK;
 }
 
+int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double out_us[8]) {
+  if (!ctx || !T_camera_lidar || n_poses <= 0 || n_poses > NID_MAX_POSES || !out_us) {
+    set_last_error("invalid arguments (one launch: n_poses <= 8)");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  VL_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->h_timeline) VL_CUDA(MemPool::instance().pinned_alloc(16 * sizeof(unsigned long long), reinterpret_cast<void**>(&ctx->h_timeline)));
+  for (int i = 0; i < 16; i++) ctx->h_timeline[i] = 0ull;
+  ctx->h_timeline[0] = ~0ull;
+  std::vector<double> nid(n_poses);
+  timespec ts0, ts1, ts2;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
+  int rc = nid_evaluate_async(ctx, T_camera_lidar, n_poses, false);
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
+  if (rc == VLCAL_OK) rc = nid_wait(ctx, nid.data(), nullptr);
+  clock_gettime(CLOCK_MONOTONIC, &ts2);
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  const unsigned long long* t = ctx->h_timeline;
+  const double base = static_cast<double>(t[0]);
+  out_us[0] = (static_cast<double>(t[1]) - base) * 1e-3;  // last block: main loop done (since first block start)
+  out_us[1] = (static_cast<double>(t[2]) - base) * 1e-3;  // merged + fenced
+  out_us[2] = (static_cast<double>(t[3]) - base) * 1e-3;  // ticket known
+  out_us[3] = (static_cast<double>(t[4]) - base) * 1e-3;  // finalize math done
+  out_us[4] = (static_cast<double>(t[5]) - base) * 1e-3;  // published
+  out_us[5] = ((ts1.tv_sec - ts0.tv_sec) * 1e9 + (ts1.tv_nsec - ts0.tv_nsec)) * 1e-3;  // host: launch call
+  out_us[6] = ((ts2.tv_sec - ts0.tv_sec) * 1e9 + (ts2.tv_nsec - ts0.tv_nsec)) * 1e-3;  // host: launch -> results visible
+  out_us[7] = 0.0;
+  MemPool::instance().pinned_free(ctx->h_timeline);
+  ctx->h_timeline = nullptr;
+  return rc;
+}
+
 int vlcal_nid_trim_memory(void) {
   MemPool::instance().trim();
   return VLCAL_OK;
@@ -798,10 +840,5 @@ int vlcal_nid_debug_filter_check(vlcal_nid_ctx* ctx, const double* T_camera_lida
   return VLCAL_OK;
 }
 
-int vlcal_nid_evaluate_bspline(vlcal_nid_ctx* ctx, const double* T_params, int n_poses, double* nid_out, int32_t* ok_out, double* hist_out) {
-  (void)ctx, (void)T_params, (void)n_poses, (void)nid_out, (void)ok_out, (void)hist_out;
-  set_last_error("mode B (B-spline NIDCost) kernel is not built yet");
-  return VLCAL_ERR_UNSUPPORTED;
-}
 
 }  // extern "C"

@@ -91,6 +91,8 @@ struct vlcal_nid_ctx {
   // async state
   bool in_flight = false;
   int in_flight_poses = 0;
+  // debug timeline (vlcal_nid_debug_timeline)
+  unsigned long long* h_timeline = nullptr;  // pinned + mapped [16]
   // profiling
   bool profiling = false;
   std::vector<vlcal::ProfileEvents> events;

@@ -37,6 +37,7 @@ struct NidArgs {
   float pose32[NID_MAX_POSES][16]; // fp32 filter copy: R (9, row-major), t (3), max|t| (1), pad
   FastCam fast;                    // fp32 filter constants (fast.enabled == 0 -> exact kernel only)
   unsigned long long* dbg;         // verify kernel only: {point-poses, uncertain, mismatches, max ratio bits}
+  unsigned long long* timeline;    // optional [16]: globaltimer stamps of the launch (vlcal_nid_debug_timeline)
   int* ghist;                 // [NID_MAX_POSES][nb] global accumulators, zero on entry, zero on exit
   unsigned int* counter;      // block ticket, zero on entry, zero on exit
   double* nid_out;            // [n_poses]
@@ -78,6 +79,17 @@ template <int MODEL>
 __device__ __forceinline__ int classify_exact(const NidArgs& a, const double* __restrict__ T, double x, double y, double z) {
   const int pix = exact_pixel<MODEL>(a, T, x, y, z);
   return pix < 0 ? -1 : static_cast<int>(__ldg(a.bin_image + pix));  // :43,:46 via the pre-binned image
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// timeline slots: 0 first block start (min), 1 last-block: main loop done, 2 merged+fenced, 3 ticket known,
+// 4 finalize math done, 5 results published (after the system fence), 6 last block start
+__device__ __forceinline__ void stamp(const NidArgs& a, int slot) {
+  if (a.timeline && threadIdx.x == 0) a.timeline[slot] = global_ns();
 }
 
 // ---- fp32 filter --------------------------------------------------------------------------------------------
@@ -189,6 +201,7 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
     __syncwarp();
   }
   __syncthreads();
+  stamp(a, 4);
   if (threadIdx.x == 0) {
     *a.counter = 0u;
     if (a.done_flag) {  // publish to the polling host thread: results first, then the sequence number
@@ -196,11 +209,13 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
       *reinterpret_cast<volatile unsigned long long*>(a.done_flag) = a.done_seq;
     }
   }
+  stamp(a, 5);
 }
 
 // block epilogue shared by the histogram kernels: merge copies -> global accumulators -> last block finalizes
 __device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, int* smem_hist, bool* s_is_last) {
   const int per_copy = a.n_poses * a.nb;
+  const unsigned long long t_main = a.timeline ? global_ns() : 0ull;
   __syncthreads();
   for (int k = threadIdx.x; k < per_copy; k += blockDim.x) {
     int s = 0;
@@ -209,12 +224,18 @@ __device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, int* smem_h
   }
   __threadfence();
   __syncthreads();
+  const unsigned long long t_merged = a.timeline ? global_ns() : 0ull;
   if (threadIdx.x == 0) {
     const unsigned int ticket = atomicAdd(a.counter, 1u);
     *s_is_last = (ticket == gridDim.x - 1);
   }
   __syncthreads();
   if (!*s_is_last) return;
+  if (a.timeline && threadIdx.x == 0) {
+    a.timeline[1] = t_main;
+    a.timeline[2] = t_merged;
+    a.timeline[3] = global_ns();
+  }
   __threadfence();
   nid_finalize(a, smem_hist);
 }
@@ -224,6 +245,7 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __gri
   extern __shared__ int smem_hist[];
   __shared__ bool s_is_last;
   const int per_copy = a.n_poses * a.nb;
+  if (a.timeline && threadIdx.x == 0) atomicMin(a.timeline + 0, global_ns());
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
   int* my_hist = smem_hist + ((threadIdx.x >> 5) % a.copies) * per_copy;
@@ -268,6 +290,7 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   __shared__ unsigned char q_pose[NID_THREADS / 32][NID_QUEUE];
   static_assert(F32, "the fp32 filter runs on the float4 cloud layout");
   const int per_copy = a.n_poses * a.nb;
+  if (a.timeline && threadIdx.x == 0) atomicMin(a.timeline + 0, global_ns());
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

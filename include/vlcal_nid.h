@@ -144,6 +144,9 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
  * 1 = exact fp64 only, 2 = fp32 filter with 2 points/thread */
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
 
+/* measurement hook: one launch (n_poses <= 8) with %globaltimer stamps; out_us = {main loop done, merged, ticket, finalize done,
+ * published} in microseconds since the first block started, then host-side {launch call, launch->results visible} */
+int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double out_us[8]);
 /* device / pinned buffers of destroyed contexts are cached for reuse (contexts are rebuilt every outer iteration);
  * this releases the cache back to the CUDA driver */
 int vlcal_nid_trim_memory(void);

@@ -353,3 +353,53 @@ def test_filter_disabled_cases_fall_back_to_the_exact_kernel_not_to_cpu(gpu, ora
     Ts = util.random_poses(pr["T"], 2, seed=1)
     _, hist = cost.calculate_batch(Ts, return_hist=True)
     assert np.array_equal(hist, _oracle_eval(oracle, pr, Ts)[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mode B: NIDCost::operator()<double> value (B-spline soft histogram)
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def _sophus_params(T):
+    from scipy.spatial.transform import Rotation
+
+    q = Rotation.from_matrix(T[:3, :3]).as_quat()  # x y z w
+    return np.concatenate([q, T[:3, 3]])
+
+
+@pytest.mark.parametrize("model", util.MODELS)
+def test_bspline_nid_matches_oracle(gpu, oracle, model):
+    pr = util.random_problem(model, n=30000, seed=61)
+    Ts = util.random_poses(pr["T"], 11, seed=3)  # > one launch of 8 poses
+    tps = np.stack([_sophus_params(T) for T in Ts])
+    cam = gpu.create_camera(model, pr["intrinsics"], pr["distortion"])
+    cost = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], pr["points"], pr["intensities"]), 16)
+    ok, nid, hist = cost.evaluate(tps, return_hist=True)
+    ocam = oracle.create_camera(model, pr["intrinsics"], pr["distortion"])
+    for p in range(len(Ts)):
+        rok, rnid, rhist = oracle.nid_cost_bspline(ocam, pr["image"], pr["points"], pr["intensities"], 16, tps[p])
+        assert bool(ok[p]) == rok
+        assert abs(nid[p] - rnid) < 1e-9, abs(nid[p] - rnid)  # 2^-40 fixed-point accumulation vs serial double sum
+        assert np.abs(hist[p] - rhist).max() < 1e-6 and abs(hist[p].sum() - rhist.sum()) < 1e-5
+        assert hist[p].sum() > 1000
+    # deterministic run to run (integer accumulation) and batch == single
+    ok2, nid2 = cost.evaluate(tps)
+    assert np.array_equal(nid, nid2)
+    assert cost(tps[9])[1] == nid[9]
+
+
+def test_bspline_other_bins_and_failure_flag(gpu, oracle):
+    pr = util.random_problem("plumb_bob", n=10000, seed=62)
+    tp = _sophus_params(pr["T"])
+    cam = gpu.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
+    ocam = oracle.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
+    for bins in (8, 32):
+        ok, nid = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], pr["points"], pr["intensities"]), bins).evaluate(tp[None])
+        rok, rnid, _ = oracle.nid_cost_bspline(ocam, pr["image"], pr["points"], pr["intensities"], bins, tp)
+        assert ok[0] == rok and abs(nid[0] - rnid) < 1e-9
+    # every point behind / outside -> no inliers -> NaN -> the functor returns false (nid_cost.hpp:98-102)
+    far = np.array([[0.0, 0.0, -5.0, 1.0]] * 10)
+    T = np.eye(4)
+    ok, nid = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], far * [1, 1, 1, 1] + [1e4, 0, 0, 0], np.full(10, 0.5)), 16).evaluate(_sophus_params(T)[None])
+    rok, _, _ = oracle.nid_cost_bspline(ocam, pr["image"], far + [1e4, 0, 0, 0], np.full(10, 0.5), 16, _sophus_params(T))
+    assert (not ok[0]) and (not rok)

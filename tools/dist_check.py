@@ -1,0 +1,47 @@
+"""torchrun worker: bag-sharded joint Nelder-Mead over NCCL == the same solve with all bags on one GPU.
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dist_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import direct_visual_lidar_calibration_b200 as V
+from direct_visual_lidar_calibration_b200 import calibration as VC
+from direct_visual_lidar_calibration_b200 import synthetic as S
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+bags = [S.make_bag("pinhole_640x480", "frustum", 40000 + 5000 * r, config_index=7, bag_index=r, scale=0.5) for r in range(world)]
+cam = V.create_camera(bags[0]["camera_model"], bags[0]["intrinsics"], bags[0]["distortion"])
+T0 = S.perturb(S.gt_T_camera_lidar(), (0.3, -0.3, 0.3), (0.01, -0.01, 0.01))
+params = V.VisualCameraCalibrationParams()
+params.max_inner_iterations = 60
+buf = torch.zeros(16, dtype=torch.float64, device="cuda")
+
+
+def allreduce(vals):
+    k = vals.shape[0]
+    buf[:k] = torch.from_numpy(vals).cuda()
+    dist.all_reduce(buf[:k])
+    vals[:] = buf[:k].cpu().numpy()
+
+
+mine = V.CostCalculatorNID(cam, V.VisualLiDARData(bags[rank]["image"], bags[rank]["points"], bags[rank]["intensities"]), device=local)
+T, r = VC.estimate_pose_on_costs([mine], T0, params, allreduce=allreduce)
+out = torch.from_numpy(np.concatenate([T.reshape(-1), r["x"], [r["y"], r["num_iterations"], r["num_evaluations"]]])).cuda()
+gathered = [torch.zeros_like(out) for _ in range(world)]
+dist.all_gather(gathered, out)
+if rank == 0:
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "ranks diverged"
+    costs = [V.CostCalculatorNID(cam, V.VisualLiDARData(b["image"], b["points"], b["intensities"]), device=local) for b in bags]
+    T1, r1 = VC.estimate_pose_on_costs(costs, T0, params)
+    same = np.array_equal(T1, T) and r1["num_iterations"] == r["num_iterations"] and r1["num_evaluations"] == r["num_evaluations"]
+    close = np.abs(T1 - T).max() < 1e-12 and abs(r1["y"] - r["y"]) < 1e-12
+    print(f"DIST_CHECK world={world} identical={same} close={close} iters={r['num_iterations']} y={r['y']:.12f} y_single={r1['y']:.12f}")
+    assert close and r1["num_iterations"] == r["num_iterations"]
+dist.barrier()
+dist.destroy_process_group()

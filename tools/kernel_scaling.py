@@ -31,3 +31,13 @@ for n in (1024, 65536, 262144, len(pts)):
             cost.set_profiling(False)
             us = 1e3 * pr["kernel_ms_total"] / pr["kernel_launches"]
             print(json.dumps({"kernel": name, "n_points": n, "poses": P, "us_per_launch": round(us, 3), "gpointposes_per_s": round(n * P / us * 1e-3, 2)}), flush=True)
+
+# where the time of one launch goes (globaltimer stamps inside the kernel + host clock)
+for n in (1024, len(pts)):
+    cost = V.CostCalculatorNID(cam, V.VisualLiDARData(bag["image"], pts[:n], inten[:n]))
+    for P in (1, 4, 8):
+        for _ in range(5):
+            cost.calculate_batch(poses[:P])
+        tl = [cost.debug_timeline(poses[:P]) for _ in range(20)]
+        med = {k: round(float(np.median([t[k] for t in tl])), 2) for k in tl[0]}
+        print(json.dumps({"timeline_us": med, "n_points": n, "poses": P}), flush=True)
