@@ -37,7 +37,7 @@ struct NidArgs {
   float pose32[NID_MAX_POSES][16]; // fp32 filter copy: R (9, row-major), t (3), max|t| (1), pad
   FastCam fast;                    // fp32 filter constants (fast.enabled == 0 -> exact kernel only)
   unsigned long long* dbg;         // verify kernel only: {point-poses, uncertain, mismatches, max ratio bits}
-  unsigned long long* timeline;    // optional [16]: globaltimer stamps of the launch (vlcal_nid_debug_timeline)
+  unsigned long long* timeline;    // optional [16] mapped host words: globaltimer stamps of the launch (vlcal_nid_debug_timeline)
   int* ghist;                 // [NID_MAX_POSES][nb] global accumulators, zero on entry, zero on exit
   unsigned int* counter;      // block ticket, zero on entry, zero on exit
   double* nid_out;            // [n_poses]
@@ -146,7 +146,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 // entropies + NID for every pose of the launch; run by the last block only (:54-64).
 // One warp per pose (the serial tail of the launch is one pose deep, not P): lane l owns joint bins l, l+32, ...;
 // marginals are the row / column sums of the joint (the reference increments all three together, :49-51).
-// Summation order is a fixed function of (bins, lane), independent of P and of the pose's slot.
+// The joint counts are fetched in batches of FIN_CH independent L2 loads per lane (one round trip for 16 bins), not
+// one dependent load per bin.  Summation order is a fixed function of (bins, lane), independent of P and of the slot.
+constexpr int FIN_CH = 8;
+
 static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   int* h_image = smem_i + warp * 2 * a.bins;  // [bins] per warp
@@ -156,12 +159,21 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
     for (int i = lane; i < 2 * a.bins; i += 32) h_image[i] = 0;
     __syncwarp();
     int part = 0;
-    for (int k = lane; k < a.nb; k += 32) {
-      const int c = __ldcg(g + k);
-      if (c) {
-        atomicAdd(&h_image[k % a.bins], c);
-        atomicAdd(&h_points[k / a.bins], c);
-        part += c;
+    int c[FIN_CH];
+    for (int k0 = 0; k0 < a.nb; k0 += 32 * FIN_CH) {  // pass 1: marginals + inlier count
+#pragma unroll
+      for (int m = 0; m < FIN_CH; m++) {
+        const int k = k0 + m * 32 + lane;
+        c[m] = k < a.nb ? __ldcg(g + k) : 0;
+      }
+#pragma unroll
+      for (int m = 0; m < FIN_CH; m++) {
+        const int k = k0 + m * 32 + lane;
+        if (c[m]) {
+          atomicAdd(&h_image[k % a.bins], c[m]);
+          atomicAdd(&h_points[k / a.bins], c[m]);
+          part += c[m];
+        }
       }
     }
 #pragma unroll
@@ -170,9 +182,25 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
     const double sum = static_cast<double>(part);  // :54 sum = hist_image.sum()
     // :59-61  H = -sum p*log(p + 1e-6)
     double t_rs = 0.0, t_r = 0.0, t_s = 0.0;
-    for (int k = lane; k < a.nb; k += 32) {
-      const double pr = static_cast<double>(__ldcg(g + k)) / sum;
-      t_rs += pr * log(pr + 1e-6);
+    const bool single = a.nb <= 32 * FIN_CH;  // the counts of pass 1 are still in registers
+    for (int k0 = 0; k0 < a.nb; k0 += 32 * FIN_CH) {  // pass 2: joint entropy, export, self-clean
+      if (!single) {
+#pragma unroll
+        for (int m = 0; m < FIN_CH; m++) {
+          const int k = k0 + m * 32 + lane;
+          c[m] = k < a.nb ? __ldcg(g + k) : 0;
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < FIN_CH; m++) {
+        const int k = k0 + m * 32 + lane;
+        if (k < a.nb) {
+          const double pr = static_cast<double>(c[m]) / sum;
+          t_rs += pr * log(pr + 1e-6);
+          if (a.hist_out) a.hist_out[static_cast<size_t>(p) * a.nb + k] = c[m];
+          g[k] = 0;
+        }
+      }
     }
     for (int k = lane; k < a.bins; k += 32) {
       const double pi = static_cast<double>(h_image[k]) / sum;
@@ -192,11 +220,6 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
       const double nid = (Hrs - MI) / Hrs;  // :64 (NaN when there are no inliers, as in the reference)
       a.nid_out[p] = nid;
       if (a.nid_host) a.nid_host[p] = nid;
-    }
-    // export + self-clean
-    for (int k = lane; k < a.nb; k += 32) {
-      if (a.hist_out) a.hist_out[static_cast<size_t>(p) * a.nb + k] = __ldcg(g + k);
-      g[k] = 0;
     }
     __syncwarp();
   }
@@ -245,7 +268,7 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __gri
   extern __shared__ int smem_hist[];
   __shared__ bool s_is_last;
   const int per_copy = a.n_poses * a.nb;
-  if (a.timeline && threadIdx.x == 0) atomicMin(a.timeline + 0, global_ns());
+  if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
   int* my_hist = smem_hist + ((threadIdx.x >> 5) % a.copies) * per_copy;
@@ -290,7 +313,7 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   __shared__ unsigned char q_pose[NID_THREADS / 32][NID_QUEUE];
   static_assert(F32, "the fp32 filter runs on the float4 cloud layout");
   const int per_copy = a.n_poses * a.nb;
-  if (a.timeline && threadIdx.x == 0) atomicMin(a.timeline + 0, global_ns());
+  if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
