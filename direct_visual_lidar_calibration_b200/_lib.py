@@ -125,6 +125,12 @@ def load_library():
     L.vlcal_nid_debug_timeline.argtypes = [vp, dp, C.c_int, dp]
     L.vlcal_nid_filter_enabled.argtypes = [vp]
     L.vlcal_nid_debug_filter_check.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_uint64), dp]
+    L.vlcal_nid_p2p_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp]
+    L.vlcal_nid_p2p_connect.argtypes = [vp, vp]
+    L.vlcal_nid_p2p_attach.argtypes = [vp, vp]
+    L.vlcal_nid_p2p_destroy.argtypes = [vp]
+    L.vlcal_nid_p2p_destroy.restype = None
+    L.vlcal_nid_p2p_set_default.argtypes = [vp]
     L.vlcal_view_cull.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int64, dp, vp, C.POINTER(C.c_int64)]
     L.vlcal_nm_default_params.argtypes = [C.POINTER(NMParams)]
     L.vlcal_nm_default_params.restype = None

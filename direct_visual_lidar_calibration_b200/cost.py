@@ -96,6 +96,10 @@ class CostCalculatorNID:
     def points_are_f32(self) -> bool:
         return bool(self._L.vlcal_nid_points_are_f32(self._ctx))
 
+    def attach_peer_exchange(self, px):
+        """Multi-GPU, one bag per rank: evaluations return the sum over ranks (fused in-kernel exchange)."""
+        _lib.check(self._L.vlcal_nid_p2p_attach(self._ctx, px.handle if px is not None else None))
+
     def debug_timeline(self, Ts):
         Tc = T_to_colmajor(Ts)
         out = np.zeros(8)

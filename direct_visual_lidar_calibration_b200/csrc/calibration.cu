@@ -14,6 +14,8 @@ using namespace vlcal;
 
 namespace {
 
+vlcal_p2p* g_default_p2p = nullptr;  // vlcal_nid_p2p_set_default
+
 struct PoseObjective {
   vlcal_nid_ctx* const* ctxs;
   int n_ctxs;
@@ -53,7 +55,9 @@ struct PoseObjective {
         for (int i = 0; i < count; i++) partial[i] += vals[i];  // sum_costs += costs[i]->calculate(T)
       }
     }
-    if (allreduce) allreduce(partial.data(), count, user);
+    // with a peer exchange attached (one bag per rank) the kernel already returned the sum over ranks
+    const bool fused = n_ctxs == 1 && ctxs[0]->p2p != nullptr;
+    if (allreduce && !fused) allreduce(partial.data(), count, user);
     for (int i = 0; i < count; i++) ys[i] = status == VLCAL_OK ? partial[i] : NAN;
   }
 
@@ -152,6 +156,7 @@ int inner_solve_resident(
     rc = nid_ctx_create(device, VLCAL_NID_MODE_HISTOGRAM, cam, bags[b].image, culled, params->nid_bins, bags[b].max_fov, &ctx);  // :82-84
     if (rc != VLCAL_OK) return rc;
     ctx->profiling = profiling != 0;
+    if (g_default_p2p && bags.size() == 1 && g_default_p2p->device == device) ctx->p2p = g_default_p2p;
     ctxs.v.push_back(ctx);
   }
   vlcal_nm_result local;
@@ -193,6 +198,15 @@ int check_common(const vlcal_calib_params* params, const double* init_T, double*
 }  // namespace
 
 extern "C" {
+
+int vlcal_nid_p2p_set_default(vlcal_p2p* px) {
+  if (px && !px->connected) {
+    set_last_error("peer exchange is not connected");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  g_default_p2p = px;
+  return VLCAL_OK;
+}
 
 void vlcal_nm_default_params(vlcal_nm_params* p) {  // nelder_mead.hpp:12
   const host::NelderMeadParams d;

@@ -434,6 +434,13 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
     fill_pose32(a, pc);
     a.fast = ctx->fast;
     a.timeline = ctx->h_timeline;
+    if (ctx->p2p && ctx->p2p->connected && ctx->p2p->world > 1) {
+      for (int r = 0; r < ctx->p2p->world; r++) a.peer_box[r] = ctx->p2p->peers[r];
+      a.p2p_world = ctx->p2p->world;
+      a.p2p_rank = ctx->p2p->rank;
+      a.p2p_seq = ++ctx->p2p->seq;
+      a.p2p_error = ctx->p2p->h_error;
+    }
     a.ghist = ctx->d_ghist;
     a.counter = ctx->d_counter;
     a.nid_out = ctx->d_nid + p0;
@@ -517,6 +524,10 @@ int nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out) {
       }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    if (ctx->p2p && ctx->p2p->h_error && *ctx->p2p->h_error) {
+      set_last_error("peer exchange timed out: a rank died or the ranks are not evaluating in lockstep");
+      return VLCAL_ERR_CUDA;
+    }
   }
   if (ctx->events_used > 256) {
     VL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -774,6 +785,75 @@ int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, i
   MemPool::instance().pinned_free(ctx->h_timeline);
   ctx->h_timeline = nullptr;
   return rc;
+}
+
+int vlcal_nid_p2p_create(int device, int rank, int world, vlcal_p2p** out, void* ipc_handle_out) {
+  if (!out || !ipc_handle_out || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) {
+    set_last_error("invalid arguments (1 <= world <= 8)");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  if (vlcal_nid_device_count() == 0) {
+    set_last_error("no CUDA device available");
+    return VLCAL_ERR_NO_DEVICE;
+  }
+  if (device < 0) VL_CUDA(cudaGetDevice(&device));
+  VL_CUDA(cudaSetDevice(device));
+  std::unique_ptr<vlcal_p2p> p(new vlcal_p2p());
+  p->device = device, p->rank = rank, p->world = world;
+  VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->local), sizeof(P2PMailbox)));  // own allocation: cudaIpc shares whole allocations
+  VL_CUDA(cudaMemset(p->local, 0, sizeof(P2PMailbox)));
+  VL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p->h_error), sizeof(int), cudaHostAllocDefault));
+  *p->h_error = 0;
+  cudaIpcMemHandle_t h;
+  VL_CUDA(cudaIpcGetMemHandle(&h, p->local));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(ipc_handle_out, &h, sizeof(h));
+  p->peers[rank] = p->local;
+  *out = p.release();
+  return VLCAL_OK;
+}
+
+int vlcal_nid_p2p_connect(vlcal_p2p* p, const void* all_handles) {
+  if (!p || !all_handles) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  VL_CUDA(cudaSetDevice(p->device));
+  for (int r = 0; r < p->world; r++) {
+    if (r == p->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(all_handles) + 64 * r, sizeof(h));
+    void* ptr = nullptr;
+    VL_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peers[r] = static_cast<P2PMailbox*>(ptr);
+  }
+  p->connected = true;
+  return VLCAL_OK;
+}
+
+int vlcal_nid_p2p_attach(vlcal_nid_ctx* ctx, vlcal_p2p* p) {
+  if (!ctx) {
+    set_last_error("ctx is NULL");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  if (p && (!p->connected || p->device != ctx->device)) {
+    set_last_error("peer exchange is not connected or lives on another device");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  ctx->p2p = p;
+  return VLCAL_OK;
+}
+
+void vlcal_nid_p2p_destroy(vlcal_p2p* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < p->world; r++) {
+    if (r != p->rank && p->peers[r]) cudaIpcCloseMemHandle(p->peers[r]);
+  }
+  if (p->local) cudaFree(p->local);
+  if (p->h_error) cudaFreeHost(p->h_error);
+  delete p;
 }
 
 int vlcal_nid_trim_memory(void) {

@@ -61,6 +61,20 @@ struct ProfileEvents {
 
 }  // namespace vlcal
 
+namespace vlcal {
+struct P2PMailbox;
+}
+
+// one per process: this rank's mailbox + the mapped mailboxes of the peers (vlcal_nid_p2p_*)
+struct vlcal_p2p {
+  int device = 0, rank = 0, world = 1;
+  vlcal::P2PMailbox* local = nullptr;
+  vlcal::P2PMailbox* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool connected = false;
+  unsigned long long seq = 0;
+  int* h_error = nullptr;  // pinned + mapped
+};
+
 struct vlcal_nid_ctx {
   int device = 0;
   int mode = 0;
@@ -91,6 +105,7 @@ struct vlcal_nid_ctx {
   // async state
   bool in_flight = false;
   int in_flight_poses = 0;
+  vlcal_p2p* p2p = nullptr;  // attached peer exchange (not owned)
   // debug timeline (vlcal_nid_debug_timeline)
   unsigned long long* h_timeline = nullptr;  // pinned + mapped [16]
   // profiling

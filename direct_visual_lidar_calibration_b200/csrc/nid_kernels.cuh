@@ -23,6 +23,18 @@ constexpr int NID_MAX_POSES = 8;   // poses carried by one launch
 constexpr int NID_THREADS = 256;   // threads per block
 constexpr int NID_MAX_BINS = 128;  // bins*bins*4 B must fit shared memory at least once
 
+// ---- fused bag all-reduce over NVLink peer memory (multi-GPU, one bag per rank) -------------------------------
+// The joint objective is sum_bags NID (visual_camera_calibration.cpp:105-110).  With one process per GPU and one bag
+// per process, the finalizing block of every rank stores its P scores straight into every peer's mailbox (P2P stores
+// through NVLink / NVSwitch, buffers shared with cudaIpc), bumps a sequence word, waits for the other ranks' words and
+// adds the G contributions in rank order -- so all ranks publish bit-identical sums without a separate collective
+// launch and without leaving the kernel.  Two slots (seq & 1) because a rank can be at most one exchange ahead.
+constexpr int P2P_MAX_RANKS = 8;
+struct P2PMailbox {
+  double vals[P2P_MAX_RANKS][2][8];        // [sender][slot][pose]
+  unsigned long long seq[P2P_MAX_RANKS][2];  // [sender][slot]
+};
+
 struct NidArgs {
   const void* points;        // float4[n] (x,y,z,intensity) or double4[n]
   const uint8_t* bin_image;  // H x W image bins: clamp(int(u8/255.0*bins), 0, bins-1)  (:43,:46)
@@ -37,6 +49,10 @@ struct NidArgs {
   float pose32[NID_MAX_POSES][16]; // fp32 filter copy: R (9, row-major), t (3), max|t| (1), pad
   FastCam fast;                    // fp32 filter constants (fast.enabled == 0 -> exact kernel only)
   unsigned long long* dbg;         // verify kernel only: {point-poses, uncertain, mismatches, max ratio bits}
+  P2PMailbox* peer_box[P2P_MAX_RANKS];  // peer_box[r]: rank r's mailbox as mapped in this process (self included)
+  int p2p_world, p2p_rank;         // p2p_world <= 1: no exchange
+  unsigned long long p2p_seq;
+  int* p2p_error;                  // mapped host word, set to 1 if a peer never answered
   unsigned long long* timeline;    // optional [16] mapped host words: globaltimer stamps of the launch (vlcal_nid_debug_timeline)
   int* ghist;                 // [NID_MAX_POSES][nb] global accumulators, zero on entry, zero on exit
   unsigned int* counter;      // block ticket, zero on entry, zero on exit
@@ -144,86 +160,153 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // entropies + NID for every pose of the launch; run by the last block only (:54-64).
-// One warp per pose (the serial tail of the launch is one pose deep, not P): lane l owns joint bins l, l+32, ...;
-// marginals are the row / column sums of the joint (the reference increments all three together, :49-51).
-// The joint counts are fetched in batches of FIN_CH independent L2 loads per lane (one round trip for 16 bins), not
-// one dependent load per bin.  Summation order is a fixed function of (bins, lane), independent of P and of the slot.
+// This is the serial tail of every launch, so it is laid out for latency: the block's 8 warps are split evenly over
+// the P poses (8/P warps per pose), every lane fetches its joint bins with independent L2 loads, and a lane evaluates
+// only nb / (32 * warps_per_pose) logarithms.  Marginals are the row / column sums of the joint (the reference
+// increments all three together, :49-51).
+// The NID must be a function of the histogram ALONE (Nelder-Mead compares scores that were computed in launches with
+// different P; equal histograms must give equal bits): the p*log(p) terms are therefore staged in shared memory and
+// reduced by one warp in a canonical order -- lane l adds terms l, l+32, ... in ascending order, then a fixed xor tree.
 constexpr int FIN_CH = 8;
+
+__device__ __forceinline__ double warp_tree_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// called by the finalizing block after every pose's local score sits in a.nid_out (block-synchronised)
+static __device__ void nid_peer_allreduce(const NidArgs& a) {
+  const int slot = static_cast<int>(a.p2p_seq & 1ull);
+  const int t = threadIdx.x;
+  if (t < a.n_poses * a.p2p_world) {  // one thread per (peer, pose): remote stores over NVLink
+    const int g = t / a.n_poses, p = t % a.n_poses;
+    a.peer_box[g]->vals[a.p2p_rank][slot][p] = a.nid_out[p];
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t < a.p2p_world) {  // sequence word after the payload (system-scope fence above orders them)
+    *reinterpret_cast<volatile unsigned long long*>(&a.peer_box[t]->seq[a.p2p_rank][slot]) = a.p2p_seq;
+    // wait for rank t's contribution to land in OUR mailbox
+    volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(&a.peer_box[a.p2p_rank]->seq[t][slot]);
+    const unsigned long long t0 = global_ns();
+    unsigned int spins = 0;
+    while (*w != a.p2p_seq) {
+      if ((++spins & 1023u) == 0 && global_ns() - t0 > 2000000000ull) {  // 2 s: a peer died or fell out of lockstep
+        if (a.p2p_error) *a.p2p_error = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t < a.n_poses) {
+    double total = 0.0;
+    for (int r = 0; r < a.p2p_world; r++) total += __ldcv(&a.peer_box[a.p2p_rank]->vals[r][slot][t]);  // rank order: identical on every rank
+    a.nid_out[t] = total;
+    if (a.nid_host) a.nid_host[t] = total;
+  }
+  __syncthreads();
+}
 
 static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-  int* h_image = smem_i + warp * 2 * a.bins;  // [bins] per warp
-  int* h_points = h_image + a.bins;           // [bins]
-  for (int p = warp; p < a.n_poses; p += n_warps) {
-    int* g = a.ghist + static_cast<size_t>(p) * a.nb;
-    for (int i = lane; i < 2 * a.bins; i += 32) h_image[i] = 0;
-    __syncwarp();
+  __shared__ int s_cnt[NID_THREADS / 32];  // per-warp partial inlier counts
+  // splitting a pose over several warps needs staging room: the block's histogram copies provide it when copies >= 4
+  const int wpp = a.copies >= 4 ? max(1, n_warps / a.n_poses) : 1;  // warps per pose
+  const int ppr = n_warps / wpp;                                     // poses per round
+  double* s_term = reinterpret_cast<double*>(smem_i);                // [ppr][nb] staged p*log(p+1e-6) terms (wpp > 1)
+  int* s_marg = smem_i + (wpp > 1 ? 2 * ppr * a.nb : 0);             // [ppr][2*bins] marginal counts
+  for (int p0 = 0; p0 < a.n_poses; p0 += ppr) {
+    const int slot = warp / wpp, sub = warp % wpp;  // pose slot of this warp within the round, rank within the pose
+    const int p = p0 + slot;
+    const bool active = slot < ppr && p < a.n_poses;
+    int* h_image = s_marg + slot * 2 * a.bins;  // [bins]
+    int* h_points = h_image + a.bins;           // [bins]
+    for (int i = threadIdx.x; i < ppr * 2 * a.bins; i += blockDim.x) s_marg[i] = 0;
+    __syncthreads();
+    int* g = a.ghist + static_cast<size_t>(active ? p : 0) * a.nb;
+    const int span = wpp * 32;  // joint bins covered per step by the warps of one pose
     int part = 0;
     int c[FIN_CH];
-    for (int k0 = 0; k0 < a.nb; k0 += 32 * FIN_CH) {  // pass 1: marginals + inlier count
+    const bool single = a.nb <= span * FIN_CH;  // pass-1 counts stay in registers for pass 2
+    if (active) {
+      for (int k0 = 0; k0 < a.nb; k0 += span * FIN_CH) {  // pass 1: marginals + inlier count
 #pragma unroll
-      for (int m = 0; m < FIN_CH; m++) {
-        const int k = k0 + m * 32 + lane;
-        c[m] = k < a.nb ? __ldcg(g + k) : 0;
-      }
+        for (int m = 0; m < FIN_CH; m++) {
+          const int k = k0 + m * span + sub * 32 + lane;
+          c[m] = k < a.nb ? __ldcg(g + k) : 0;
+        }
 #pragma unroll
-      for (int m = 0; m < FIN_CH; m++) {
-        const int k = k0 + m * 32 + lane;
-        if (c[m]) {
-          atomicAdd(&h_image[k % a.bins], c[m]);
-          atomicAdd(&h_points[k / a.bins], c[m]);
-          part += c[m];
+        for (int m = 0; m < FIN_CH; m++) {
+          const int k = k0 + m * span + sub * 32 + lane;
+          if (c[m]) {
+            atomicAdd(&h_image[k % a.bins], c[m]);
+            atomicAdd(&h_points[k / a.bins], c[m]);
+            part += c[m];
+          }
         }
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __syncwarp();
-    const double sum = static_cast<double>(part);  // :54 sum = hist_image.sum()
-    // :59-61  H = -sum p*log(p + 1e-6)
-    double t_rs = 0.0, t_r = 0.0, t_s = 0.0;
-    const bool single = a.nb <= 32 * FIN_CH;  // the counts of pass 1 are still in registers
-    for (int k0 = 0; k0 < a.nb; k0 += 32 * FIN_CH) {  // pass 2: joint entropy, export, self-clean
-      if (!single) {
+    if (lane == 0) s_cnt[warp] = part;
+    __syncthreads();
+    double t_rs = 0.0;  // canonical per-lane partial of the joint entropy (only meaningful when wpp == 1)
+    double sum = 0.0;
+    if (active) {
+      int total = 0;
+      for (int w = 0; w < wpp; w++) total += s_cnt[slot * wpp + w];
+      sum = static_cast<double>(total);  // :54 sum = hist_image.sum()
+      // :59-61  H = -sum p*log(p + 1e-6)
+      for (int k0 = 0; k0 < a.nb; k0 += span * FIN_CH) {  // pass 2: joint entropy terms, export, self-clean
+        if (!single) {
+#pragma unroll
+          for (int m = 0; m < FIN_CH; m++) {
+            const int k = k0 + m * span + sub * 32 + lane;
+            c[m] = k < a.nb ? __ldcg(g + k) : 0;
+          }
+        }
 #pragma unroll
         for (int m = 0; m < FIN_CH; m++) {
-          const int k = k0 + m * 32 + lane;
-          c[m] = k < a.nb ? __ldcg(g + k) : 0;
+          const int k = k0 + m * span + sub * 32 + lane;
+          if (k < a.nb) {
+            const double pr = static_cast<double>(c[m]) / sum;
+            const double term = pr * log(pr + 1e-6);
+            if (wpp > 1) {
+              s_term[slot * a.nb + k] = term;
+            } else {
+              t_rs += term;  // k ascends with (k0, m): already the canonical order
+            }
+            if (a.hist_out) a.hist_out[static_cast<size_t>(p) * a.nb + k] = c[m];
+            g[k] = 0;
+          }
         }
       }
-#pragma unroll
-      for (int m = 0; m < FIN_CH; m++) {
-        const int k = k0 + m * 32 + lane;
-        if (k < a.nb) {
-          const double pr = static_cast<double>(c[m]) / sum;
-          t_rs += pr * log(pr + 1e-6);
-          if (a.hist_out) a.hist_out[static_cast<size_t>(p) * a.nb + k] = c[m];
-          g[k] = 0;
-        }
+    }
+    if (wpp > 1) __syncthreads();
+    if (active && sub == 0) {  // one warp per pose: canonical reductions
+      if (wpp > 1) {
+        for (int k = lane; k < a.nb; k += 32) t_rs += s_term[slot * a.nb + k];
+      }
+      double t_r = 0.0, t_s = 0.0;
+      for (int k = lane; k < a.bins; k += 32) {
+        const double pi = static_cast<double>(h_image[k]) / sum;
+        const double pp = static_cast<double>(h_points[k]) / sum;
+        t_r += pi * log(pi + 1e-6);
+        t_s += pp * log(pp + 1e-6);
+      }
+      const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);
+      if (lane == 0) {
+        const double MI = Hr + Hs - Hrs;      // :63
+        const double nid = (Hrs - MI) / Hrs;  // :64 (NaN when there are no inliers, as in the reference)
+        a.nid_out[p] = nid;
+        if (a.nid_host) a.nid_host[p] = nid;
       }
     }
-    for (int k = lane; k < a.bins; k += 32) {
-      const double pi = static_cast<double>(h_image[k]) / sum;
-      const double pp = static_cast<double>(h_points[k]) / sum;
-      t_r += pi * log(pi + 1e-6);
-      t_s += pp * log(pp + 1e-6);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      t_rs += __shfl_xor_sync(0xffffffffu, t_rs, o);
-      t_r += __shfl_xor_sync(0xffffffffu, t_r, o);
-      t_s += __shfl_xor_sync(0xffffffffu, t_s, o);
-    }
-    if (lane == 0) {
-      const double Hrs = -t_rs, Hr = -t_r, Hs = -t_s;
-      const double MI = Hr + Hs - Hrs;      // :63
-      const double nid = (Hrs - MI) / Hrs;  // :64 (NaN when there are no inliers, as in the reference)
-      a.nid_out[p] = nid;
-      if (a.nid_host) a.nid_host[p] = nid;
-    }
-    __syncwarp();
+    __syncthreads();
   }
-  __syncthreads();
+  if (a.p2p_world > 1) nid_peer_allreduce(a);
   stamp(a, 4);
   if (threadIdx.x == 0) {
     *a.counter = 0u;

@@ -157,6 +157,24 @@ int vlcal_nid_filter_enabled(const vlcal_nid_ctx* ctx);
  * exact path (MUST be 0), *max_bound_ratio = max |uv_fp32 - uv_exact| / error-bound over kept in-image verdicts (< 1). */
 int vlcal_nid_debug_filter_check(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, uint64_t counts[3], double* max_bound_ratio);
 
+/* ---- multi-GPU: fused bag all-reduce over NVLink peer memory ---------------------------------------------------------
+ * One process per GPU, ONE bag (cost object) per process.  The joint objective is sum_bags NID
+ * (visual_camera_calibration.cpp:105-110): with an exchange attached, the finalizing block of every evaluation stores its
+ * scores into every peer's mailbox (P2P stores, cudaIpc-shared buffers), waits for the peers' and adds the contributions
+ * in rank order, so vlcal_nid_evaluate / _wait return the SUM OVER RANKS, identical bits on every rank, without a
+ * separate collective.  All ranks must evaluate the same number of poses in the same order (Nelder-Mead does).
+ *   1. every rank: vlcal_nid_p2p_create(device, rank, world, &px, handle)   (handle: 64 bytes out)
+ *   2. exchange the 64-byte handles between the ranks (e.g. torch.distributed.all_gather), concatenate in rank order
+ *   3. every rank: vlcal_nid_p2p_connect(px, all_handles);   4. vlcal_nid_p2p_attach(ctx, px) on each new context */
+typedef struct vlcal_p2p vlcal_p2p;
+int vlcal_nid_p2p_create(int device, int rank, int world, vlcal_p2p** out, void* ipc_handle_out);
+int vlcal_nid_p2p_connect(vlcal_p2p* px, const void* all_handles);
+int vlcal_nid_p2p_attach(vlcal_nid_ctx* ctx, vlcal_p2p* px); /* px == NULL detaches */
+void vlcal_nid_p2p_destroy(vlcal_p2p* px);
+/* contexts that vlcal_estimate_pose_nelder_mead / vlcal_calibrate_nelder_mead build internally attach this exchange when the
+ * process passes exactly one bag (then the allreduce callback is not used); NULL clears it */
+int vlcal_nid_p2p_set_default(vlcal_p2p* px);
+
 /* ---- view culling: ViewCulling::cull (src/vlcal/calib/view_culling.cpp:21-92) ------------
  * GPU z-buffer hidden-point removal at pose T.  indices_out: capacity n_points int32, receives the kept
  * original indices in ascending order; *n_kept their count.  max_fov_rad < 0 -> estimate_camera_fov. */

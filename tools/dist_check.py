@@ -32,6 +32,21 @@ def allreduce(vals):
 
 mine = V.CostCalculatorNID(cam, V.VisualLiDARData(bags[rank]["image"], bags[rank]["points"], bags[rank]["intensities"]), device=local)
 T, r = VC.estimate_pose_on_costs([mine], T0, params, allreduce=allreduce)
+
+# fused in-kernel exchange over peer memory must reproduce the NCCL-callback result bit for bit
+from direct_visual_lidar_calibration_b200.distributed import PeerExchange
+
+px = PeerExchange(local, rank, world)
+px.connect_with_torch()
+mine.attach_peer_exchange(px)
+Tp, rp = VC.estimate_pose_on_costs([mine], T0, params)
+mine.attach_peer_exchange(None)
+same_p2p = np.array_equal(Tp, T) and rp["num_iterations"] == r["num_iterations"] and rp["y"] == r["y"]
+flags = torch.tensor([1.0 if same_p2p else 0.0], device="cuda")
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"P2P_CHECK world={world} fused_equals_nccl={bool(flags.item())} y_p2p={rp['y']:.15f} y_nccl={r['y']:.15f}")
+assert flags.item() == 1.0, "fused peer exchange diverged from the NCCL path"
 out = torch.from_numpy(np.concatenate([T.reshape(-1), r["x"], [r["y"], r["num_iterations"], r["num_evaluations"]]])).cuda()
 gathered = [torch.zeros_like(out) for _ in range(world)]
 dist.all_gather(gathered, out)
@@ -44,4 +59,5 @@ if rank == 0:
     print(f"DIST_CHECK world={world} identical={same} close={close} iters={r['num_iterations']} y={r['y']:.12f} y_single={r1['y']:.12f}")
     assert close and r1["num_iterations"] == r["num_iterations"]
 dist.barrier()
+px.close()
 dist.destroy_process_group()
