@@ -13,8 +13,11 @@ counting the evaluations the serial reference would have made (speculatively sco
   --impl reference : the CPU oracle (line-by-line restatement of the reference, oracle/vlcal_oracle.c) on a bounded
           sample of the same step (the reference itself cannot be compiled in this image: no Eigen/OpenCV/GTSAM)
 
-N > 1 (torchrun, one rank per GPU): weak scaling over bags -- rank r owns bag r, the joint objective sum_bags NID is
-formed by one NCCL all-reduce of the P candidate scores per Nelder-Mead batch (visual_camera_calibration.cpp:105-110).
+N > 1 (torchrun, one rank per GPU): weak scaling over bags -- rank r owns bag r and the joint objective sum_bags NID
+(visual_camera_calibration.cpp:105-110) is formed INSIDE the histogram kernel: the finalizing block of every rank
+stores its P candidate scores into every peer's cudaIpc-shared mailbox over NVLink, waits for the peers' and adds them
+in rank order (--exchange p2p, default; torch.distributed/NCCL only bootstraps the handles and the timing barrier).
+--exchange nccl does one NCCL all-reduce per Nelder-Mead batch from the host callback instead (A/B).
 """
 import argparse
 import json
