@@ -185,7 +185,7 @@ struct FastCam {
   float fx, fy, cx, cy, xi;
   float d[8];
   // error-bound constants (fast_filter.hpp), SAFETY folded in
-  float a1, a2, a3;      // |k1|, |k2|, |k3|  (numerator of the radial factor)
+  float a1, a2, a3, a4;  // |k1|, |k2|, |k3| (numerator of the radial factor) / fisheye |k1..k4|
   float b1, b2, b3;      // |k4|, |k5|, |k6|  (denominator, rational model)
   float p3, p4;          // 3(|p1|+|p2|), 4(|p1|+|p2|)
   float sfx, sfy;        // SAFETY * |fx|, SAFETY * |fy|
@@ -251,8 +251,91 @@ __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float 
     Eu = fmaf(c.sfx, e, c.cu);
     Ev = fmaf(c.sfy, e, c.cv);
     return ok;
-  } else {
-    return false;
+  } else if constexpr (MODEL == CAM_EQUIRECTANGULAR) {
+    // u = W (0.5 + atan2(x, z) / 2pi),  v = H (0.5 + asin(y/|p|) / pi)   (equirectangular.hpp:21-27)
+    const float rxz2 = fmaf(pcx, pcx, pcz * pcz);
+    const float inv_rxz = rsqrtf(rxz2);
+    const float rxz = rxz2 * inv_rxz;
+    const float inv_n = __fdividef(1.0f, nrm);
+    const float lon = atan2f(pcx, pcz);
+    const float asn = asinf(pcy * inv_n);
+    u = c.fx * fmaf(lon, 0.15915494309189535f, 0.5f);  // c.fx = W, c.fy = H
+    v = c.fy * fmaf(asn, 0.3183098861837907f, 0.5f);
+    // |d lon| <= sqrt(2) delta / (rxz - 2 delta) + atan2f error (<= 8u pi);  |d asin| <= |d(y/|p|)| * |p| / rxz + asinf error
+    const float t_lon = 1.5f * delta * inv_rxz;
+    const float t_by = fmaf(2.9f * delta, inv_n, 4.0f * F32_U);
+    const float t_asn = 1.03f * t_by * nrm * inv_rxz;
+    Eu = fmaf(c.sfx, t_lon, c.cu);  // sfx = S W / 2pi, cu = S (W/2pi * 8u pi + 4u W)
+    Ev = fmaf(c.sfy, t_asn, c.cv);  // sfy = S H / pi,  cv = S (H/pi * 8u + 4u H)
+    // away from the |p|^2 < 1e-3 branch (:15), from the poles and from the seam's ill-conditioning
+    return (nrm * nrm > 2e-3f) && (rxz > 40.0f * delta) && (rxz > 0.05f * nrm);
+  } else if constexpr (MODEL == CAM_FISHEYE) {
+    // theta = atan2(r, |z|), theta_d = theta (1 + k1 th^2 + ... + k4 th^8), uv = f theta_d (x, y)/r + c  (fisheye.hpp:15-35)
+    const float r2 = fmaf(pcx, pcx, pcy * pcy);
+    const float inv_r = rsqrtf(r2);
+    const float r = r2 * inv_r;
+    const float theta = atan2f(r, fabsf(pcz));
+    const float t2 = theta * theta;
+    const float poly = fmaf(t2, fmaf(t2, fmaf(t2, fmaf(t2, c.d[3], c.d[2]), c.d[1]), c.d[0]), 1.0f);
+    const float s = theta * poly * inv_r;
+    u = fmaf(c.fx, s * pcx, c.cx);
+    v = fmaf(c.fy, s * pcy, c.cy);
+    const float t2b = fmaf(t2, 1.002f, 1e-6f);
+    const float pm = fmaf(t2b, fmaf(t2b, fmaf(t2b, fmaf(t2b, c.a4, c.a3), c.a2), c.a1), 1.0f);                             // >= |poly|
+    const float pd = fmaf(t2b, fmaf(t2b, fmaf(t2b, fmaf(t2b, 9.0f * c.a4, 7.0f * c.a3), 5.0f * c.a2), 3.0f * c.a1), 1.0f);  // >= |d theta_d / d theta|
+    // |d(theta_d x / r)| <= (2 pd + 8 pm) delta / |p| + (9 pd + 19 pm) u     (DESIGN.md / fast_filter.hpp)
+    const float e = fmaf(fmaf(2.0f, pd, 8.0f * pm), delta * __fdividef(1.0f, nrm), fmaf(9.0f, pd, 19.0f * pm) * F32_U);
+    Eu = fmaf(c.sfx, e, c.cu);
+    Ev = fmaf(c.sfy, e, c.cv);
+    return (r > 8.0f * delta) && (nrm > 40.0f * delta);  // r -> 0 is the reference's NaN corner (theta_d / r)
+  } else if constexpr (MODEL == CAM_OMNIDIR) {
+    // s = p/|p|, m = (sx, sy)/(sz + xi), plumb-bob style distortion with (k1, k2, p1, p2)   (omnidir.hpp:25-40)
+    const float inv_n = __fdividef(1.0f, nrm);
+    const float sx = pcx * inv_n, sy = pcy * inv_n, sz = pcz * inv_n;
+    const float D = sz + c.xi;
+    const float inv_d = __fdividef(1.0f, D);
+    const float x = sx * inv_d, y = sy * inv_d;
+    const float x2 = x * x, y2 = y * y, xy = x * y;
+    const float r2 = x2 + y2;
+    const float dr = fmaf(r2, fmaf(r2, c.d[1], c.d[0]), 1.0f);
+    const float p1 = c.d[2], p2 = c.d[3];
+    const float nx = fmaf(x, dr, fmaf(2.0f * p1, xy, p2 * fmaf(2.0f, x2, r2)));
+    const float ny = fmaf(y, dr, fmaf(2.0f * p2, xy, p1 * fmaf(2.0f, y2, r2)));
+    u = fmaf(c.fx, nx, c.cx);
+    v = fmaf(c.fy, ny, c.cy);
+    const float r2b = fmaf(r2, 1.001f, 1e-6f);
+    const float mh = fmaf(0.5f, r2b, 0.5f);
+    const float L = fmaf(r2b, fmaf(r2b, fmaf(r2b, c.l3, c.l2), c.l1), c.l0);
+    const float M16 = fmaf(r2b, fmaf(r2b, fmaf(r2b, fmaf(r2b, c.m4, c.m3), c.m2), c.m1), c.m0);
+    const float es = fmaf(2.9f * delta, inv_n, 3.0f * F32_U);                       // per-component error of the unit vector
+    const float exy = fmaf(1.12f * es * inv_d, 1.0f + mh, (4.0f * F32_U) * mh);     // |m_fp32 - m|
+    const float e = fmaf(L, exy, M16);
+    Eu = fmaf(c.sfx, e, c.cu);
+    Ev = fmaf(c.sfy, e, c.cv);
+    return (D > 0.1f) && (nrm > 40.0f * delta);
+  } else {  // CAM_ATAN
+    // pt = (x, y)/z; r < 1e-3 or d0 < 1e-7: identity, else pt * atan(r * 2 tan(d0/2)) / (d0 r)   (atan.hpp:14-38)
+    const float inv = __fdividef(1.0f, pcz);
+    const float x = pcx * inv, y = pcy * inv;
+    const float r2 = fmaf(x, x, y * y);
+    const float inv_r = rsqrtf(r2);
+    const float r = r2 * inv_r;
+    const float mh = fmaf(0.5f, r2, 0.5f) * 1.001f;
+    const float rho = delta * inv;
+    const float exy = fmaf(rho, 1.0f + mh, (4.0f * F32_U) * mh);
+    float factor = 1.0f;
+    bool ok = true;
+    if (c.aux0 > 0.0f) {  // distortion active (d0 >= 1e-7): aux0 = 1/d0, aux1 = 2 tan(d0/2)
+      const bool small = r < 1e-3f;
+      ok = fabsf(r - 1e-3f) > fmaf(4.0f, exy, 1e-7f);  // the branch is a (tiny) discontinuity: never straddle it
+      factor = small ? 1.0f : c.aux0 * atanf(r * c.aux1) * inv_r;
+    }
+    u = fmaf(c.fx, factor * x, c.cx);
+    v = fmaf(c.fy, factor * y, c.cy);
+    const float e = fmaf(c.l0, exy, c.m0 * mh);  // l0 = 1.5 max(1, d1 d2) (Lipschitz), m0 = 8u max(1, d1 d2)
+    Eu = fmaf(c.sfx, e, c.cu);
+    Ev = fmaf(c.sfy, e, c.cv);
+    return ok;
   }
 }
 

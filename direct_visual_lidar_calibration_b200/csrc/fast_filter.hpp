@@ -63,6 +63,57 @@ inline FastCam make_fast_cam(const CameraParams& cam, int width, int height, dou
     }
     f.enabled = 1;
   }
+  const double Wd = width, Hd = height;
+  if (cam.model == CAM_EQUIRECTANGULAR) {
+    // intr = [W, H] (the projection scales by the intrinsics, not by the image size passed to the cost)
+    const double W = std::fabs(cam.intr[0]), H = std::fabs(cam.intr[1]);
+    f.fx = static_cast<float>(cam.intr[0]);
+    f.fy = static_cast<float>(cam.intr[1]);
+    f.sfx = up(SAFETY * W / (2.0 * M_PI));
+    f.sfy = up(SAFETY * H / M_PI);
+    f.cu = up(SAFETY * (W / (2.0 * M_PI) * 8.0 * U * M_PI + 4.0 * U * (W + Wd + 1.0)));
+    f.cv = up(SAFETY * (H / M_PI * 8.0 * U + 4.0 * U * (H + Hd + 1.0)));
+    f.enabled = 1;
+  } else if (cam.model == CAM_FISHEYE) {
+    const double* d = cam.dist;
+    f.a1 = up(std::fabs(d[0])), f.a2 = up(std::fabs(d[1])), f.a3 = up(std::fabs(d[2])), f.a4 = up(std::fabs(d[3]));
+    f.sfx = up(SAFETY * std::fabs(cam.intr[0]));
+    f.sfy = up(SAFETY * std::fabs(cam.intr[1]));
+    f.cu = up(SAFETY * 4.0 * U * (Wd + std::fabs(cam.intr[2]) + 1.0));
+    f.cv = up(SAFETY * 4.0 * U * (Hd + std::fabs(cam.intr[3]) + 1.0));
+    f.enabled = 1;
+  } else if (cam.model == CAM_OMNIDIR) {
+    const double* d = cam.dist;
+    const double a1 = std::fabs(d[0]), a2 = std::fabs(d[1]), P = std::fabs(d[2]) + std::fabs(d[3]);
+    const double p3 = 3.0 * P, p4 = 4.0 * P;
+    f.l0 = up(1.0 + p4), f.l1 = up(4.0 * a1 + p4), f.l2 = up(7.0 * a2), f.l3 = 0.0f;
+    const double s16 = 16.0 * U;
+    f.m0 = up(s16 * 0.5), f.m1 = up(s16 * (0.5 + 0.5 * a1 + p3)), f.m2 = up(s16 * 0.5 * (a1 + a2)), f.m3 = up(s16 * 0.5 * a2), f.m4 = 0.0f;
+    f.sfx = up(SAFETY * std::fabs(cam.intr[0]));
+    f.sfy = up(SAFETY * std::fabs(cam.intr[1]));
+    f.cu = up(SAFETY * 4.0 * U * (Wd + std::fabs(cam.intr[2]) + 1.0));
+    f.cv = up(SAFETY * 4.0 * U * (Hd + std::fabs(cam.intr[3]) + 1.0));
+    f.enabled = 1;
+  } else if (cam.model == CAM_ATAN) {
+    if (!(cos_fov >= 0.05)) return f;  // pinhole division
+    const double d0 = cam.dist[0];
+    double G = 1.0;
+    f.aux0 = 0.0f, f.aux1 = 0.0f;
+    if (!(d0 < 1e-7)) {  // atan.hpp:17 (second operand): distortion active
+      const double d1 = 1.0 / d0, d2 = 2.0 * std::tan(d0 / 2.0);
+      if (!(std::isfinite(d1) && std::isfinite(d2)) || d1 <= 0.0 || d2 <= 0.0) return f;
+      f.aux0 = static_cast<float>(d1);
+      f.aux1 = static_cast<float>(d2);
+      G = std::max(1.0, d1 * d2);
+    }
+    f.l0 = up(1.5 * G);
+    f.m0 = up(8.0 * U * G);
+    f.sfx = up(SAFETY * std::fabs(cam.intr[0]));
+    f.sfy = up(SAFETY * std::fabs(cam.intr[1]));
+    f.cu = up(SAFETY * 4.0 * U * (Wd + std::fabs(cam.intr[2]) + 1.0));
+    f.cv = up(SAFETY * 4.0 * U * (Hd + std::fabs(cam.intr[3]) + 1.0));
+    f.enabled = 1;
+  }
   return f;
 }
 
