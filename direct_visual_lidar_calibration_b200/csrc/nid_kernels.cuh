@@ -379,15 +379,107 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __gri
 
 constexpr int NID_QUEUE = 64;  // per-warp queue of (point, pose) pairs waiting for the exact path
 
+// per-warp state of the filter kernel's hot loop
+struct FilterWarp {
+  int* my_hist;            // this warp's histogram copy [P][nb]
+  unsigned int* q_idx;     // [NID_QUEUE] deferred point indices
+  unsigned char* q_pose;   // [NID_QUEUE] deferred pose slots
+  int qn;                  // queue fill, warp-uniform
+  int lane;
+  unsigned int lt_mask;
+};
+
+template <int MODEL>
+__device__ __forceinline__ void filter_drain32(const NidArgs& a, FilterWarp& w, const float4* __restrict__ pts, int first, int count) {
+  if (w.lane < count) {  // entries [first, first+count), count <= 32: one deferred (point, pose) per lane, exact path
+    const unsigned int i = w.q_idx[first + w.lane];
+    const int p = w.q_pose[first + w.lane];
+    const float4 q = __ldg(pts + i);
+    const int ib = classify_exact<MODEL>(a, a.pose[p], q.x, q.y, q.z);
+    if (ib >= 0) atomicAdd(&w.my_hist[p * a.nb + ib + lidar_bin_of(q.w, a.bins) * a.bins], 1);
+  }
+}
+
+// one tile = 32*K consecutive points starting at `tile` (K per lane, warp-coalesced rows), swept over all P poses.
+// Software pipeline over the poses: the image-bin gathers of pose p are issued unconditionally (clamped address), stay
+// in flight while pose p+1 is classified, and are consumed by the histogram atomics one iteration later.
+template <int MODEL, int K>
+__device__ __forceinline__ void filter_tile(const NidArgs& a, FilterWarp& w, const float4* __restrict__ pts, unsigned int tile, unsigned int end) {
+  float px[K], py[K], pz[K], pa[K];
+  int lboff[K];
+  unsigned int idx[K];
+  unsigned int valid_bits = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    idx[j] = tile + j * 32 + w.lane;
+    const bool valid = idx[j] < end;
+    float4 q = make_float4(0.f, 0.f, -1.f, 0.f);
+    if (valid) q = __ldg(pts + idx[j]);
+    valid_bits |= (valid ? 1u : 0u) << j;
+    px[j] = q.x, py[j] = q.y, pz[j] = q.z;
+    pa[j] = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
+    lboff[j] = lidar_bin_of(q.w, a.bins) * a.bins;
+  }
+  int pend_bin[K];
+  unsigned int pend_ok = 0;
+  int* pend_hist = w.my_hist;
+  for (int p = 0; p <= a.n_poses; p++) {
+    int verdict[K];
+    unsigned int unc_bits = 0, ok_bits = 0;
+    if (p < a.n_poses) {
+      const float* __restrict__ P = a.pose32[p];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        int vd = classify_fast<MODEL>(a, P, px[j], py[j], pz[j], pa[j]);
+        vd = ((valid_bits >> j) & 1u) ? vd : VERDICT_REJECT;
+        verdict[j] = vd;
+        ok_bits |= (vd >= 0 ? 1u : 0u) << j;
+        unc_bits |= (vd == VERDICT_UNCERTAIN ? 1u : 0u) << j;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; j++) {  // consume the previous pose's gathers
+      if ((pend_ok >> j) & 1u) atomicAdd(&pend_hist[pend_bin[j] + lboff[j]], 1);  // :49 hist(image_bin, lidar_bin)++
+    }
+    pend_ok = ok_bits;
+    if (p < a.n_poses) {
+      pend_hist = w.my_hist + p * a.nb;
+#pragma unroll
+      for (int j = 0; j < K; j++) pend_bin[j] = __ldg(a.bin_image + max(verdict[j], 0));
+      if (__any_sync(0xffffffffu, unc_bits != 0)) {  // some lane deferred a point: queue it for the exact path
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          const bool mine = (unc_bits >> j) & 1u;
+          const unsigned int m = __ballot_sync(0xffffffffu, mine);
+          if (m) {
+            if (mine) {
+              const int pos = w.qn + __popc(m & w.lt_mask);
+              w.q_idx[pos] = idx[j];
+              w.q_pose[pos] = static_cast<unsigned char>(p);
+            }
+            w.qn += __popc(m);
+            __syncwarp();
+            if (w.qn >= 32) {
+              filter_drain32<MODEL>(a, w, pts, w.qn - 32, 32);
+              w.qn -= 32;
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // K1 (default): fp32 filter + exact fp64 recheck.
 // Every (point, pose) is first classified in fp32 together with a rigorous error bound; verdicts that are farther
 // than the bound from every decision edge (FoV cone, integer pixel boundaries, image border) are final.  The rest
 // (~2 %) are pushed on a per-warp shared-memory queue and re-decided 32 at a time by the exact double path, so the
 // fp64 pipe runs with full warps instead of diverging inside the hot loop.  The histogram is therefore bit-identical
 // to the all-fp64 kernel (tests/test_gpu_parity.py::test_filter_kernel_*).
-// Loop structure: each thread keeps NID_KPT points in registers (warp-coalesced 512-byte rows) and sweeps the P poses
-// over them, so the pose constants are fetched once per NID_KPT points and NID_KPT independent chains are in flight.
-// NID_KPT = points held in registers per thread while the poses are swept.
+// Work split: the cloud is cut into one contiguous, equally long range per warp (multiple of 32 points), processed as
+// NID_KPT-row tiles (NID_KPT points per lane in registers: pose constants fetched once per tile, NID_KPT independent
+// chains in flight) plus single-row tiles for the remainder, so no warp does a whole extra tile more than another.
 template <int MODEL, bool F32, int NID_KPT>
 __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __grid_constant__ NidArgs a) {
   extern __shared__ int smem_hist[];
@@ -399,95 +491,28 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned int lt_mask = (1u << lane) - 1u;
-  int* my_hist = smem_hist + (warp % a.copies) * per_copy;
+  const int warp = threadIdx.x >> 5;
+  FilterWarp w;
+  w.lane = threadIdx.x & 31;
+  w.lt_mask = (1u << w.lane) - 1u;
+  w.my_hist = smem_hist + (warp % a.copies) * per_copy;
+  w.q_idx = q_idx[warp];
+  w.q_pose = q_pose[warp];
+  w.qn = 0;
   const float4* __restrict__ pts = static_cast<const float4*>(a.points);
   const unsigned int n = static_cast<unsigned int>(a.n);  // host guarantees n < 2^31 for this kernel
-  int qn = 0;                                             // queue fill, warp-uniform
 
-  auto drain32 = [&](int first, int count) {  // entries [first, first+count), count <= 32
-    if (lane < count) {
-      const unsigned int i = q_idx[warp][first + lane];
-      const int p = q_pose[warp][first + lane];
-      const float4 q = __ldg(pts + i);
-      const int ib = classify_exact<MODEL>(a, a.pose[p], q.x, q.y, q.z);
-      if (ib >= 0) atomicAdd(&my_hist[p * a.nb + ib + lidar_bin_of(q.w, a.bins) * a.bins], 1);
-    }
-  };
-
-  constexpr unsigned int TILE = 32 * NID_KPT;
   const unsigned int warps_total = gridDim.x * (NID_THREADS / 32);
   const unsigned int warp_global = blockIdx.x * (NID_THREADS / 32) + warp;
-  for (unsigned long long tile = static_cast<unsigned long long>(warp_global) * TILE; tile < n; tile += static_cast<unsigned long long>(warps_total) * TILE) {
-    float px[NID_KPT], py[NID_KPT], pz[NID_KPT], pa[NID_KPT];
-    int lboff[NID_KPT];
-    unsigned int idx[NID_KPT];
-    unsigned int valid_bits = 0;
-#pragma unroll
-    for (int j = 0; j < NID_KPT; j++) {
-      idx[j] = static_cast<unsigned int>(tile) + j * 32 + lane;
-      const bool valid = idx[j] < n;
-      float4 q = make_float4(0.f, 0.f, -1.f, 0.f);
-      if (valid) q = __ldg(pts + idx[j]);
-      valid_bits |= (valid ? 1u : 0u) << j;
-      px[j] = q.x, py[j] = q.y, pz[j] = q.z;
-      pa[j] = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
-      lboff[j] = lidar_bin_of(q.w, a.bins) * a.bins;
-    }
-    // software pipeline over the poses: the image-bin gathers of pose p are issued unconditionally (clamped address),
-    // stay in flight while pose p+1 is classified, and are consumed by the histogram atomics one iteration later
-    int pend_bin[NID_KPT];
-    unsigned int pend_ok = 0;
-    int* pend_hist = my_hist;
-    for (int p = 0; p <= a.n_poses; p++) {
-      int verdict[NID_KPT];
-      unsigned int unc_bits = 0, ok_bits = 0;
-      if (p < a.n_poses) {
-        const float* __restrict__ P = a.pose32[p];
-#pragma unroll
-        for (int j = 0; j < NID_KPT; j++) {
-          int vd = classify_fast<MODEL>(a, P, px[j], py[j], pz[j], pa[j]);
-          vd = ((valid_bits >> j) & 1u) ? vd : VERDICT_REJECT;
-          verdict[j] = vd;
-          ok_bits |= (vd >= 0 ? 1u : 0u) << j;
-          unc_bits |= (vd == VERDICT_UNCERTAIN ? 1u : 0u) << j;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NID_KPT; j++) {  // consume the previous pose's gathers
-        if ((pend_ok >> j) & 1u) atomicAdd(&pend_hist[pend_bin[j] + lboff[j]], 1);  // :49 hist(image_bin, lidar_bin)++
-      }
-      pend_ok = ok_bits;
-      if (p < a.n_poses) {
-        pend_hist = my_hist + p * a.nb;
-#pragma unroll
-        for (int j = 0; j < NID_KPT; j++) pend_bin[j] = __ldg(a.bin_image + max(verdict[j], 0));
-        if (__any_sync(0xffffffffu, unc_bits != 0)) {  // some lane deferred a point: queue it for the exact path
-#pragma unroll
-          for (int j = 0; j < NID_KPT; j++) {
-            const bool mine = (unc_bits >> j) & 1u;
-            const unsigned int m = __ballot_sync(0xffffffffu, mine);
-            if (m) {
-              if (mine) {
-                const int pos = qn + __popc(m & lt_mask);
-                q_idx[warp][pos] = idx[j];
-                q_pose[warp][pos] = static_cast<unsigned char>(p);
-              }
-              qn += __popc(m);
-              __syncwarp();
-              if (qn >= 32) {
-                drain32(qn - 32, 32);
-                qn -= 32;
-                __syncwarp();
-              }
-            }
-          }
-        }
-      }
-    }
+  const unsigned int chunk = ((n + warps_total - 1) / warps_total + 31u) & ~31u;  // points per warp, multiple of 32
+  const unsigned long long lo = static_cast<unsigned long long>(warp_global) * chunk;
+  if (lo < n) {
+    const unsigned int end = static_cast<unsigned int>(min(static_cast<unsigned long long>(n), lo + chunk));
+    unsigned int t = static_cast<unsigned int>(lo);
+    for (; t + 32u * NID_KPT <= end; t += 32u * NID_KPT) filter_tile<MODEL, NID_KPT>(a, w, pts, t, end);
+    for (; t < end; t += 32u) filter_tile<MODEL, 1>(a, w, pts, t, end);
   }
-  if (qn > 0) drain32(0, qn);
+  if (w.qn > 0) filter_drain32<MODEL>(a, w, pts, 0, w.qn);
   nid_block_epilogue(a, smem_hist, &s_is_last);
 }
 
