@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 default, 1 exact-fp64 only)")
+    ap.add_argument("--no-tile-order", action="store_true", help="keep the cloud in input order (A/B for the tile-ordered layout)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused in-kernel peer-memory exchange (default) or NCCL all-reduce per batch")
     ap.add_argument("--ref-iterations", type=int, default=12, help="NM iterations per reference-arm step (bounded sample)")
     return ap.parse_args()
@@ -250,6 +251,8 @@ def main():
     culled = V.VisualLiDARData(bag["image"], data.points[idx], data.intensities[idx])
     cost = V.CostCalculatorNID(cam, culled, V.NIDCostParams(16), device=device)
     cost.set_kernel_variant(args.variant)
+    if not args.no_tile_order:
+        cost.reorder_for_pose(bag["T_init"])  # same grouping the e2e path gets from its culling pass
     if px is not None:
         cost.attach_peer_exchange(px)
         px.set_default(True)  # cost objects built inside the e2e call attach it too

@@ -123,6 +123,7 @@ def load_library():
     L.vlcal_nid_reset_profile.argtypes = [vp]
     L.vlcal_nid_set_kernel_variant.argtypes = [vp, C.c_int]
     L.vlcal_nid_debug_timeline.argtypes = [vp, dp, C.c_int, dp]
+    L.vlcal_nid_reorder_for_pose.argtypes = [vp, dp]
     L.vlcal_nid_filter_enabled.argtypes = [vp]
     L.vlcal_nid_debug_filter_check.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_uint64), dp]
     L.vlcal_nid_p2p_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp), vp]

@@ -96,6 +96,10 @@ class CostCalculatorNID:
     def points_are_f32(self) -> bool:
         return bool(self._L.vlcal_nid_points_are_f32(self._ctx))
 
+    def reorder_for_pose(self, T_camera_lidar):
+        """Group the cloud by projected image tile at this pose (values are unchanged; gathers coalesce)."""
+        _lib.check(self._L.vlcal_nid_reorder_for_pose(self._ctx, _dp(T_to_colmajor(T_camera_lidar))))
+
     def attach_peer_exchange(self, px):
         """Multi-GPU, one bag per rank: evaluations return the sum over ranks (fused in-kernel exchange)."""
         _lib.check(self._L.vlcal_nid_p2p_attach(self._ctx, px.handle if px is not None else None))

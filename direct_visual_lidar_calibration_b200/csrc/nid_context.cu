@@ -856,6 +856,29 @@ void vlcal_nid_p2p_destroy(vlcal_p2p* p) {
   delete p;
 }
 
+int vlcal_nid_reorder_for_pose(vlcal_nid_ctx* ctx, const double T_camera_lidar[16]) {
+  if (!ctx || !T_camera_lidar) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  if (ctx->in_flight) {
+    set_last_error("an evaluation is in flight on this context");
+    return VLCAL_ERR_BUSY;
+  }
+  VL_CUDA(cudaSetDevice(ctx->device));
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::shared_ptr<DeviceCloud> sorted;
+  int64_t kept = 0;
+  const int rc = view_cull_device(ctx->cam, ctx->image->width, ctx->image->height, ctx->max_fov, false, *ctx->cloud, T_camera_lidar, nullptr, &sorted, nullptr, &kept, /*keep_all=*/true);
+  if (rc != VLCAL_OK) return rc;
+  if (kept != ctx->cloud->n) {
+    set_last_error("reorder lost points");
+    return VLCAL_ERR_CUDA;
+  }
+  ctx->cloud = sorted;
+  return VLCAL_OK;
+}
+
 int vlcal_nid_trim_memory(void) {
   MemPool::instance().trim();
   return VLCAL_OK;

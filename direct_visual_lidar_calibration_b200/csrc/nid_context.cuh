@@ -52,7 +52,7 @@ int upload_image(int device, const uint8_t* image, int width, int height, int ro
 // GPU ViewCulling (view_culling.cpp:21-92): returns a compacted cloud and/or the kept indices
 int view_cull_device(
   const CameraParams& cam, int width, int height, double max_fov, bool depth_culling, const DeviceCloud& cloud, const double T[16], cudaStream_t stream,
-  std::shared_ptr<DeviceCloud>* culled_out, int32_t* indices_host_out, int64_t* n_kept);
+  std::shared_ptr<DeviceCloud>* culled_out, int32_t* indices_host_out, int64_t* n_kept, bool keep_all = false);
 
 struct ProfileEvents {
   cudaEvent_t start, stop;

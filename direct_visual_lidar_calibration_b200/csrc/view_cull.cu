@@ -28,6 +28,9 @@ struct CullArgs {
   int* pix;            // [n] iy*W+ix of candidates, -1 otherwise
   double* dist;        // [n] |pt_camera.head<3>()|
   int depth;
+  int tiles_x;         // image tiles of 32 x 8 pixels (tile-ordered compaction)
+  int n_tiles;
+  int keep_all;        // reorder mode: nothing is dropped, points outside the view go to one extra bucket
 };
 
 template <bool F32>
@@ -76,11 +79,41 @@ __global__ void __launch_bounds__(CULL_THREADS) cull_project_kernel(const __grid
 
 __device__ __forceinline__ bool cull_keep(const CullArgs& a, long long i) {
   if (i >= a.n) return false;
+  if (a.keep_all) return true;
   const int pix = a.pix[i];
   if (pix < 0) return false;
   if (!a.depth) return true;
   const double cell = static_cast<double>(__uint_as_float(a.zbuf[pix]));
   return !(a.dist[i] > __dadd_rn(cell, 0.1));  // :81
+}
+
+// ---- tile-ordered compaction (internal cost objects only) -----------------------------------------------------
+// The NID histogram is integer, hence invariant under any permutation of the cloud.  Kept points are therefore
+// written grouped by the 32x8-pixel image tile they project to at the culling pose (counting sort: per-tile counts,
+// scan, atomic cursors), so that the 32 lanes of a warp of the cost kernel gather their image bins from a handful
+// of 32-byte sectors instead of 32 scattered ones.  The public vlcal_view_cull keeps the reference's ascending order.
+__device__ __forceinline__ int cull_tile_of(const CullArgs& a, int pix) {
+  if (pix < 0) return a.n_tiles - 1;  // keep_all: not in view at this pose
+  const int iy = pix / a.width, ix = pix - iy * a.width;
+  return (iy >> 3) * a.tiles_x + (ix >> 5);
+}
+
+__global__ void __launch_bounds__(CULL_THREADS) cull_tile_count_kernel(const __grid_constant__ CullArgs a, int* tile_counts) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cull_keep(a, i)) atomicAdd(&tile_counts[cull_tile_of(a, a.pix[i])], 1);
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(CULL_THREADS) cull_tile_scatter_kernel(const __grid_constant__ CullArgs a, const int* tile_offsets, int* tile_cursor, void* points_out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (!cull_keep(a, i)) return;
+  const int tile = cull_tile_of(a, a.pix[i]);
+  const int dst = tile_offsets[tile] + atomicAdd(&tile_cursor[tile], 1);
+  if constexpr (F32) {
+    static_cast<float4*>(points_out)[dst] = static_cast<const float4*>(a.points)[i];
+  } else {
+    static_cast<double4*>(points_out)[dst] = static_cast<const double4*>(a.points)[i];
+  }
 }
 
 __global__ void __launch_bounds__(CULL_THREADS) cull_count_kernel(const __grid_constant__ CullArgs a, int* block_counts) {
@@ -187,7 +220,7 @@ struct DevBuf {  // pooled scratch; returned to the pool after the culling pass 
 
 int view_cull_device(
   const CameraParams& cam, int width, int height, double max_fov, bool depth_culling, const DeviceCloud& cloud, const double T[16], cudaStream_t stream,
-  std::shared_ptr<DeviceCloud>* culled_out, int32_t* indices_host_out, int64_t* n_kept) {
+  std::shared_ptr<DeviceCloud>* culled_out, int32_t* indices_host_out, int64_t* n_kept, bool keep_all) {
   VL_CUDA(cudaSetDevice(cloud.device));
   const long long n = cloud.n;
   if (n == 0) {
@@ -209,7 +242,6 @@ int view_cull_device(
   VL_CUDA(zbuf.alloc(cloud.device, sizeof(unsigned int) * npix));
   VL_CUDA(pix.alloc(cloud.device, sizeof(int) * n));
   VL_CUDA(dist.alloc(cloud.device, sizeof(double) * n));
-  VL_CUDA(counts.alloc(cloud.device, sizeof(int) * num_blocks));
   VL_CUDA(total.alloc(cloud.device, sizeof(long long)));
   // :40 dist_map filled with cv::Scalar(DBL_MAX) -> saturates to +inf in CV_32F
   fill_u32_kernel<<<static_cast<unsigned int>((npix + 255) / 256), 256, 0, stream>>>(static_cast<unsigned int*>(zbuf.p), npix, 0x7f800000u);
@@ -228,14 +260,31 @@ int view_cull_device(
   a.zbuf = static_cast<unsigned int*>(zbuf.p);
   a.pix = static_cast<int*>(pix.p);
   a.dist = static_cast<double*>(dist.p);
-  a.depth = depth_culling ? 1 : 0;
+  a.depth = (depth_culling && !keep_all) ? 1 : 0;
+  a.keep_all = keep_all ? 1 : 0;
 
   CullProjectKernel project = pick_cull_kernel(cam.model, cloud.f32);
   project<<<num_blocks, CULL_THREADS, 0, stream>>>(a);
   VL_CUDA(cudaGetLastError());
-  cull_count_kernel<<<num_blocks, CULL_THREADS, 0, stream>>>(a, static_cast<int*>(counts.p));
+
+  const bool by_tile = culled_out != nullptr && indices_host_out == nullptr;  // internal cost object: order is free
+  DevBuf cursor;
+  int num_counts = num_blocks;
+  if (by_tile) {
+    a.tiles_x = (width + 31) / 32;
+    num_counts = a.tiles_x * ((height + 7) / 8) + 1;  // + the out-of-view bucket of keep_all
+    a.n_tiles = num_counts;
+    VL_CUDA(counts.alloc(cloud.device, sizeof(int) * num_counts));
+    VL_CUDA(cursor.alloc(cloud.device, sizeof(int) * num_counts));
+    VL_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int) * num_counts, stream));
+    VL_CUDA(cudaMemsetAsync(cursor.p, 0, sizeof(int) * num_counts, stream));
+    cull_tile_count_kernel<<<num_blocks, CULL_THREADS, 0, stream>>>(a, static_cast<int*>(counts.p));
+  } else {
+    VL_CUDA(counts.alloc(cloud.device, sizeof(int) * num_counts));
+    cull_count_kernel<<<num_blocks, CULL_THREADS, 0, stream>>>(a, static_cast<int*>(counts.p));
+  }
   VL_CUDA(cudaGetLastError());
-  cull_scan_kernel<<<1, 1024, 0, stream>>>(static_cast<int*>(counts.p), num_blocks, static_cast<long long*>(total.p));
+  cull_scan_kernel<<<1, 1024, 0, stream>>>(static_cast<int*>(counts.p), num_counts, static_cast<long long*>(total.p));
   VL_CUDA(cudaGetLastError());
   long long kept = 0;
   VL_CUDA(cudaMemcpyAsync(&kept, total.p, sizeof(long long), cudaMemcpyDeviceToHost, stream));
@@ -250,7 +299,15 @@ int view_cull_device(
     if (kept > 0) VL_CUDA(MemPool::instance().device_alloc(cloud.device, static_cast<size_t>(kept) * culled->bytes_per_point(), &culled->d_points));
   }
   if (indices_host_out && kept > 0) VL_CUDA(idx.alloc(cloud.device, sizeof(int) * kept));
-  if (kept > 0 && (culled_out || indices_host_out)) {
+  if (kept > 0 && by_tile) {
+    if (cloud.f32) {
+      cull_tile_scatter_kernel<true><<<num_blocks, CULL_THREADS, 0, stream>>>(a, static_cast<int*>(counts.p), static_cast<int*>(cursor.p), culled->d_points);
+    } else {
+      cull_tile_scatter_kernel<false><<<num_blocks, CULL_THREADS, 0, stream>>>(a, static_cast<int*>(counts.p), static_cast<int*>(cursor.p), culled->d_points);
+    }
+    VL_CUDA(cudaGetLastError());
+    VL_CUDA(cudaStreamSynchronize(stream));
+  } else if (kept > 0 && (culled_out || indices_host_out)) {
     if (cloud.f32) {
       cull_scatter_kernel<true><<<num_blocks, CULL_THREADS, 0, stream>>>(a, static_cast<int*>(counts.p), static_cast<int*>(idx.p), culled ? culled->d_points : nullptr);
     } else {
@@ -304,5 +361,5 @@ extern "C" int vlcal_view_cull(
   std::shared_ptr<DeviceCloud> cloud;
   rc = upload_cloud(device, points_xyzw, zeros.data(), n_points, nullptr, &cloud);
   if (rc != VLCAL_OK) return rc;
-  return view_cull_device(cam, width, height, max_fov_rad, enable_depth_buffer_culling != 0, *cloud, T_camera_lidar, nullptr, nullptr, indices_out, n_kept);
+  return view_cull_device(cam, width, height, max_fov_rad, enable_depth_buffer_culling != 0, *cloud, T_camera_lidar, nullptr, nullptr, indices_out, n_kept, false);
 }

@@ -159,6 +159,17 @@ def test_edge_cases(gpu, oracle):
         V.CostCalculatorNID(cam, bad)
 
 
+def test_reorder_for_pose_changes_nothing_but_the_order(gpu, oracle):
+    pr = util.random_problem("plumb_bob", n=50000, seed=13)
+    Ts = util.random_poses(pr["T"], 6, seed=2)
+    cost = _cost(gpu, pr)
+    nid0, hist0 = cost.calculate_batch(Ts, return_hist=True)
+    cost.reorder_for_pose(Ts[0])
+    nid1, hist1 = cost.calculate_batch(Ts, return_hist=True)
+    assert np.array_equal(hist0, hist1) and np.array_equal(nid0, nid1, equal_nan=True)
+    assert np.array_equal(hist1, _oracle_eval(oracle, pr, Ts)[1])
+
+
 def test_permutation_invariance(gpu):
     pr = util.random_problem("fisheye", n=40000, seed=12)
     perm = np.random.default_rng(1).permutation(40000)
@@ -405,3 +416,22 @@ def test_bspline_other_bins_and_failure_flag(gpu, oracle):
     ok, nid = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], far * [1, 1, 1, 1] + [1e4, 0, 0, 0], np.full(10, 0.5)), 16).evaluate(_sophus_params(T)[None])
     rok, _, _ = oracle.nid_cost_bspline(ocam, pr["image"], far + [1e4, 0, 0, 0], np.full(10, 0.5), 16, _sophus_params(T))
     assert (not ok[0]) and (not rok)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-GPU: fused bag all-reduce over NVLink peer memory (needs >= 2 GPUs on the box; skipped otherwise)
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def test_fused_peer_exchange_matches_nccl_and_single_gpu(gpu):
+    import subprocess
+    import sys
+
+    if gpu.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`); tools/gpu_multi.sh records the result in profiles/")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "dist_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "P2P_CHECK world=2 fused_equals_nccl=True" in out.stdout
+    assert "DIST_CHECK world=2 identical=True close=True" in out.stdout
