@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 default, 1 exact-fp64 only)")
     ap.add_argument("--no-tile-order", action="store_true", help="keep the cloud in input order (A/B for the tile-ordered layout)")
+    ap.add_argument("--solver", default="auto", choices=["auto", "host", "device"], help="inner-solve loop: device-resident (auto when possible) or host-driven")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused in-kernel peer-memory exchange (default) or NCCL all-reduce per batch")
     ap.add_argument("--ref-iterations", type=int, default=12, help="NM iterations per reference-arm step (bounded sample)")
     return ap.parse_args()
@@ -213,6 +214,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = local_rank
+    V.set_solver_mode({"auto": 0, "host": 1, "device": 2}[args.solver])
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -354,7 +356,7 @@ def main():
         "config": {
             "workload": WORKLOAD, "points": data.size(), "culled_points": n_culled, "image": f"{W}x{H}", "bags": world, "parallelism": f"bags{world}" if world > 1 else "single", "exchange": (args.exchange if world > 1 else None),
             "l2": "flushed (256 MiB write) between steps; within a step the culled cloud is re-read every NM iteration by the algorithm itself",
-            "kernel_variant": args.variant,
+            "kernel_variant": args.variant, "solver": args.solver,
         },
         "evals_per_step": evals_ref / args.steps, "evals_computed_per_step": evals_cmp / args.steps, "batches_per_step": batches / args.steps,
         "mpoints_per_s": mpoints, "wall_s_timed_region": wall,

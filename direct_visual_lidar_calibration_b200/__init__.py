@@ -14,7 +14,7 @@ this package is the thin host-side mirror of the reference's interface for that 
 
 There is no CPU fallback: without the built library or without a CUDA device every compute call raises.
 """
-from ._lib import VlcalError, build_library, device_count, library_path, load_library
+from ._lib import VlcalError, build_library, device_count, library_path, load_library, set_solver_mode
 from .camera import GenericCamera, create_camera
 from .cost import CostCalculatorNID, NIDCost, NIDCostParams, VisualLiDARData
 from .culling import ViewCulling, ViewCullingParams
@@ -22,7 +22,7 @@ from .nelder_mead import NelderMead, NelderMeadParams
 from .calibration import RegistrationType, VisualCameraCalibration, VisualCameraCalibrationParams, estimate_camera_fov, se3_expmap
 
 __all__ = [
-    "VlcalError", "build_library", "device_count", "library_path", "load_library",
+    "VlcalError", "build_library", "device_count", "library_path", "load_library", "set_solver_mode",
     "GenericCamera", "create_camera",
     "CostCalculatorNID", "NIDCost", "NIDCostParams", "VisualLiDARData",
     "ViewCulling", "ViewCullingParams",

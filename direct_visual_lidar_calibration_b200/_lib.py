@@ -132,6 +132,7 @@ def load_library():
     L.vlcal_nid_p2p_destroy.argtypes = [vp]
     L.vlcal_nid_p2p_destroy.restype = None
     L.vlcal_nid_p2p_set_default.argtypes = [vp]
+    L.vlcal_nid_set_solver_mode.argtypes = [C.c_int]
     L.vlcal_view_cull.argtypes = [C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int64, dp, vp, C.POINTER(C.c_int64)]
     L.vlcal_nm_default_params.argtypes = [C.POINTER(NMParams)]
     L.vlcal_nm_default_params.restype = None
@@ -150,6 +151,11 @@ def check(rc: int):
     if rc != OK:
         msg = load_library().vlcal_nid_last_error().decode(errors="replace")
         raise VlcalError(rc, msg)
+
+
+def set_solver_mode(mode: int):
+    """0 auto, 1 host loop, 2 device-resident loop (see include/vlcal_nid.h)."""
+    check(load_library().vlcal_nid_set_solver_mode(int(mode)))
 
 
 def device_count() -> int:

@@ -394,6 +394,65 @@ static void fill_pose32(NidArgs& a, int pc) {
   }
 }
 
+// everything of NidArgs that does not depend on the batch
+static void fill_common_args(vlcal_nid_ctx* ctx, NidArgs& a) {
+  std::memset(&a, 0, sizeof(a));
+  a.points = ctx->cloud->d_points;
+  a.bin_image = ctx->d_bin_image;
+  a.n = ctx->cloud->n;
+  a.width = ctx->image->width;
+  a.height = ctx->image->height;
+  a.bins = ctx->bins;
+  a.nb = ctx->bins * ctx->bins;
+  a.cos_fov = ctx->cos_fov;
+  a.cam = ctx->cam;
+  a.fast = ctx->fast;
+  a.timeline = ctx->h_timeline;
+  if (ctx->p2p && ctx->p2p->connected && ctx->p2p->world > 1) {
+    for (int r = 0; r < ctx->p2p->world; r++) a.peer_box[r] = ctx->p2p->peers[r];
+    a.p2p_world = ctx->p2p->world;
+    a.p2p_rank = ctx->p2p->rank;
+    a.p2p_counter = ctx->p2p->d_counter;
+    a.p2p_error = ctx->p2p->h_error;
+  }
+  a.ghist = ctx->d_ghist;
+  a.counter = ctx->d_counter;
+}
+
+static NidKernel select_kernel(vlcal_nid_ctx* ctx) {
+  // the fp32 filter needs the float4 layout, a camera/FoV it has bounds for, and 32-bit point indices
+  const bool use_filter = ctx->variant != 1 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
+  return pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? (ctx->variant == 2 ? 3 : 0) : 1);
+}
+
+static int launch_one(vlcal_nid_ctx* ctx, NidKernel kernel, NidArgs& a, int geometry_poses, int profile_poses) {
+  LaunchGeom g{1, 0, 1};
+  {
+    const int rc = launch_geometry(kernel, geometry_poses, a.nb, &g);
+    if (rc != VLCAL_OK) return rc;
+  }
+  a.copies = g.copies;
+  const long long want_blocks = (a.n + NID_THREADS - 1) / NID_THREADS;
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want_blocks, static_cast<long long>(ctx->num_sms) * g.blocks_per_sm)));
+  ProfileEvents* ev = nullptr;
+  if (ctx->profiling) {
+    if (ctx->events_used == ctx->events.size()) {
+      ProfileEvents e;
+      VL_CUDA(cudaEventCreate(&e.start));
+      VL_CUDA(cudaEventCreate(&e.stop));
+      e.poses = 0;
+      ctx->events.push_back(e);
+    }
+    ev = &ctx->events[ctx->events_used++];
+    ev->poses = profile_poses;
+    VL_CUDA(cudaEventRecord(ev->start, ctx->stream));
+  }
+  kernel<<<grid, NID_THREADS, g.smem, ctx->stream>>>(a);
+  VL_CUDA(cudaGetLastError());
+  if (ev) VL_CUDA(cudaEventRecord(ev->stop, ctx->stream));
+  return VLCAL_OK;
+}
+
 int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses, bool want_hist) {
   if (ctx->in_flight) {
     set_last_error("an evaluation is already in flight on this context");
@@ -409,78 +468,79 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
     if (rc != VLCAL_OK) return rc;
   }
   const int nb = ctx->bins * ctx->bins;
-  // the fp32 filter needs the float4 layout, a camera/FoV it has bounds for, and 32-bit point indices
-  const bool use_filter = ctx->variant != 1 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
-  NidKernel kernel = pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? (ctx->variant == 2 ? 3 : 0) : 1);
+  NidKernel kernel = select_kernel(ctx);
   for (int p0 = 0; p0 < n_poses; p0 += ctx->max_poses) {
     const int pc = std::min(ctx->max_poses, n_poses - p0);
     NidArgs a;
-    std::memset(&a, 0, sizeof(a));
-    a.points = ctx->cloud->d_points;
-    a.bin_image = ctx->d_bin_image;
-    a.n = ctx->cloud->n;
-    a.width = ctx->image->width;
-    a.height = ctx->image->height;
-    a.bins = ctx->bins;
-    a.nb = nb;
+    fill_common_args(ctx, a);
     a.n_poses = pc;
-    a.cos_fov = ctx->cos_fov;
-    a.cam = ctx->cam;
     for (int p = 0; p < pc; p++) {
       const double* T = T_colmajor + 16 * static_cast<size_t>(p0 + p);
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 4; c++) a.pose[p][4 * r + c] = T[r + 4 * c];
     }
     fill_pose32(a, pc);
-    a.fast = ctx->fast;
-    a.timeline = ctx->h_timeline;
-    if (ctx->p2p && ctx->p2p->connected && ctx->p2p->world > 1) {
-      for (int r = 0; r < ctx->p2p->world; r++) a.peer_box[r] = ctx->p2p->peers[r];
-      a.p2p_world = ctx->p2p->world;
-      a.p2p_rank = ctx->p2p->rank;
-      a.p2p_seq = ++ctx->p2p->seq;
-      a.p2p_error = ctx->p2p->h_error;
-    }
-    a.ghist = ctx->d_ghist;
-    a.counter = ctx->d_counter;
     a.nid_out = ctx->d_nid + p0;
     a.nid_host = ctx->h_nid + p0;  // UVA: pinned host memory is directly addressable from the device
     const bool last_chunk = p0 + pc >= n_poses;
     a.done_flag = last_chunk ? ctx->h_flag : nullptr;
     a.done_seq = ctx->seq + 1;
     a.hist_out = want_hist ? ctx->d_hist_out + static_cast<size_t>(p0) * nb : nullptr;
-
-    LaunchGeom g{1, 0, 1};
-    {
-      const int rc = launch_geometry(kernel, pc, nb, &g);
-      if (rc != VLCAL_OK) return rc;
-    }
-    a.copies = g.copies;
-    const long long want_blocks = (a.n + NID_THREADS - 1) / NID_THREADS;
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want_blocks, static_cast<long long>(ctx->num_sms) * g.blocks_per_sm)));
-
-    ProfileEvents* ev = nullptr;
-    if (ctx->profiling) {
-      if (ctx->events_used == ctx->events.size()) {
-        ProfileEvents e;
-        VL_CUDA(cudaEventCreate(&e.start));
-        VL_CUDA(cudaEventCreate(&e.stop));
-        e.poses = 0;
-        ctx->events.push_back(e);
-      }
-      ev = &ctx->events[ctx->events_used++];
-      ev->poses = pc;
-      VL_CUDA(cudaEventRecord(ev->start, ctx->stream));
-    }
-    kernel<<<grid, NID_THREADS, g.smem, ctx->stream>>>(a);
-    VL_CUDA(cudaGetLastError());
-    if (ev) VL_CUDA(cudaEventRecord(ev->stop, ctx->stream));
+    const int rc = launch_one(ctx, kernel, a, pc, pc);
+    if (rc != VLCAL_OK) return rc;
     ctx->launches++;
     ctx->poses_total += pc;
   }
   ctx->seq += 1;
   ctx->in_flight = true;
   ctx->in_flight_poses = n_poses;
+  return VLCAL_OK;
+}
+
+int nid_enqueue_device_steps(vlcal_nid_ctx* ctx, NmDevice* d_nm, int count) {
+  if (ctx->in_flight) {
+    set_last_error("an evaluation is in flight on this context");
+    return VLCAL_ERR_BUSY;
+  }
+  if (ctx->mode != VLCAL_NID_MODE_HISTOGRAM) {
+    set_last_error("device-resident solver loop needs a histogram-mode context");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  VL_CUDA(cudaSetDevice(ctx->device));
+  {
+    const int rc = ensure_outputs(ctx, NID_MAX_POSES, false);
+    if (rc != VLCAL_OK) return rc;
+  }
+  if (ctx->max_poses < NID_MAX_POSES) {
+    set_last_error("device-resident solver loop needs room for 8 poses per launch (bins too large)");
+    return VLCAL_ERR_UNSUPPORTED;
+  }
+  NidKernel kernel = select_kernel(ctx);
+  NidArgs a;
+  fill_common_args(ctx, a);
+  a.nm = d_nm;
+  a.n_poses = 0;
+  a.nid_out = ctx->d_nid;
+  for (int k = 0; k < count; k++) {
+    const int rc = launch_one(ctx, kernel, a, NID_MAX_POSES, 0);
+    if (rc != VLCAL_OK) return rc;
+  }
+  return VLCAL_OK;
+}
+
+int nid_account_device_steps(vlcal_nid_ctx* ctx, int enqueued, int worked, int poses) {
+  // events of the launches that found the solver finished (exit at once) are dropped, the others accumulated
+  if (ctx->profiling) {
+    const size_t first = ctx->events_used - static_cast<size_t>(enqueued);
+    for (int k = 0; k < worked; k++) {
+      float ms = 0.f;
+      VL_CUDA(cudaEventElapsedTime(&ms, ctx->events[first + k].start, ctx->events[first + k].stop));
+      ctx->kernel_ms_accum += ms;
+    }
+    ctx->events_used = first;
+  }
+  ctx->launches += worked;
+  ctx->poses_total += poses;
   return VLCAL_OK;
 }
 
@@ -802,6 +862,8 @@ int vlcal_nid_p2p_create(int device, int rank, int world, vlcal_p2p** out, void*
   p->device = device, p->rank = rank, p->world = world;
   VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->local), sizeof(P2PMailbox)));  // own allocation: cudaIpc shares whole allocations
   VL_CUDA(cudaMemset(p->local, 0, sizeof(P2PMailbox)));
+  VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_counter), sizeof(unsigned long long)));
+  VL_CUDA(cudaMemset(p->d_counter, 0, sizeof(unsigned long long)));
   VL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p->h_error), sizeof(int), cudaHostAllocDefault));
   *p->h_error = 0;
   cudaIpcMemHandle_t h;
@@ -852,6 +914,7 @@ void vlcal_nid_p2p_destroy(vlcal_p2p* p) {
     if (r != p->rank && p->peers[r]) cudaIpcCloseMemHandle(p->peers[r]);
   }
   if (p->local) cudaFree(p->local);
+  if (p->d_counter) cudaFree(p->d_counter);
   if (p->h_error) cudaFreeHost(p->h_error);
   delete p;
 }

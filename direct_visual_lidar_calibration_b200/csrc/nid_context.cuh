@@ -71,7 +71,7 @@ struct vlcal_p2p {
   vlcal::P2PMailbox* local = nullptr;
   vlcal::P2PMailbox* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool connected = false;
-  unsigned long long seq = 0;
+  unsigned long long* d_counter = nullptr;  // device word: exchanges done (advanced by the kernels)
   int* h_error = nullptr;  // pinned + mapped
 };
 
@@ -124,4 +124,9 @@ int nid_ctx_create(
   int device, int mode, const CameraParams& cam, std::shared_ptr<DeviceImage> image, std::shared_ptr<DeviceCloud> cloud, int bins, double max_fov, vlcal_nid_ctx** out);
 int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses, bool want_hist);
 int nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out);
+struct NmDevice;
+// device-resident solver loop: enqueue `count` launches that read their poses from / advance `d_nm`; no waiting
+int nid_enqueue_device_steps(vlcal_nid_ctx* ctx, NmDevice* d_nm, int count);
+// after the stream was synchronised: account the first `worked` launches of the last enqueue in the profile
+int nid_account_device_steps(vlcal_nid_ctx* ctx, int enqueued, int worked, int poses);
 }  // namespace vlcal

@@ -16,6 +16,8 @@
 #include <cstdint>
 
 #include "camera_models.cuh"
+#include "nm_machine.cuh"
+#include "se3_math.cuh"
 
 namespace vlcal {
 
@@ -35,6 +37,31 @@ struct P2PMailbox {
   unsigned long long seq[P2P_MAX_RANKS][2];  // [sender][slot]
 };
 
+// ---- device-resident Nelder-Mead loop ---------------------------------------------------------------------
+// With NidArgs::nm set, a launch takes its candidate poses from this block of device memory instead of from its kernel
+// parameters, and the finalizing block -- once the scores of the batch are known -- advances the Nelder-Mead state
+// machine (nm_machine.cuh) and writes the NEXT batch of poses T = init_T * Expmap(x) back into it.  The host can then
+// enqueue many launches back to back without waiting for any of them: the per-iteration host round trip (launch
+// latency + PCIe + wake-up, ~10 us of a ~40 us iteration) disappears from the critical path.  Launches enqueued after
+// the solver finished see n_poses == 0 and exit at once.
+struct NmDevice {
+  NmMachine nm;
+  double init_T[16];                    // column-major start pose (visual_camera_calibration.cpp:104)
+  double pose[NID_MAX_POSES][12];       // pending batch: row-major 3x4 [R|t]
+  float pose32[NID_MAX_POSES][16];      // fp32 filter copy (R, t, max|t|)
+  int n_poses;                          // poses of the pending batch; 0 once finished
+  int trace_cap, trace_count;           // reference-order evaluations (x[6], y) for callback replay on the host
+  double* trace;
+  unsigned long long steps_done;
+};
+
+// where a launch reads its poses from (kernel parameters or NmDevice)
+struct PoseView {
+  int n_poses;
+  const double (*pose)[12];
+  const float (*pose32)[16];
+};
+
 struct NidArgs {
   const void* points;        // float4[n] (x,y,z,intensity) or double4[n]
   const uint8_t* bin_image;  // H x W image bins: clamp(int(u8/255.0*bins), 0, bins-1)  (:43,:46)
@@ -51,8 +78,10 @@ struct NidArgs {
   unsigned long long* dbg;         // verify kernel only: {point-poses, uncertain, mismatches, max ratio bits}
   P2PMailbox* peer_box[P2P_MAX_RANKS];  // peer_box[r]: rank r's mailbox as mapped in this process (self included)
   int p2p_world, p2p_rank;         // p2p_world <= 1: no exchange
-  unsigned long long p2p_seq;
   int* p2p_error;                  // mapped host word, set to 1 if a peer never answered
+  unsigned long long* p2p_counter; // device word: number of exchanges done (kept on the device so that it only advances
+                                   // when an exchange really happens -- launches that exit early do not consume a slot)
+  NmDevice* nm;                    // device-resident solver loop (nullptr: poses come from the kernel parameters)
   unsigned long long* timeline;    // optional [16] mapped host words: globaltimer stamps of the launch (vlcal_nid_debug_timeline)
   int* ghist;                 // [NID_MAX_POSES][nb] global accumulators, zero on entry, zero on exit
   unsigned int* counter;      // block ticket, zero on entry, zero on exit
@@ -62,6 +91,20 @@ struct NidArgs {
   unsigned long long done_seq;
   int* hist_out;              // optional [n_poses][nb], index = image_bin + lidar_bin*bins
 };
+
+__device__ __forceinline__ PoseView make_pose_view(const NidArgs& a) {
+  PoseView v;
+  if (a.nm) {
+    v.n_poses = a.nm->n_poses;
+    v.pose = a.nm->pose;
+    v.pose32 = a.nm->pose32;
+  } else {
+    v.n_poses = a.n_poses;
+    v.pose = a.pose;
+    v.pose32 = a.pose32;
+  }
+  return v;
+}
 
 // ---- exact decision for one (point, pose): pixel index iy*W+ix (>= 0), or -1 if the reference skips the point
 template <int MODEL>
@@ -176,22 +219,26 @@ __device__ __forceinline__ double warp_tree_sum(double v) {
 }
 
 // called by the finalizing block after every pose's local score sits in a.nid_out (block-synchronised)
-static __device__ void nid_peer_allreduce(const NidArgs& a) {
-  const int slot = static_cast<int>(a.p2p_seq & 1ull);
+static __device__ void nid_peer_allreduce(const NidArgs& a, const PoseView& pv) {
+  __shared__ unsigned long long s_seq;
   const int t = threadIdx.x;
-  if (t < a.n_poses * a.p2p_world) {  // one thread per (peer, pose): remote stores over NVLink
-    const int g = t / a.n_poses, p = t % a.n_poses;
+  if (t == 0) s_seq = ++(*a.p2p_counter);  // every rank performs the same sequence of exchanges
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int slot = static_cast<int>(seq & 1ull);
+  if (t < pv.n_poses * a.p2p_world) {  // one thread per (peer, pose): remote stores over NVLink
+    const int g = t / pv.n_poses, p = t % pv.n_poses;
     a.peer_box[g]->vals[a.p2p_rank][slot][p] = a.nid_out[p];
     __threadfence_system();
   }
   __syncthreads();
   if (t < a.p2p_world) {  // sequence word after the payload (system-scope fence above orders them)
-    *reinterpret_cast<volatile unsigned long long*>(&a.peer_box[t]->seq[a.p2p_rank][slot]) = a.p2p_seq;
+    *reinterpret_cast<volatile unsigned long long*>(&a.peer_box[t]->seq[a.p2p_rank][slot]) = seq;
     // wait for rank t's contribution to land in OUR mailbox
     volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(&a.peer_box[a.p2p_rank]->seq[t][slot]);
     const unsigned long long t0 = global_ns();
     unsigned int spins = 0;
-    while (*w != a.p2p_seq) {
+    while (*w != seq) {
       if ((++spins & 1023u) == 0 && global_ns() - t0 > 2000000000ull) {  // 2 s: a peer died or fell out of lockstep
         if (a.p2p_error) *a.p2p_error = 1;
         break;
@@ -200,7 +247,7 @@ static __device__ void nid_peer_allreduce(const NidArgs& a) {
     __threadfence_system();
   }
   __syncthreads();
-  if (t < a.n_poses) {
+  if (t < pv.n_poses) {
     double total = 0.0;
     for (int r = 0; r < a.p2p_world; r++) total += __ldcv(&a.peer_box[a.p2p_rank]->vals[r][slot][t]);  // rank order: identical on every rank
     a.nid_out[t] = total;
@@ -209,18 +256,57 @@ static __device__ void nid_peer_allreduce(const NidArgs& a) {
   __syncthreads();
 }
 
-static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
+// T = init_T * Expmap(x) for candidate k of the pending batch (visual_camera_calibration.cpp:104) -> pose / pose32 slots
+VL_HD void nm_pose_of_candidate(NmDevice* nm, int k) {
+  double E[16], T[16];
+  se3_expmap_gtsam_hd(&nm->nm.cand[k][1], E);
+  isometry_mul_hd(nm->init_T, E, T);
+  double tmax = 0.0;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 4; c++) nm->pose[k][4 * r + c] = T[r + 4 * c];
+    for (int c = 0; c < 3; c++) nm->pose32[k][3 * r + c] = static_cast<float>(T[r + 4 * c]);
+    nm->pose32[k][9 + r] = static_cast<float>(T[r + 12]);
+    tmax = fmax(tmax, fabs(T[r + 12]));
+  }
+  nm->pose32[k][12] = nextafterf(static_cast<float>(tmax), INFINITY);  // max|t| rounded up (fp32 filter bound)
+  nm->pose32[k][13] = nm->pose32[k][14] = nm->pose32[k][15] = 0.f;
+}
+
+// device-resident solver loop: consume the scores of the batch, advance the state machine, emit the next poses
+static __device__ void nm_device_advance(const NidArgs& a) {
+  NmDevice* nm = a.nm;
+  if (threadIdx.x == 0) {
+    nm->nm.step(a.nid_out);
+    const int n = nm->nm.n;
+    for (int k = 0; k < nm->nm.n_obs; k++) {  // reference-order evaluations, replayed by the host for params.callback
+      if (nm->trace_count < nm->trace_cap) {
+        double* e = nm->trace + static_cast<size_t>(nm->trace_count) * (NM_MAX_N + 1);
+        for (int d = 0; d < n; d++) e[d] = nm->nm.obs_x[k][d];
+        e[NM_MAX_N] = nm->nm.obs_y[k];
+      }
+      nm->trace_count++;
+    }
+    nm->steps_done++;
+  }
+  __syncthreads();
+  const int n_next = nm->nm.n_cand;  // 0 when finished
+  if (threadIdx.x < n_next) nm_pose_of_candidate(nm, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x == 0) nm->n_poses = n_next;
+}
+
+static __device__ void nid_finalize(const NidArgs& a, const PoseView& pv, int* smem_i) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   __shared__ int s_cnt[NID_THREADS / 32];  // per-warp partial inlier counts
   // splitting a pose over several warps needs staging room: the block's histogram copies provide it when copies >= 4
-  const int wpp = a.copies >= 4 ? max(1, n_warps / a.n_poses) : 1;  // warps per pose
+  const int wpp = a.copies >= 4 ? max(1, n_warps / pv.n_poses) : 1;  // warps per pose
   const int ppr = n_warps / wpp;                                     // poses per round
   double* s_term = reinterpret_cast<double*>(smem_i);                // [ppr][nb] staged p*log(p+1e-6) terms (wpp > 1)
   int* s_marg = smem_i + (wpp > 1 ? 2 * ppr * a.nb : 0);             // [ppr][2*bins] marginal counts
-  for (int p0 = 0; p0 < a.n_poses; p0 += ppr) {
+  for (int p0 = 0; p0 < pv.n_poses; p0 += ppr) {
     const int slot = warp / wpp, sub = warp % wpp;  // pose slot of this warp within the round, rank within the pose
     const int p = p0 + slot;
-    const bool active = slot < ppr && p < a.n_poses;
+    const bool active = slot < ppr && p < pv.n_poses;
     int* h_image = s_marg + slot * 2 * a.bins;  // [bins]
     int* h_points = h_image + a.bins;           // [bins]
     for (int i = threadIdx.x; i < ppr * 2 * a.bins; i += blockDim.x) s_marg[i] = 0;
@@ -306,7 +392,8 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
     }
     __syncthreads();
   }
-  if (a.p2p_world > 1) nid_peer_allreduce(a);
+  if (a.p2p_world > 1) nid_peer_allreduce(a, pv);
+  if (a.nm) nm_device_advance(a);
   stamp(a, 4);
   if (threadIdx.x == 0) {
     *a.counter = 0u;
@@ -319,8 +406,8 @@ static __device__ void nid_finalize(const NidArgs& a, int* smem_i) {
 }
 
 // block epilogue shared by the histogram kernels: merge copies -> global accumulators -> last block finalizes
-__device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, int* smem_hist, bool* s_is_last) {
-  const int per_copy = a.n_poses * a.nb;
+__device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, const PoseView& pv, int* smem_hist, bool* s_is_last) {
+  const int per_copy = pv.n_poses * a.nb;
   const unsigned long long t_main = a.timeline ? global_ns() : 0ull;
   __syncthreads();
   for (int k = threadIdx.x; k < per_copy; k += blockDim.x) {
@@ -343,14 +430,16 @@ __device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, int* smem_h
     a.timeline[3] = global_ns();
   }
   __threadfence();
-  nid_finalize(a, smem_hist);
+  nid_finalize(a, pv, smem_hist);
 }
 
 template <int MODEL, bool F32>
 __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __grid_constant__ NidArgs a) {
   extern __shared__ int smem_hist[];
   __shared__ bool s_is_last;
-  const int per_copy = a.n_poses * a.nb;
+  const PoseView pv = make_pose_view(a);
+  if (pv.n_poses == 0) return;  // device-resident loop: the solver has finished
+  const int per_copy = pv.n_poses * a.nb;
   if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
@@ -367,14 +456,14 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __gri
       x = q.x, y = q.y, z = q.z, w = q.w;
     }
     const int lb = lidar_bin_of(w, a.bins);
-    for (int p = 0; p < a.n_poses; p++) {
-      const int ib = classify_exact<MODEL>(a, a.pose[p], x, y, z);
+    for (int p = 0; p < pv.n_poses; p++) {
+      const int ib = classify_exact<MODEL>(a, pv.pose[p], x, y, z);
       if (ib >= 0) {
         atomicAdd(&my_hist[p * a.nb + ib + lb * a.bins], 1);  // :49 hist(image_bin, lidar_bin)++
       }
     }
   }
-  nid_block_epilogue(a, smem_hist, &s_is_last);
+  nid_block_epilogue(a, pv, smem_hist, &s_is_last);
 }
 
 constexpr int NID_QUEUE = 64;  // per-warp queue of (point, pose) pairs waiting for the exact path
@@ -390,12 +479,12 @@ struct FilterWarp {
 };
 
 template <int MODEL>
-__device__ __forceinline__ void filter_drain32(const NidArgs& a, FilterWarp& w, const float4* __restrict__ pts, int first, int count) {
+__device__ __forceinline__ void filter_drain32(const NidArgs& a, const PoseView& pv, FilterWarp& w, const float4* __restrict__ pts, int first, int count) {
   if (w.lane < count) {  // entries [first, first+count), count <= 32: one deferred (point, pose) per lane, exact path
     const unsigned int i = w.q_idx[first + w.lane];
     const int p = w.q_pose[first + w.lane];
     const float4 q = __ldg(pts + i);
-    const int ib = classify_exact<MODEL>(a, a.pose[p], q.x, q.y, q.z);
+    const int ib = classify_exact<MODEL>(a, pv.pose[p], q.x, q.y, q.z);
     if (ib >= 0) atomicAdd(&w.my_hist[p * a.nb + ib + lidar_bin_of(q.w, a.bins) * a.bins], 1);
   }
 }
@@ -404,7 +493,7 @@ __device__ __forceinline__ void filter_drain32(const NidArgs& a, FilterWarp& w, 
 // Software pipeline over the poses: the image-bin gathers of pose p are issued unconditionally (clamped address), stay
 // in flight while pose p+1 is classified, and are consumed by the histogram atomics one iteration later.
 template <int MODEL, int K>
-__device__ __forceinline__ void filter_tile(const NidArgs& a, FilterWarp& w, const float4* __restrict__ pts, unsigned int tile, unsigned int end) {
+__device__ __forceinline__ void filter_tile(const NidArgs& a, const PoseView& pv, FilterWarp& w, const float4* __restrict__ pts, unsigned int tile, unsigned int end) {
   float px[K], py[K], pz[K], pa[K];
   int lboff[K];
   unsigned int idx[K];
@@ -423,11 +512,11 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, FilterWarp& w, con
   int pend_bin[K];
   unsigned int pend_ok = 0;
   int* pend_hist = w.my_hist;
-  for (int p = 0; p <= a.n_poses; p++) {
+  for (int p = 0; p <= pv.n_poses; p++) {
     int verdict[K];
     unsigned int unc_bits = 0, ok_bits = 0;
-    if (p < a.n_poses) {
-      const float* __restrict__ P = a.pose32[p];
+    if (p < pv.n_poses) {
+      const float* __restrict__ P = pv.pose32[p];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         int vd = classify_fast<MODEL>(a, P, px[j], py[j], pz[j], pa[j]);
@@ -442,7 +531,7 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, FilterWarp& w, con
       if ((pend_ok >> j) & 1u) atomicAdd(&pend_hist[pend_bin[j] + lboff[j]], 1);  // :49 hist(image_bin, lidar_bin)++
     }
     pend_ok = ok_bits;
-    if (p < a.n_poses) {
+    if (p < pv.n_poses) {
       pend_hist = w.my_hist + p * a.nb;
 #pragma unroll
       for (int j = 0; j < K; j++) pend_bin[j] = __ldg(a.bin_image + max(verdict[j], 0));
@@ -460,7 +549,7 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, FilterWarp& w, con
             w.qn += __popc(m);
             __syncwarp();
             if (w.qn >= 32) {
-              filter_drain32<MODEL>(a, w, pts, w.qn - 32, 32);
+              filter_drain32<MODEL>(a, pv, w, pts, w.qn - 32, 32);
               w.qn -= 32;
               __syncwarp();
             }
@@ -487,7 +576,9 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   __shared__ unsigned int q_idx[NID_THREADS / 32][NID_QUEUE];
   __shared__ unsigned char q_pose[NID_THREADS / 32][NID_QUEUE];
   static_assert(F32, "the fp32 filter runs on the float4 cloud layout");
-  const int per_copy = a.n_poses * a.nb;
+  const PoseView pv = make_pose_view(a);
+  if (pv.n_poses == 0) return;  // device-resident loop: the solver has finished
+  const int per_copy = pv.n_poses * a.nb;
   if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
@@ -509,11 +600,11 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   if (lo < n) {
     const unsigned int end = static_cast<unsigned int>(min(static_cast<unsigned long long>(n), lo + chunk));
     unsigned int t = static_cast<unsigned int>(lo);
-    for (; t + 32u * NID_KPT <= end; t += 32u * NID_KPT) filter_tile<MODEL, NID_KPT>(a, w, pts, t, end);
-    for (; t < end; t += 32u) filter_tile<MODEL, 1>(a, w, pts, t, end);
+    for (; t + 32u * NID_KPT <= end; t += 32u * NID_KPT) filter_tile<MODEL, NID_KPT>(a, pv, w, pts, t, end);
+    for (; t < end; t += 32u) filter_tile<MODEL, 1>(a, pv, w, pts, t, end);
   }
-  if (w.qn > 0) filter_drain32<MODEL>(a, w, pts, 0, w.qn);
-  nid_block_epilogue(a, smem_hist, &s_is_last);
+  if (w.qn > 0) filter_drain32<MODEL>(a, pv, w, pts, 0, w.qn);
+  nid_block_epilogue(a, pv, smem_hist, &s_is_last);
 }
 
 // debug / test kernel: runs BOTH paths on every (point, pose) and counts, in a.dbg:

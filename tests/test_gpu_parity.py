@@ -229,6 +229,63 @@ def test_inner_solve_follows_oracle_evaluation_by_evaluation(gpu, oracle):
     assert calib.stats["total_batches"] < ref["num_evaluations"]  # batched: fewer launches than evaluations
 
 
+def test_device_resident_loop_equals_host_loop_and_oracle(gpu, oracle):
+    """The Nelder-Mead state machine advanced inside the kernel's finalizing block (solver mode 2) must walk exactly the
+    trajectory of the host loop (mode 1) and of the oracle: same x, y, iterations, evaluations, callback sequence."""
+    V = gpu
+    bag = _synthetic_bag(40000, cfg=6)
+    cam = V.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    data = V.VisualLiDARData(bag["image"], bag["points"], bag["intensities"])
+    params = V.VisualCameraCalibrationParams()
+    params.max_inner_iterations = 100
+    out = {}
+    try:
+        for mode in (1, 2):
+            V.set_solver_mode(mode)
+            calib = V.VisualCameraCalibration(cam, [data], params)
+            T, r = calib.estimate_pose_nelder_mead(bag["T_init"])
+            out[mode] = (T, r, [c for _, c in calib.trace], calib.stats)
+    finally:
+        V.set_solver_mode(0)
+    (Th, rh, trh, sth), (Td, rd, trd, std) = out[1], out[2]
+    assert np.array_equal(Th, Td) and np.array_equal(rh["x"], rd["x"]) and rh["y"] == rd["y"]
+    assert rh["num_iterations"] == rd["num_iterations"] and rh["num_evaluations"] == rd["num_evaluations"] and rh["converged"] == rd["converged"]
+    assert rh["num_batches"] == rd["num_batches"] and rh["num_evaluations_computed"] == rd["num_evaluations_computed"]
+    assert trh == trd and len(trd) > 3
+    ocam = oracle.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    op = oracle.default_calib_params()
+    op.max_inner_iterations = 100
+    ref = oracle.estimate_pose_nelder_mead(ocam, [(bag["image"], bag["points"], bag["intensities"])], bag["T_init"], op)
+    assert np.array_equal(rd["x"], ref["x"]) and rd["num_iterations"] == ref["num_iterations"] and rd["num_evaluations"] == ref["num_evaluations"]
+    assert np.abs(Td - ref["T"]).max() == 0.0 and abs(rd["y"] - ref["y"]) < NID_TOL
+    # max_inner_iterations = 0: the loop body never runs, the result is the un-sorted x0 (nelder_mead.hpp:49,99)
+    params.max_inner_iterations = 0
+    try:
+        V.set_solver_mode(2)
+        T0, r0 = V.VisualCameraCalibration(cam, [data], params).estimate_pose_nelder_mead(bag["T_init"])
+    finally:
+        V.set_solver_mode(0)
+    assert r0["num_evaluations"] == 7 and np.array_equal(r0["x"], np.zeros(6)) and np.abs(T0 - bag["T_init"]).max() < 1e-15
+
+
+def test_device_resident_loop_full_calibrate_single_bag(gpu, oracle):
+    V = gpu
+    bag = _synthetic_bag(30000, cfg=8)
+    cam = V.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    ocam = oracle.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    params = V.VisualCameraCalibrationParams()
+    params.max_inner_iterations, params.max_outer_iterations = 50, 3
+    params.delta_trans_thresh, params.delta_rot_thresh = 1e-4, 1e-5
+    calib = V.VisualCameraCalibration(cam, [V.VisualLiDARData(bag["image"], bag["points"], bag["intensities"])], params)
+    T = calib.calibrate(bag["T_init"])  # auto mode -> device-resident loop (one bag)
+    op = oracle.default_calib_params()
+    op.max_inner_iterations, op.max_outer_iterations, op.delta_trans_thresh, op.delta_rot_thresh = 50, 3, 1e-4, 1e-5
+    ref = oracle.calibrate(ocam, [(bag["image"], bag["points"], bag["intensities"])], bag["T_init"], op)
+    assert calib.stats["outer_iterations"] == ref["outer_iterations"] and calib.stats["inner_iterations"] == ref["inner_iterations"]
+    assert calib.stats["total_evaluations"] == ref["total_evaluations"]
+    assert np.abs(T - ref["T"]).max() < 1e-15
+
+
 def test_full_calibrate_matches_oracle_two_bags(gpu, oracle):
     V = gpu
     b1, b2 = _synthetic_bag(30000, cfg=4), _synthetic_bag(25000, cfg=5)
