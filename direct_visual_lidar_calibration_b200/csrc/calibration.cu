@@ -116,7 +116,7 @@ int run_inner_solve_device(
   const double x0[6] = {0, 0, 0, 0, 0, 0};
   h->nm.begin(6, nm, x0);  // :126 optimize(f, Zero)
   std::memcpy(h->init_T, init_T, sizeof(h->init_T));
-  for (int k = 0; k < h->nm.n_cand; k++) nm_pose_of_candidate(h, k);
+  for (int k = 0; k < h->nm.n_cand; k++) nm_pose_of_candidate(h->nm.cand[k], h->init_T, h, k);
   h->n_poses = h->nm.n_cand;
   h->trace_cap = trace_cap;
   h->trace_count = 0;

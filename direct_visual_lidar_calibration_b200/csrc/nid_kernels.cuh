@@ -256,41 +256,59 @@ static __device__ void nid_peer_allreduce(const NidArgs& a, const PoseView& pv) 
   __syncthreads();
 }
 
-// T = init_T * Expmap(x) for candidate k of the pending batch (visual_camera_calibration.cpp:104) -> pose / pose32 slots
-VL_HD void nm_pose_of_candidate(NmDevice* nm, int k) {
+// T = init_T * Expmap(x) for one candidate of the pending batch (visual_camera_calibration.cpp:104) -> pose / pose32 slot k
+VL_HD void nm_pose_of_candidate(const double* cand_vertex, const double* init_T, NmDevice* out, int k) {
   double E[16], T[16];
-  se3_expmap_gtsam_hd(&nm->nm.cand[k][1], E);
-  isometry_mul_hd(nm->init_T, E, T);
+  se3_expmap_gtsam_hd(cand_vertex + 1, E);
+  isometry_mul_hd(init_T, E, T);
   double tmax = 0.0;
   for (int r = 0; r < 3; r++) {
-    for (int c = 0; c < 4; c++) nm->pose[k][4 * r + c] = T[r + 4 * c];
-    for (int c = 0; c < 3; c++) nm->pose32[k][3 * r + c] = static_cast<float>(T[r + 4 * c]);
-    nm->pose32[k][9 + r] = static_cast<float>(T[r + 12]);
+    for (int c = 0; c < 4; c++) out->pose[k][4 * r + c] = T[r + 4 * c];
+    for (int c = 0; c < 3; c++) out->pose32[k][3 * r + c] = static_cast<float>(T[r + 4 * c]);
+    out->pose32[k][9 + r] = static_cast<float>(T[r + 12]);
     tmax = fmax(tmax, fabs(T[r + 12]));
   }
-  nm->pose32[k][12] = nextafterf(static_cast<float>(tmax), INFINITY);  // max|t| rounded up (fp32 filter bound)
-  nm->pose32[k][13] = nm->pose32[k][14] = nm->pose32[k][15] = 0.f;
+  out->pose32[k][12] = nextafterf(static_cast<float>(tmax), INFINITY);  // max|t| rounded up (fp32 filter bound)
+  out->pose32[k][13] = out->pose32[k][14] = out->pose32[k][15] = 0.f;
 }
 
-// device-resident solver loop: consume the scores of the batch, advance the state machine, emit the next poses
+// device-resident solver loop: consume the scores of the batch, advance the state machine, emit the next poses.
+// The machine is staged in shared memory: stepping it in place in HBM would be hundreds of dependent L2 round trips.
 static __device__ void nm_device_advance(const NidArgs& a) {
+  static_assert(sizeof(NmMachine) % 8 == 0, "NmMachine is copied as 8-byte words");
+  __shared__ NmMachine s_nm;
+  __shared__ double s_init_T[16];
   NmDevice* nm = a.nm;
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&nm->nm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_nm);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(NmMachine) / 8); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 16) s_init_T[threadIdx.x] = nm->init_T[threadIdx.x];
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    nm->nm.step(a.nid_out);
-    const int n = nm->nm.n;
-    for (int k = 0; k < nm->nm.n_obs; k++) {  // reference-order evaluations, replayed by the host for params.callback
-      if (nm->trace_count < nm->trace_cap) {
-        double* e = nm->trace + static_cast<size_t>(nm->trace_count) * (NM_MAX_N + 1);
-        for (int d = 0; d < n; d++) e[d] = nm->nm.obs_x[k][d];
-        e[NM_MAX_N] = nm->nm.obs_y[k];
+    s_nm.step(a.nid_out);
+    const int n = s_nm.n;
+    int count = nm->trace_count;
+    for (int k = 0; k < s_nm.n_obs; k++) {  // reference-order evaluations, replayed by the host for params.callback
+      if (count < nm->trace_cap) {
+        double* e = nm->trace + static_cast<size_t>(count) * (NM_MAX_N + 1);
+        for (int d = 0; d < n; d++) e[d] = s_nm.obs_x[k][d];
+        e[NM_MAX_N] = s_nm.obs_y[k];
       }
-      nm->trace_count++;
+      count++;
     }
+    nm->trace_count = count;
     nm->steps_done++;
   }
   __syncthreads();
-  const int n_next = nm->nm.n_cand;  // 0 when finished
-  if (threadIdx.x < n_next) nm_pose_of_candidate(nm, threadIdx.x);
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_nm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&nm->nm);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(NmMachine) / 8); i += blockDim.x) dst[i] = src[i];
+  }
+  const int n_next = s_nm.n_cand;  // 0 when finished
+  if (threadIdx.x < n_next) nm_pose_of_candidate(s_nm.cand[threadIdx.x], s_init_T, nm, threadIdx.x);
   __syncthreads();
   if (threadIdx.x == 0) nm->n_poses = n_next;
 }
