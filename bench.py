@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 default, 1 exact-fp64 only)")
     ap.add_argument("--no-tile-order", action="store_true", help="keep the cloud in input order (A/B for the tile-ordered layout)")
-    ap.add_argument("--solver", default="auto", choices=["auto", "host", "device"], help="inner-solve loop: device-resident (auto when possible) or host-driven")
+    ap.add_argument("--solver", default="auto", choices=["auto", "host", "device"], help="inner-solve loop: host-driven (auto = host; measured faster) or device-resident")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused in-kernel peer-memory exchange (default) or NCCL all-reduce per batch")
     ap.add_argument("--ref-iterations", type=int, default=12, help="NM iterations per reference-arm step (bounded sample)")
     return ap.parse_args()

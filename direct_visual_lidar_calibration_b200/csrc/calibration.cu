@@ -190,7 +190,7 @@ int run_inner_solve(
     set_last_error("device-resident solver loop requested but this solve needs the host between batches (several local bags / host all-reduce / bins too large)");
     return VLCAL_ERR_UNSUPPORTED;
   }
-  if (device_ok && g_solver_mode != 1) {
+  if (device_ok && g_solver_mode == 2) {
     return run_inner_solve_device(ctxs[0], params, init_T, callback, user, T_out, nm_result);
   }
   PoseObjective obj;

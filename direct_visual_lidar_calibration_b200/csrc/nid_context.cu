@@ -425,6 +425,8 @@ static NidKernel select_kernel(vlcal_nid_ctx* ctx) {
   return pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? (ctx->variant == 2 ? 3 : 0) : 1);
 }
 
+constexpr int PROFILE_STRIDE = 4;
+
 static int launch_one(vlcal_nid_ctx* ctx, NidKernel kernel, NidArgs& a, int geometry_poses, int profile_poses) {
   LaunchGeom g{1, 0, 1};
   {
@@ -435,7 +437,8 @@ static int launch_one(vlcal_nid_ctx* ctx, NidKernel kernel, NidArgs& a, int geom
   const long long want_blocks = (a.n + NID_THREADS - 1) / NID_THREADS;
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want_blocks, static_cast<long long>(ctx->num_sms) * g.blocks_per_sm)));
   ProfileEvents* ev = nullptr;
-  if (ctx->profiling) {
+  // event pairs cost ~3 us of host time per launch on the Nelder-Mead critical path: sample one launch in four
+  if (ctx->profiling && (ctx->launch_counter++ % PROFILE_STRIDE) == 0) {
     if (ctx->events_used == ctx->events.size()) {
       ProfileEvents e;
       VL_CUDA(cudaEventCreate(&e.start));
@@ -529,13 +532,23 @@ int nid_enqueue_device_steps(vlcal_nid_ctx* ctx, NmDevice* d_nm, int count) {
 }
 
 int nid_account_device_steps(vlcal_nid_ctx* ctx, int enqueued, int worked, int poses) {
-  // events of the launches that found the solver finished (exit at once) are dropped, the others accumulated
+  // sampled events of this enqueue: keep those of launches that did work, drop the ones that found the solver finished
   if (ctx->profiling) {
-    const size_t first = ctx->events_used - static_cast<size_t>(enqueued);
-    for (int k = 0; k < worked; k++) {
-      float ms = 0.f;
-      VL_CUDA(cudaEventElapsedTime(&ms, ctx->events[first + k].start, ctx->events[first + k].stop));
-      ctx->kernel_ms_accum += ms;
+    const int64_t first_launch = ctx->launch_counter - enqueued;  // index of the first launch of this enqueue
+    int sampled = 0;
+    for (int k = 0; k < enqueued; k++)
+      if (((first_launch + k) % PROFILE_STRIDE) == 0) sampled++;
+    const size_t first = ctx->events_used - static_cast<size_t>(sampled);
+    int e = 0;
+    for (int k = 0; k < enqueued; k++) {
+      if (((first_launch + k) % PROFILE_STRIDE) != 0) continue;
+      if (k < worked) {
+        float ms = 0.f;
+        VL_CUDA(cudaEventElapsedTime(&ms, ctx->events[first + e].start, ctx->events[first + e].stop));
+        ctx->kernel_ms_accum += ms;
+        ctx->timed_launches++;
+      }
+      e++;
     }
     ctx->events_used = first;
   }
@@ -549,6 +562,7 @@ static int drain_profile(vlcal_nid_ctx* ctx) {
     float ms = 0.f;
     VL_CUDA(cudaEventElapsedTime(&ms, ctx->events[i].start, ctx->events[i].stop));
     ctx->kernel_ms_accum += ms;
+    ctx->timed_launches++;
   }
   ctx->events_used = 0;
   return VLCAL_OK;
@@ -793,7 +807,8 @@ int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* 
   const int rc = drain_profile(ctx);
   if (rc != VLCAL_OK) return rc;
   if (kernel_launches) *kernel_launches = ctx->launches;
-  if (kernel_ms_total) *kernel_ms_total = ctx->kernel_ms_accum;
+  // sampled launches are representative of the rest: report the total scaled to all launches
+  if (kernel_ms_total) *kernel_ms_total = ctx->timed_launches > 0 ? ctx->kernel_ms_accum * (static_cast<double>(ctx->launches) / ctx->timed_launches) : 0.0;
   if (poses_total) *poses_total = ctx->poses_total;
   return VLCAL_OK;
 }
@@ -804,6 +819,8 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
   VL_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->events_used = 0;
   ctx->launches = 0;
+  ctx->timed_launches = 0;
+  ctx->launch_counter = 0;
   ctx->poses_total = 0;
   ctx->kernel_ms_accum = 0.0;
   return VLCAL_OK;

@@ -113,6 +113,8 @@ struct vlcal_nid_ctx {
   std::vector<vlcal::ProfileEvents> events;
   size_t events_used = 0;
   int64_t launches = 0;
+  int64_t timed_launches = 0;  // launches bracketed by events (profiling samples 1 launch in PROFILE_STRIDE)
+  int64_t launch_counter = 0;
   int64_t poses_total = 0;
   double kernel_ms_accum = 0.0;
 

@@ -173,20 +173,15 @@ __device__ __forceinline__ int classify_fast(const NidArgs& a, const float* __re
   const bool fov_rej = g < 0.0f;
   float u, v, Eu, Ev;
   const bool proj_ok = project_fast<MODEL>(a.fast, pcx, pcy, pcz, nrm, delta, u, v, Eu, Ev);
-  const float wf = static_cast<float>(a.width), hf = static_cast<float>(a.height);
-  const bool bad = !proj_ok || !(Eu < 0.25f) || !(Ev < 0.25f);       // bound useless (or NaN)
-  const bool out = (u < -1.0f - Eu) || (u > wf + Eu) || (v < -1.0f - Ev) || (v > hf + Ev);  // certainly truncates outside
-  // an integer (truncation edge / image border) within the bound of either coordinate; NaN lands here
+  // an integer (truncation edge / image border) within the bound of either coordinate -> uncertain.  |c - rint(c)| <= 0.5,
+  // so a bound >= 0.5 (useless) or NaN lands here too, and a coordinate that is NOT near an integer truncates exactly
+  // like the reference's, wherever it lies: no separate far-outside test is needed.
   const bool edge = !(fabsf(u - rintf(u)) > Eu) || !(fabsf(v - rintf(v)) > Ev);
-  const int ix = __float2int_rz(u), iy = __float2int_rz(v);          // truncation toward zero, like cast<int>()
-  const bool inside = ix >= 0 && ix < a.width && iy >= 0 && iy < a.height;
-  int verdict = inside ? iy * a.width + ix : VERDICT_REJECT;
-  verdict = edge ? VERDICT_UNCERTAIN : verdict;
-  verdict = out ? VERDICT_REJECT : verdict;
-  verdict = bad ? VERDICT_UNCERTAIN : verdict;
-  verdict = fov_rej ? VERDICT_REJECT : verdict;
-  verdict = fov_unc ? VERDICT_UNCERTAIN : verdict;
-  return verdict;
+  const int ix = __float2int_rz(u), iy = __float2int_rz(v);  // truncation toward zero, like cast<int>()
+  const bool inside = static_cast<unsigned int>(ix) < static_cast<unsigned int>(a.width) && static_cast<unsigned int>(iy) < static_cast<unsigned int>(a.height);
+  const bool uncertain = fov_unc || (!fov_rej && (edge || !proj_ok));
+  const bool accept = !fov_unc && !fov_rej && !edge && proj_ok && inside;
+  return accept ? iy * a.width + ix : (uncertain ? VERDICT_UNCERTAIN : VERDICT_REJECT);
 }
 
 __device__ __forceinline__ int lidar_bin_of(double intensity, int bins) {

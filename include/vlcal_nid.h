@@ -203,11 +203,13 @@ int vlcal_view_cull(
 /* ---- solver surface ------------------------------------------------------------------ */
 
 /* how vlcal_estimate_pose_nelder_mead* / vlcal_calibrate_nelder_mead iterate (process-wide):
- *   0 auto (default): device-resident loop whenever the solve has one local bag (scores local or summed by the in-kernel peer
- *     exchange) -- the Nelder-Mead state machine advances inside the kernel's finalizing block and launches are enqueued
- *     back to back; otherwise the host loop.   1 host loop always.   2 device-resident loop or VLCAL_ERR_UNSUPPORTED.
- * Both loops run the same state machine (same trajectory); with the device loop params.callback is delivered from the
- * evaluation trace, in the reference's order, up to one chunk of launches late. */
+ *   0 / 1 host loop (default): one launch per Nelder-Mead batch, scores published to mapped host memory, host polls.
+ *   2 device-resident loop (one local bag; scores local or summed by the in-kernel peer exchange): the state machine
+ *     advances inside the kernel's finalizing block, launches are enqueued back to back; VLCAL_ERR_UNSUPPORTED otherwise.
+ * Both loops run the same state machine (bit-identical trajectory, tests/test_gpu_parity.py).  Measured on B200 at the C2
+ * size the host loop is the faster one (38 vs 48 us per batch: stepping the machine + Expmap on one SM costs more than the
+ * host round trip it removes), hence the default; with mode 2 params.callback is delivered from the evaluation trace, in
+ * the reference's order, up to one chunk of launches late. */
 int vlcal_nid_set_solver_mode(int mode);
 
 /* dfo::NelderMead<N>::Params (include/dfo/nelder_mead.hpp:11-22) */

@@ -277,7 +277,11 @@ def test_device_resident_loop_full_calibrate_single_bag(gpu, oracle):
     params.max_inner_iterations, params.max_outer_iterations = 50, 3
     params.delta_trans_thresh, params.delta_rot_thresh = 1e-4, 1e-5
     calib = V.VisualCameraCalibration(cam, [V.VisualLiDARData(bag["image"], bag["points"], bag["intensities"])], params)
-    T = calib.calibrate(bag["T_init"])  # auto mode -> device-resident loop (one bag)
+    try:
+        V.set_solver_mode(2)  # device-resident loop
+        T = calib.calibrate(bag["T_init"])
+    finally:
+        V.set_solver_mode(0)
     op = oracle.default_calib_params()
     op.max_inner_iterations, op.max_outer_iterations, op.delta_trans_thresh, op.delta_rot_thresh = 50, 3, 1e-4, 1e-5
     ref = oracle.calibrate(ocam, [(bag["image"], bag["points"], bag["intensities"])], bag["T_init"], op)
