@@ -494,5 +494,5 @@ def test_fused_peer_exchange_matches_nccl_and_single_gpu(gpu):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "dist_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "P2P_CHECK world=2 fused_equals_nccl=True" in out.stdout
-    assert "DIST_CHECK world=2 identical=True close=True" in out.stdout
+    assert "P2P_CHECK world=2 fused_close_to_nccl=True fused_equals_nccl=True" in out.stdout
+    assert "DIST_CHECK world=2 identical=True close=True fused_identical_to_single_gpu=True" in out.stdout

@@ -40,13 +40,26 @@ px = PeerExchange(local, rank, world)
 px.connect_with_torch()
 mine.attach_peer_exchange(px)
 Tp, rp = VC.estimate_pose_on_costs([mine], T0, params)
+# the device-resident solver loop composes with the exchange: same trajectory again, no host between batches
+V.set_solver_mode(2)
+Td, rd = VC.estimate_pose_on_costs([mine], T0, params)
+V.set_solver_mode(0)
+assert np.array_equal(Td, Tp) and rd["y"] == rp["y"] and rd["num_iterations"] == rp["num_iterations"], "device-resident loop + exchange diverged"
 mine.attach_peer_exchange(None)
-same_p2p = np.array_equal(Tp, T) and rp["num_iterations"] == r["num_iterations"] and rp["y"] == r["y"]
-flags = torch.tensor([1.0 if same_p2p else 0.0], device="cuda")
+# NCCL may add the G contributions in any order (ring / tree); the fused exchange adds them in rank (= bag) order like the
+# reference's sequential sum_costs += costs[i]->calculate(T): identical to NCCL for G = 2, last-bit close beyond.
+close_p2p = np.abs(Tp - T).max() < 1e-12 and rp["num_iterations"] == r["num_iterations"] and abs(rp["y"] - r["y"]) < 1e-12
+same_p2p = np.array_equal(Tp, T) and rp["y"] == r["y"]
+flags = torch.tensor([1.0 if close_p2p else 0.0, 1.0 if same_p2p else 0.0], device="cuda")
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"P2P_CHECK world={world} fused_equals_nccl={bool(flags.item())} y_p2p={rp['y']:.15f} y_nccl={r['y']:.15f}")
-assert flags.item() == 1.0, "fused peer exchange diverged from the NCCL path"
+    print(f"P2P_CHECK world={world} fused_close_to_nccl={bool(flags[0].item())} fused_equals_nccl={bool(flags[1].item())} y_p2p={rp['y']:.15f} y_nccl={r['y']:.15f}")
+assert flags[0].item() == 1.0, "fused peer exchange diverged from the NCCL path"
+out_p = torch.from_numpy(np.concatenate([Tp.reshape(-1), rp["x"], [rp["y"], rp["num_iterations"], rp["num_evaluations"]]])).cuda()
+gathered_p = [torch.zeros_like(out_p) for _ in range(world)]
+dist.all_gather(gathered_p, out_p)
+assert all(torch.equal(g, gathered_p[0]) for g in gathered_p), "ranks diverged on the fused path"
+
 out = torch.from_numpy(np.concatenate([T.reshape(-1), r["x"], [r["y"], r["num_iterations"], r["num_evaluations"]]])).cuda()
 gathered = [torch.zeros_like(out) for _ in range(world)]
 dist.all_gather(gathered, out)
@@ -56,8 +69,9 @@ if rank == 0:
     T1, r1 = VC.estimate_pose_on_costs(costs, T0, params)
     same = np.array_equal(T1, T) and r1["num_iterations"] == r["num_iterations"] and r1["num_evaluations"] == r["num_evaluations"]
     close = np.abs(T1 - T).max() < 1e-12 and abs(r1["y"] - r["y"]) < 1e-12
-    print(f"DIST_CHECK world={world} identical={same} close={close} iters={r['num_iterations']} y={r['y']:.12f} y_single={r1['y']:.12f}")
-    assert close and r1["num_iterations"] == r["num_iterations"]
+    fused_same = np.array_equal(T1, Tp) and r1["y"] == rp["y"] and r1["num_iterations"] == rp["num_iterations"]
+    print(f"DIST_CHECK world={world} identical={same} close={close} fused_identical_to_single_gpu={fused_same} iters={r['num_iterations']} y={r['y']:.12f} y_single={r1['y']:.12f}")
+    assert close and r1["num_iterations"] == r["num_iterations"] and fused_same
 dist.barrier()
 px.close()
 dist.destroy_process_group()
