@@ -338,8 +338,16 @@ def main():
     alg_bytes = 16 * n_culled + W * H  # per launch: one pass over the float4 cloud + the image plane
     k_ms = prof["kernel_ms_total"] / max(1, prof["kernel_launches"])
     achieved = alg_bytes / (k_ms * 1e-3) * 1e-9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath) and args.points == 1_000_000:
+        try:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"], tj["source"]
+        except Exception:
+            pass
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src, "kernel": "nid_hist_*_kernel", "avg_launch_us": 1e3 * k_ms, "algorithmic_bytes_per_launch": alg_bytes,
         "poses_per_launch": prof["poses_total"] / max(1, prof["kernel_launches"]),
         "kernel_share_of_step": prof["kernel_ms_total"] / total_ms,
