@@ -209,23 +209,27 @@ int upload_image(int device, const uint8_t* image, int width, int height, int ro
 using NidKernel = void (*)(const NidArgs);
 
 // kind: 0 = fp32 filter + exact recheck (float4 layout only; 4 points/thread), 1 = exact fp64, 2 = verify (debug),
-//       3 = fp32 filter with 2 points/thread (A/B measurement)
+//       3 = fp32 filter with 2 points/thread (A/B measurement); devloop: device-resident solver-loop variant of 0 / 1
 template <int MODEL>
-static NidKernel pick_layout(bool f32, int kind) {
-  if (f32 && kind == 0) return nid_hist_filter_kernel<MODEL, true, 4>;
-  if (f32 && kind == 3) return nid_hist_filter_kernel<MODEL, true, 2>;
+static NidKernel pick_layout(bool f32, int kind, bool devloop) {
+  if (devloop) {
+    if (f32 && (kind == 0 || kind == 3)) return nid_hist_filter_kernel<MODEL, true, 4, true>;
+    return f32 ? nid_hist_exact_kernel<MODEL, true, true> : nid_hist_exact_kernel<MODEL, false, true>;
+  }
+  if (f32 && kind == 0) return nid_hist_filter_kernel<MODEL, true, 4, false>;
+  if (f32 && kind == 3) return nid_hist_filter_kernel<MODEL, true, 2, false>;
   if (f32 && kind == 2) return nid_filter_verify_kernel<MODEL, true>;
-  return f32 ? nid_hist_exact_kernel<MODEL, true> : nid_hist_exact_kernel<MODEL, false>;
+  return f32 ? nid_hist_exact_kernel<MODEL, true, false> : nid_hist_exact_kernel<MODEL, false, false>;
 }
 
-static NidKernel pick_kernel(int model, bool f32, int kind) {
+static NidKernel pick_kernel(int model, bool f32, int kind, bool devloop = false) {
   switch (model) {
-    case CAM_PLUMB_BOB: return pick_layout<CAM_PLUMB_BOB>(f32, kind);
-    case CAM_FISHEYE: return pick_layout<CAM_FISHEYE>(f32, kind);
-    case CAM_ATAN: return pick_layout<CAM_ATAN>(f32, kind);
-    case CAM_OMNIDIR: return pick_layout<CAM_OMNIDIR>(f32, kind);
-    case CAM_EQUIRECTANGULAR: return pick_layout<CAM_EQUIRECTANGULAR>(f32, kind);
-    case CAM_RATIONAL_POLYNOMIAL: return pick_layout<CAM_RATIONAL_POLYNOMIAL>(f32, kind);
+    case CAM_PLUMB_BOB: return pick_layout<CAM_PLUMB_BOB>(f32, kind, devloop);
+    case CAM_FISHEYE: return pick_layout<CAM_FISHEYE>(f32, kind, devloop);
+    case CAM_ATAN: return pick_layout<CAM_ATAN>(f32, kind, devloop);
+    case CAM_OMNIDIR: return pick_layout<CAM_OMNIDIR>(f32, kind, devloop);
+    case CAM_EQUIRECTANGULAR: return pick_layout<CAM_EQUIRECTANGULAR>(f32, kind, devloop);
+    case CAM_RATIONAL_POLYNOMIAL: return pick_layout<CAM_RATIONAL_POLYNOMIAL>(f32, kind, devloop);
     default: return nullptr;
   }
 }
@@ -419,10 +423,10 @@ static void fill_common_args(vlcal_nid_ctx* ctx, NidArgs& a) {
   a.counter = ctx->d_counter;
 }
 
-static NidKernel select_kernel(vlcal_nid_ctx* ctx) {
+static NidKernel select_kernel(vlcal_nid_ctx* ctx, bool devloop = false) {
   // the fp32 filter needs the float4 layout, a camera/FoV it has bounds for, and 32-bit point indices
   const bool use_filter = ctx->variant != 1 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
-  return pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? (ctx->variant == 2 ? 3 : 0) : 1);
+  return pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? (ctx->variant == 2 ? 3 : 0) : 1, devloop);
 }
 
 constexpr int PROFILE_STRIDE = 4;
@@ -518,7 +522,7 @@ int nid_enqueue_device_steps(vlcal_nid_ctx* ctx, NmDevice* d_nm, int count) {
     set_last_error("device-resident solver loop needs room for 8 poses per launch (bins too large)");
     return VLCAL_ERR_UNSUPPORTED;
   }
-  NidKernel kernel = select_kernel(ctx);
+  NidKernel kernel = select_kernel(ctx, /*devloop=*/true);
   NidArgs a;
   fill_common_args(ctx, a);
   a.nm = d_nm;

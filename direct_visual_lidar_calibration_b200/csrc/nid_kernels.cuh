@@ -55,13 +55,6 @@ struct NmDevice {
   unsigned long long steps_done;
 };
 
-// where a launch reads its poses from (kernel parameters or NmDevice)
-struct PoseView {
-  int n_poses;
-  const double (*pose)[12];
-  const float (*pose32)[16];
-};
-
 struct NidArgs {
   const void* points;        // float4[n] (x,y,z,intensity) or double4[n]
   const uint8_t* bin_image;  // H x W image bins: clamp(int(u8/255.0*bins), 0, bins-1)  (:43,:46)
@@ -92,18 +85,21 @@ struct NidArgs {
   int* hist_out;              // optional [n_poses][nb], index = image_bin + lidar_bin*bins
 };
 
-__device__ __forceinline__ PoseView make_pose_view(const NidArgs& a) {
-  PoseView v;
-  if (a.nm) {
-    v.n_poses = a.nm->n_poses;
-    v.pose = a.nm->pose;
-    v.pose32 = a.nm->pose32;
-  } else {
-    v.n_poses = a.n_poses;
-    v.pose = a.pose;
-    v.pose32 = a.pose32;
-  }
-  return v;
+// where a launch reads its poses from: kernel parameters (constant bank) or, in the device-resident loop, NmDevice
+template <bool DEVLOOP>
+__device__ __forceinline__ int n_poses_of(const NidArgs& a) {
+  if constexpr (DEVLOOP) return a.nm->n_poses;
+  else return a.n_poses;
+}
+template <bool DEVLOOP>
+__device__ __forceinline__ const double* pose_of(const NidArgs& a, int p) {
+  if constexpr (DEVLOOP) return a.nm->pose[p];
+  else return a.pose[p];
+}
+template <bool DEVLOOP>
+__device__ __forceinline__ const float* pose32_of(const NidArgs& a, int p) {
+  if constexpr (DEVLOOP) return a.nm->pose32[p];
+  else return a.pose32[p];
 }
 
 // ---- exact decision for one (point, pose): pixel index iy*W+ix (>= 0), or -1 if the reference skips the point
@@ -214,15 +210,15 @@ __device__ __forceinline__ double warp_tree_sum(double v) {
 }
 
 // called by the finalizing block after every pose's local score sits in a.nid_out (block-synchronised)
-static __device__ void nid_peer_allreduce(const NidArgs& a, const PoseView& pv) {
+static __device__ void nid_peer_allreduce(const NidArgs& a, int n_poses) {
   __shared__ unsigned long long s_seq;
   const int t = threadIdx.x;
   if (t == 0) s_seq = ++(*a.p2p_counter);  // every rank performs the same sequence of exchanges
   __syncthreads();
   const unsigned long long seq = s_seq;
   const int slot = static_cast<int>(seq & 1ull);
-  if (t < pv.n_poses * a.p2p_world) {  // one thread per (peer, pose): remote stores over NVLink
-    const int g = t / pv.n_poses, p = t % pv.n_poses;
+  if (t < n_poses * a.p2p_world) {  // one thread per (peer, pose): remote stores over NVLink
+    const int g = t / n_poses, p = t % n_poses;
     a.peer_box[g]->vals[a.p2p_rank][slot][p] = a.nid_out[p];
     __threadfence_system();
   }
@@ -242,7 +238,7 @@ static __device__ void nid_peer_allreduce(const NidArgs& a, const PoseView& pv) 
     __threadfence_system();
   }
   __syncthreads();
-  if (t < pv.n_poses) {
+  if (t < n_poses) {
     double total = 0.0;
     for (int r = 0; r < a.p2p_world; r++) total += __ldcv(&a.peer_box[a.p2p_rank]->vals[r][slot][t]);  // rank order: identical on every rank
     a.nid_out[t] = total;
@@ -308,18 +304,19 @@ static __device__ void nm_device_advance(const NidArgs& a) {
   if (threadIdx.x == 0) nm->n_poses = n_next;
 }
 
-static __device__ void nid_finalize(const NidArgs& a, const PoseView& pv, int* smem_i) {
+template <bool DEVLOOP>
+static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   __shared__ int s_cnt[NID_THREADS / 32];  // per-warp partial inlier counts
   // splitting a pose over several warps needs staging room: the block's histogram copies provide it when copies >= 4
-  const int wpp = a.copies >= 4 ? max(1, n_warps / pv.n_poses) : 1;  // warps per pose
+  const int wpp = a.copies >= 4 ? max(1, n_warps / n_poses) : 1;  // warps per pose
   const int ppr = n_warps / wpp;                                     // poses per round
   double* s_term = reinterpret_cast<double*>(smem_i);                // [ppr][nb] staged p*log(p+1e-6) terms (wpp > 1)
   int* s_marg = smem_i + (wpp > 1 ? 2 * ppr * a.nb : 0);             // [ppr][2*bins] marginal counts
-  for (int p0 = 0; p0 < pv.n_poses; p0 += ppr) {
+  for (int p0 = 0; p0 < n_poses; p0 += ppr) {
     const int slot = warp / wpp, sub = warp % wpp;  // pose slot of this warp within the round, rank within the pose
     const int p = p0 + slot;
-    const bool active = slot < ppr && p < pv.n_poses;
+    const bool active = slot < ppr && p < n_poses;
     int* h_image = s_marg + slot * 2 * a.bins;  // [bins]
     int* h_points = h_image + a.bins;           // [bins]
     for (int i = threadIdx.x; i < ppr * 2 * a.bins; i += blockDim.x) s_marg[i] = 0;
@@ -405,8 +402,8 @@ static __device__ void nid_finalize(const NidArgs& a, const PoseView& pv, int* s
     }
     __syncthreads();
   }
-  if (a.p2p_world > 1) nid_peer_allreduce(a, pv);
-  if (a.nm) nm_device_advance(a);
+  if (a.p2p_world > 1) nid_peer_allreduce(a, n_poses);
+  if constexpr (DEVLOOP) nm_device_advance(a);
   stamp(a, 4);
   if (threadIdx.x == 0) {
     *a.counter = 0u;
@@ -419,8 +416,9 @@ static __device__ void nid_finalize(const NidArgs& a, const PoseView& pv, int* s
 }
 
 // block epilogue shared by the histogram kernels: merge copies -> global accumulators -> last block finalizes
-__device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, const PoseView& pv, int* smem_hist, bool* s_is_last) {
-  const int per_copy = pv.n_poses * a.nb;
+template <bool DEVLOOP>
+__device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, int n_poses, int* smem_hist, bool* s_is_last) {
+  const int per_copy = n_poses * a.nb;
   const unsigned long long t_main = a.timeline ? global_ns() : 0ull;
   __syncthreads();
   for (int k = threadIdx.x; k < per_copy; k += blockDim.x) {
@@ -443,16 +441,18 @@ __device__ __forceinline__ void nid_block_epilogue(const NidArgs& a, const PoseV
     a.timeline[3] = global_ns();
   }
   __threadfence();
-  nid_finalize(a, pv, smem_hist);
+  nid_finalize<DEVLOOP>(a, n_poses, smem_hist);
 }
 
-template <int MODEL, bool F32>
+// DEVLOOP: device-resident solver loop variant (poses from NmDevice, Nelder-Mead step in the finalizing block); kept out of
+// the default instantiation so that its register footprint does not cost the hot loop an occupancy step.
+template <int MODEL, bool F32, bool DEVLOOP>
 __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __grid_constant__ NidArgs a) {
   extern __shared__ int smem_hist[];
   __shared__ bool s_is_last;
-  const PoseView pv = make_pose_view(a);
-  if (pv.n_poses == 0) return;  // device-resident loop: the solver has finished
-  const int per_copy = pv.n_poses * a.nb;
+  const int n_poses = n_poses_of<DEVLOOP>(a);
+  if (n_poses == 0) return;  // device-resident loop: the solver has finished
+  const int per_copy = n_poses * a.nb;
   if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
@@ -469,14 +469,14 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_exact_kernel(const __gri
       x = q.x, y = q.y, z = q.z, w = q.w;
     }
     const int lb = lidar_bin_of(w, a.bins);
-    for (int p = 0; p < pv.n_poses; p++) {
-      const int ib = classify_exact<MODEL>(a, pv.pose[p], x, y, z);
+    for (int p = 0; p < n_poses; p++) {
+      const int ib = classify_exact<MODEL>(a, pose_of<DEVLOOP>(a, p), x, y, z);
       if (ib >= 0) {
         atomicAdd(&my_hist[p * a.nb + ib + lb * a.bins], 1);  // :49 hist(image_bin, lidar_bin)++
       }
     }
   }
-  nid_block_epilogue(a, pv, smem_hist, &s_is_last);
+  nid_block_epilogue<DEVLOOP>(a, n_poses, smem_hist, &s_is_last);
 }
 
 constexpr int NID_QUEUE = 64;  // per-warp queue of (point, pose) pairs waiting for the exact path
@@ -491,13 +491,13 @@ struct FilterWarp {
   unsigned int lt_mask;
 };
 
-template <int MODEL>
-__device__ __forceinline__ void filter_drain32(const NidArgs& a, const PoseView& pv, FilterWarp& w, const float4* __restrict__ pts, int first, int count) {
+template <int MODEL, bool DEVLOOP>
+__device__ __forceinline__ void filter_drain32(const NidArgs& a, FilterWarp& w, const float4* __restrict__ pts, int first, int count) {
   if (w.lane < count) {  // entries [first, first+count), count <= 32: one deferred (point, pose) per lane, exact path
     const unsigned int i = w.q_idx[first + w.lane];
     const int p = w.q_pose[first + w.lane];
     const float4 q = __ldg(pts + i);
-    const int ib = classify_exact<MODEL>(a, pv.pose[p], q.x, q.y, q.z);
+    const int ib = classify_exact<MODEL>(a, pose_of<DEVLOOP>(a, p), q.x, q.y, q.z);
     if (ib >= 0) atomicAdd(&w.my_hist[p * a.nb + ib + lidar_bin_of(q.w, a.bins) * a.bins], 1);
   }
 }
@@ -505,8 +505,8 @@ __device__ __forceinline__ void filter_drain32(const NidArgs& a, const PoseView&
 // one tile = 32*K consecutive points starting at `tile` (K per lane, warp-coalesced rows), swept over all P poses.
 // Software pipeline over the poses: the image-bin gathers of pose p are issued unconditionally (clamped address), stay
 // in flight while pose p+1 is classified, and are consumed by the histogram atomics one iteration later.
-template <int MODEL, int K>
-__device__ __forceinline__ void filter_tile(const NidArgs& a, const PoseView& pv, FilterWarp& w, const float4* __restrict__ pts, unsigned int tile, unsigned int end) {
+template <int MODEL, int K, bool DEVLOOP>
+__device__ __forceinline__ void filter_tile(const NidArgs& a, int n_poses, FilterWarp& w, const float4* __restrict__ pts, unsigned int tile, unsigned int end) {
   float px[K], py[K], pz[K], pa[K];
   int lboff[K];
   unsigned int idx[K];
@@ -525,11 +525,11 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, const PoseView& pv
   int pend_bin[K];
   unsigned int pend_ok = 0;
   int* pend_hist = w.my_hist;
-  for (int p = 0; p <= pv.n_poses; p++) {
+  for (int p = 0; p <= n_poses; p++) {
     int verdict[K];
     unsigned int unc_bits = 0, ok_bits = 0;
-    if (p < pv.n_poses) {
-      const float* __restrict__ P = pv.pose32[p];
+    if (p < n_poses) {
+      const float* __restrict__ P = pose32_of<DEVLOOP>(a, p);
 #pragma unroll
       for (int j = 0; j < K; j++) {
         int vd = classify_fast<MODEL>(a, P, px[j], py[j], pz[j], pa[j]);
@@ -544,7 +544,7 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, const PoseView& pv
       if ((pend_ok >> j) & 1u) atomicAdd(&pend_hist[pend_bin[j] + lboff[j]], 1);  // :49 hist(image_bin, lidar_bin)++
     }
     pend_ok = ok_bits;
-    if (p < pv.n_poses) {
+    if (p < n_poses) {
       pend_hist = w.my_hist + p * a.nb;
 #pragma unroll
       for (int j = 0; j < K; j++) pend_bin[j] = __ldg(a.bin_image + max(verdict[j], 0));
@@ -562,7 +562,7 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, const PoseView& pv
             w.qn += __popc(m);
             __syncwarp();
             if (w.qn >= 32) {
-              filter_drain32<MODEL>(a, pv, w, pts, w.qn - 32, 32);
+              filter_drain32<MODEL, DEVLOOP>(a, w, pts, w.qn - 32, 32);
               w.qn -= 32;
               __syncwarp();
             }
@@ -582,16 +582,16 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, const PoseView& pv
 // Work split: the cloud is cut into one contiguous, equally long range per warp (multiple of 32 points), processed as
 // NID_KPT-row tiles (NID_KPT points per lane in registers: pose constants fetched once per tile, NID_KPT independent
 // chains in flight) plus single-row tiles for the remainder, so no warp does a whole extra tile more than another.
-template <int MODEL, bool F32, int NID_KPT>
-__global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __grid_constant__ NidArgs a) {
+template <int MODEL, bool F32, int NID_KPT, bool DEVLOOP>
+__global__ void __launch_bounds__(NID_THREADS, DEVLOOP ? 1 : 3) nid_hist_filter_kernel(const __grid_constant__ NidArgs a) {
   extern __shared__ int smem_hist[];
   __shared__ bool s_is_last;
   __shared__ unsigned int q_idx[NID_THREADS / 32][NID_QUEUE];
   __shared__ unsigned char q_pose[NID_THREADS / 32][NID_QUEUE];
   static_assert(F32, "the fp32 filter runs on the float4 cloud layout");
-  const PoseView pv = make_pose_view(a);
-  if (pv.n_poses == 0) return;  // device-resident loop: the solver has finished
-  const int per_copy = pv.n_poses * a.nb;
+  const int n_poses = n_poses_of<DEVLOOP>(a);
+  if (n_poses == 0) return;  // device-resident loop: the solver has finished
+  const int per_copy = n_poses * a.nb;
   if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
   for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
   __syncthreads();
@@ -613,11 +613,11 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   if (lo < n) {
     const unsigned int end = static_cast<unsigned int>(min(static_cast<unsigned long long>(n), lo + chunk));
     unsigned int t = static_cast<unsigned int>(lo);
-    for (; t + 32u * NID_KPT <= end; t += 32u * NID_KPT) filter_tile<MODEL, NID_KPT>(a, pv, w, pts, t, end);
-    for (; t < end; t += 32u) filter_tile<MODEL, 1>(a, pv, w, pts, t, end);
+    for (; t + 32u * NID_KPT <= end; t += 32u * NID_KPT) filter_tile<MODEL, NID_KPT, DEVLOOP>(a, n_poses, w, pts, t, end);
+    for (; t < end; t += 32u) filter_tile<MODEL, 1, DEVLOOP>(a, n_poses, w, pts, t, end);
   }
-  if (w.qn > 0) filter_drain32<MODEL>(a, pv, w, pts, 0, w.qn);
-  nid_block_epilogue(a, pv, smem_hist, &s_is_last);
+  if (w.qn > 0) filter_drain32<MODEL, DEVLOOP>(a, w, pts, 0, w.qn);
+  nid_block_epilogue<DEVLOOP>(a, n_poses, smem_hist, &s_is_last);
 }
 
 // debug / test kernel: runs BOTH paths on every (point, pose) and counts, in a.dbg:
