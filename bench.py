@@ -368,7 +368,8 @@ def main():
         },
         "evals_per_step": evals_ref / args.steps, "evals_computed_per_step": evals_cmp / args.steps, "batches_per_step": batches / args.steps,
         "mpoints_per_s": mpoints, "wall_s_timed_region": wall,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                "host_breakdown_ms": {k: round(float(np.mean([r[2][k] for r in e2e_res])), 3) for k in ("upload_ms", "cull_ms", "solve_ms")}},
         "gpu_launches": int(prof["kernel_launches"]),
         "collectives": n_collectives[0],
         "roofline": roofline,

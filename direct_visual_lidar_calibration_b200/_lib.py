@@ -76,6 +76,7 @@ class CalibStats(C.Structure):
         ("outer_iterations", C.c_int), ("total_evaluations", C.c_int), ("total_evaluations_computed", C.c_int), ("total_batches", C.c_int),
         ("inner_iterations", C.c_int * 16), ("inner_final_cost", C.c_double * 16), ("culled_points", C.c_int64 * 16),
         ("kernel_launches", C.c_int64), ("kernel_ms_total", C.c_double),
+        ("upload_ms", C.c_double), ("cull_ms", C.c_double), ("solve_ms", C.c_double),
     ]
 
 

@@ -73,6 +73,7 @@ def _stats_dict(st: _lib.CalibStats):
         "total_evaluations_computed": int(st.total_evaluations_computed), "total_batches": int(st.total_batches),
         "inner_iterations": list(st.inner_iterations[:k]), "inner_final_cost": list(st.inner_final_cost[:k]), "culled_points": list(st.culled_points[:k]),
         "kernel_launches": int(st.kernel_launches), "kernel_ms_total": float(st.kernel_ms_total),
+        "upload_ms": float(st.upload_ms), "cull_ms": float(st.cull_ms), "solve_ms": float(st.solve_ms),
     }
 
 

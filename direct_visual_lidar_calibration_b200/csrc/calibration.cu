@@ -4,6 +4,7 @@
 // Same decisions as the reference (outer loop, culling at the start pose of every inner solve, one cost object per
 // bag, dfo::NelderMead<6> with the calibration parameters), but every Nelder-Mead iteration scores its candidate
 // poses {xo, xr, xe, xc} in ONE batched kernel launch per bag, and bags run concurrently on their own streams.
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -15,6 +16,10 @@
 using namespace vlcal;
 
 namespace {
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 vlcal_p2p* g_default_p2p = nullptr;  // vlcal_nid_p2p_set_default
 int g_solver_mode = 0;                // vlcal_nid_set_solver_mode: 0 auto, 1 host loop, 2 device-resident loop
@@ -260,6 +265,7 @@ int inner_solve_resident(
   vlcal_allreduce_fn allreduce, void* user, int profiling, double T_out[16], vlcal_nm_result* nm_result, vlcal_calib_stats* stats, int outer_index) {
   // :71-73 one ViewCulling object, built on dataset.front()'s image size
   const double cull_fov = bags.empty() ? 0.0 : bags[0].max_fov;
+  const double t_cull0 = now_ms();
   CtxList ctxs;
   for (size_t b = 0; b < bags.size(); b++) {
     std::shared_ptr<DeviceCloud> culled;
@@ -274,11 +280,14 @@ int inner_solve_resident(
     if (g_default_p2p && bags.size() == 1 && g_default_p2p->device == device) ctx->p2p = g_default_p2p;
     ctxs.v.push_back(ctx);
   }
+  const double t_solve0 = now_ms();
+  if (stats) stats->cull_ms += t_solve0 - t_cull0;
   vlcal_nm_result local;
   const int rc = run_inner_solve(ctxs.v.data(), static_cast<int>(ctxs.v.size()), params, init_T, callback, allreduce, user, T_out, &local);
   if (rc != VLCAL_OK) return rc;
   if (nm_result) *nm_result = local;
   if (stats) {
+    stats->solve_ms += now_ms() - t_solve0;
     stats->total_evaluations += local.num_evaluations;
     stats->total_evaluations_computed += local.num_evaluations_computed;
     stats->total_batches += local.num_batches;
@@ -432,9 +441,13 @@ int vlcal_estimate_pose_nelder_mead(
   if (device < 0) VL_CUDA(cudaGetDevice(&device));
   VL_CUDA(cudaSetDevice(device));
   std::vector<ResidentBag> resident;
+  const double t_up0 = now_ms();
   rc = upload_bags(device, cam, bags, n_bags, &resident);
   if (rc != VLCAL_OK) return rc;
-  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->upload_ms = now_ms() - t_up0;
+  }
   rc = inner_solve_resident(device, cam, resident, params, init_T_camera_lidar, callback, allreduce, user, profiling, T_out, nm_result, stats, 0);
   if (rc == VLCAL_OK && stats) stats->outer_iterations = 1;
   return rc;
@@ -465,9 +478,13 @@ int vlcal_calibrate_nelder_mead(
   if (device < 0) VL_CUDA(cudaGetDevice(&device));
   VL_CUDA(cudaSetDevice(device));
   std::vector<ResidentBag> resident;
+  const double t_up0 = now_ms();
   rc = upload_bags(device, cam, bags, n_bags, &resident);
   if (rc != VLCAL_OK) return rc;
-  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->upload_ms = now_ms() - t_up0;
+  }
 
   double T[16];
   std::memcpy(T, init_T_camera_lidar, sizeof(T));

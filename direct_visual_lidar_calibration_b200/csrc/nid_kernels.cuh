@@ -583,7 +583,7 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, int n_poses, Filte
 // NID_KPT-row tiles (NID_KPT points per lane in registers: pose constants fetched once per tile, NID_KPT independent
 // chains in flight) plus single-row tiles for the remainder, so no warp does a whole extra tile more than another.
 template <int MODEL, bool F32, int NID_KPT, bool DEVLOOP>
-__global__ void __launch_bounds__(NID_THREADS, DEVLOOP ? 1 : 3) nid_hist_filter_kernel(const __grid_constant__ NidArgs a) {
+__global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __grid_constant__ NidArgs a) {
   extern __shared__ int smem_hist[];
   __shared__ bool s_is_last;
   __shared__ unsigned int q_idx[NID_THREADS / 32][NID_QUEUE];

@@ -284,6 +284,10 @@ typedef struct {
   int64_t culled_points[16]; /* points kept by view culling in bag 0 per outer iteration */
   int64_t kernel_launches;
   double kernel_ms_total; /* only if profiling != 0 */
+  /* host wall-clock breakdown of the call, milliseconds (summed over outer iterations) */
+  double upload_ms;  /* host double -> float4 conversion + H2D of clouds and images */
+  double cull_ms;    /* GPU view culling + cost-object construction */
+  double solve_ms;   /* Nelder-Mead inner solves */
 } vlcal_calib_stats;
 
 /* the objective of estimate_pose_nelder_mead (visual_camera_calibration.cpp:103-119) over already-built cost
