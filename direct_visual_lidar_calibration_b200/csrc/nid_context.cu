@@ -159,7 +159,9 @@ int upload_cloud(int device, const double* points_xyzw, const double* intensitie
   // float4 (x,y,z,intensity) is lossless when the doubles came from a float32 PLY and intensity = k/256
   float4* stage = static_cast<float4*>(g_stage.ptr);
   int lossless = 1, w_is_one = 1;
-#pragma omp parallel for schedule(static) reduction(&& : lossless, w_is_one)
+  // memory-bound copy-convert: a dozen threads saturate it; waking every core of a 128-core host costs more than it saves
+  const int conv_threads = std::max(1, std::min(16, omp_get_max_threads()));
+#pragma omp parallel for schedule(static) reduction(&& : lossless, w_is_one) num_threads(conv_threads)
   for (int64_t i = 0; i < n; i++) {
     const double* p = points_xyzw + 4 * i;
     const float4 q = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(p[2]), static_cast<float>(intensities[i]));
@@ -175,7 +177,7 @@ int upload_cloud(int device, const double* points_xyzw, const double* intensitie
   cloud->f32 = lossless != 0;
   if (!cloud->f32) {
     double4* stage64 = static_cast<double4*>(g_stage.ptr);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(conv_threads)
     for (int64_t i = 0; i < n; i++) {
       const double* p = points_xyzw + 4 * i;
       stage64[i] = make_double4(p[0], p[1], p[2], intensities[i]);
