@@ -20,13 +20,15 @@ except Exception:
     pass
 
 
-def measure(name, bag, poses, launches=30, cpu_evals=3, variants=((0, "filter"), (1, "exact_fp64"))):
+def measure(name, bag, poses, launches=30, cpu_evals=3, variants=((0, "filter"), (2, "filter_kpt2"), (1, "exact_fp64")), tile_order=True):
     cam = V.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
     ocam = O.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
     data = V.VisualLiDARData(bag["image"], bag["points"], bag["intensities"])
     t0 = time.perf_counter()
     cost = V.CostCalculatorNID(cam, data)
     t_create = time.perf_counter() - t0
+    if tile_order:
+        cost.reorder_for_pose(poses[0])  # what the calibrate path gets from its culling pass
     n, (H, W) = data.size(), bag["image"].shape
     fov = cost.max_fov
     # parity at full size, one pose
@@ -64,7 +66,7 @@ def measure(name, bag, poses, launches=30, cpu_evals=3, variants=((0, "filter"),
             k_us = 1e3 * pr["kernel_ms_total"] / pr["kernel_launches"]
             gbs = alg_bytes / (k_us * 1e-6) * 1e-9
             print(json.dumps({
-                "config": name, "kernel": vname, "camera": bag["camera_model"], "points": n, "image": f"{W}x{H}", "poses_per_launch": P,
+                "config": name, "kernel": vname, "camera": bag["camera_model"], "points": n, "image": f"{W}x{H}", "poses_per_launch": P, "tile_ordered": tile_order,
                 "kernel_us": round(k_us, 2), "call_us": round(wall * 1e6, 2), "evals_per_s_kernel": round(P / (k_us * 1e-6)), "evals_per_s_call": round(P / wall),
                 "mpoints_per_s": round(n * P / (k_us * 1e-6) * 1e-6), "achieved_GBps": round(gbs, 1), "hbm_frac_of_measured": round(gbs / PEAK, 4),
                 "cpu_oracle_evals_per_s_1core": round(1.0 / t_cpu, 2), "cpu_oracle_omp_evals_per_s": round(1.0 / t_cpu_omp, 2), "cpu_cores": os.cpu_count(),
