@@ -496,3 +496,31 @@ def test_fused_peer_exchange_matches_nccl_and_single_gpu(gpu):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "P2P_CHECK world=2 fused_close_to_nccl=True fused_equals_nccl=True" in out.stdout
     assert "DIST_CHECK world=2 identical=True close=True fused_identical_to_single_gpu=True" in out.stdout
+
+
+def test_pose_grid_search_finds_the_basin(gpu, oracle):
+    """Config-5 style coarse grid: every score equals the oracle's, and the best grid pose is the one nearest the truth."""
+    from direct_visual_lidar_calibration_b200 import initial_guess as IG
+    from direct_visual_lidar_calibration_b200 import synthetic as S
+
+    bag = S.make_bag("pinhole_640x480", "frustum", 40000, config_index=12, scale=0.5)
+    cam = gpu.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    cost = gpu.CostCalculatorNID(cam, gpu.VisualLiDARData(bag["image"], bag["points"], bag["intensities"]))
+    T_rough = S.perturb(bag["T_gt"], (1.0, -1.0, 1.0), (0.02, 0.0, -0.02))
+    grid = dict(n_rot=(3, 3, 3), n_trans=(1, 3, 3), rot_half_deg=1.0, trans_half=0.02)
+    poses = IG.pose_grid(T_rough, **grid)
+    assert poses.shape == (243, 4, 4)
+    nid = IG.score_poses(cost, poses)
+    ocam = oracle.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    fov = oracle.estimate_camera_fov(ocam, bag["width"], bag["height"])
+    for k in (0, 100, 242):
+        assert abs(nid[k] - oracle.nid_calculate(ocam, bag["image"], bag["points"], bag["intensities"], 16, fov, poses[k])[0]) < NID_TOL
+    best, best_nid = IG.grid_search(cost, T_rough, top_k=3, **grid)
+    assert best_nid[0] == np.nanmin(nid) and best_nid[0] <= best_nid[1] <= best_nid[2]
+    # the grid contains the ground truth's neighbourhood (perturbation of +-1 deg / +-2 cm): the winner must be closer to it
+    # than the rough centre is
+    def dist_to_gt(T):
+        d = np.linalg.inv(T) @ bag["T_gt"]
+        return np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1)) + np.linalg.norm(d[:3, 3])
+
+    assert dist_to_gt(best[0]) < dist_to_gt(T_rough)
