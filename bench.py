@@ -243,8 +243,21 @@ def main():
         # fused path: the finalizing block of every evaluation exchanges the scores over NVLink peer memory
         from direct_visual_lidar_calibration_b200.distributed import PeerExchange
 
-        px = PeerExchange(device, rank, world)
-        px.connect_with_torch()
+        ok = 1.0
+        try:
+            px = PeerExchange(device, rank, world)
+        except Exception as e:  # no peer access / IPC on this box: every rank must take the same decision
+            print(f"[bench] rank {rank}: peer exchange unavailable ({e})", file=sys.stderr)
+            px, ok = None, 0.0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 1.0:
+            px.connect_with_torch()
+        else:
+            if px is not None:
+                px.close()
+            px = None
+            args.exchange = "nccl"
     ar = allreduce if (world > 1 and px is None) else None
 
     # ---- resident setup (outside the timed region): cull at the start pose, build the cost object ------------
