@@ -366,6 +366,16 @@ def main():
         "kernel_share_of_step": prof["kernel_ms_total"] / total_ms,
         "note": "a 4-pose launch does 4x the ALU work of the byte count; cloud (16 MB) is L2-resident across NM iterations by design",
     }
+    # the bound that is actually active: instruction issue.  ncu: 108 warp-instructions per (point, pose) in the hot loop
+    # (profiles/README.md); 148 SMs x 4 schedulers x 1 warp-instruction/clk x 32 lanes at the sampled SM clock.
+    sm_clock_hz = 1e6 * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0)
+    pp_per_launch = n_culled * roofline["poses_per_launch"]
+    alu_peak = 148 * 4 * 32 * sm_clock_hz / 108.0
+    roofline["issue_bound"] = {
+        "achieved_pointposes_per_s": pp_per_launch / (k_ms * 1e-3), "peak_pointposes_per_s": alu_peak,
+        "frac": pp_per_launch / (k_ms * 1e-3) / alu_peak, "instr_per_pointpose": 108,
+        "note": "kernel time includes its ~10 us serial tail (merge, finalize, publish) and launch latency; at 5 M points x 8 poses the same kernel reaches 168 G point-poses/s",
+    }
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
