@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <map>
@@ -243,17 +244,33 @@ struct LaunchGeom {
   int copies;
   size_t smem;
   int blocks_per_sm;
+  int finalize_split;
 };
 
 static std::mutex g_geom_mu;
 static std::map<std::pair<const void*, size_t>, int> g_occupancy_cache;
 
-static int launch_geometry(NidKernel kernel, int n_poses, int nb, LaunchGeom* g) {
+static int hist_copies_cap() {
+  // warp-private copies buy nothing measurable over a couple of shared ones (profiles/r01_microbench.log: 1.32 vs 1.35 T
+  // atomics/s) but every copy is zeroed and merged by every block on every launch; VLCAL_HIST_COPIES overrides for A/B
+  static const int cap = [] {
+    const char* e = std::getenv("VLCAL_HIST_COPIES");
+    const int v = e ? std::atoi(e) : 2;
+    return std::max(1, std::min(v, NID_THREADS / 32));
+  }();
+  return cap;
+}
+
+static int launch_geometry(NidKernel kernel, int n_poses, int nb, int bins, LaunchGeom* g) {
   const size_t per_copy = static_cast<size_t>(n_poses) * nb * sizeof(int);
   int copies = static_cast<int>(NID_SMEM_TARGET / per_copy);
-  copies = std::max(1, std::min(copies, NID_THREADS / 32));
+  copies = std::max(1, std::min(copies, hist_copies_cap()));
   g->copies = copies;
   g->smem = per_copy * copies;
+  // room for nid_finalize to split one pose over several warps: 8 pose slots x (nb doubles + 2*bins ints)
+  const size_t split_need = static_cast<size_t>(NID_THREADS / 32) * (static_cast<size_t>(nb) * 8 + static_cast<size_t>(bins) * 8);
+  g->finalize_split = nb <= 1024;
+  if (g->finalize_split) g->smem = std::max(g->smem, split_need);
   std::lock_guard<std::mutex> lock(g_geom_mu);
   const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), g->smem);
   auto it = g_occupancy_cache.find(key);
@@ -434,12 +451,13 @@ static NidKernel select_kernel(vlcal_nid_ctx* ctx, bool devloop = false) {
 constexpr int PROFILE_STRIDE = 4;
 
 static int launch_one(vlcal_nid_ctx* ctx, NidKernel kernel, NidArgs& a, int geometry_poses, int profile_poses) {
-  LaunchGeom g{1, 0, 1};
+  LaunchGeom g{1, 0, 1, 0};
   {
-    const int rc = launch_geometry(kernel, geometry_poses, a.nb, &g);
+    const int rc = launch_geometry(kernel, geometry_poses, a.nb, a.bins, &g);
     if (rc != VLCAL_OK) return rc;
   }
   a.copies = g.copies;
+  a.finalize_split = g.finalize_split;
   const long long want_blocks = (a.n + NID_THREADS - 1) / NID_THREADS;
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want_blocks, static_cast<long long>(ctx->num_sms) * g.blocks_per_sm)));
   ProfileEvents* ev = nullptr;

@@ -63,6 +63,7 @@ struct NidArgs {
   int bins, nb;  // nb = bins*bins
   int n_poses;   // poses in this launch (<= NID_MAX_POSES)
   int copies;    // shared-memory histogram copies per block
+  int finalize_split;  // 1: the block's shared memory is large enough to stage one pose's terms per warp group (nid_finalize)
   double cos_fov;             // cos(max_fov)  (:32)
   CameraParams cam;
   double pose[NID_MAX_POSES][12];  // row-major 3x4 [R|t] of T_camera_lidar
@@ -308,8 +309,8 @@ template <bool DEVLOOP>
 static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   __shared__ int s_cnt[NID_THREADS / 32];  // per-warp partial inlier counts
-  // splitting a pose over several warps needs staging room: the block's histogram copies provide it when copies >= 4
-  const int wpp = a.copies >= 4 ? max(1, n_warps / n_poses) : 1;  // warps per pose
+  // splitting a pose over several warps needs staging room in the block's dynamic shared memory (host checks the size)
+  const int wpp = a.finalize_split ? max(1, n_warps / n_poses) : 1;  // warps per pose
   const int ppr = n_warps / wpp;                                     // poses per round
   double* s_term = reinterpret_cast<double*>(smem_i);                // [ppr][nb] staged p*log(p+1e-6) terms (wpp > 1)
   int* s_marg = smem_i + (wpp > 1 ? 2 * ppr * a.nb : 0);             // [ppr][2*bins] marginal counts
