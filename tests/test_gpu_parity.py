@@ -524,3 +524,50 @@ def test_pose_grid_search_finds_the_basin(gpu, oracle):
         return np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1)) + np.linalg.norm(d[:3, 3])
 
     assert dist_to_gt(best[0]) < dist_to_gt(T_rough)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fuzz: the filter's error bound must hold for arbitrary (plausible and less plausible) camera parameters
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def _random_camera(model, rng):
+    W, H = int(rng.integers(320, 2049)), int(rng.integers(240, 1537))
+    f = float(rng.uniform(0.25, 1.5) * W)
+    intr4 = [f, f * float(rng.uniform(0.9, 1.1)), W / 2 + float(rng.uniform(-40, 40)), H / 2 + float(rng.uniform(-40, 40))]
+    if model == "plumb_bob":
+        return intr4, list(rng.uniform(-1, 1, 5) * [0.3, 0.2, 5e-3, 5e-3, 0.1]), (W, H)
+    if model == "rational_polynomial":
+        return intr4, list(rng.uniform(-1, 1, 8) * [0.3, 0.2, 5e-3, 5e-3, 0.1, 0.3, 0.2, 0.1]), (W, H)
+    if model == "fisheye":
+        return intr4, list(rng.uniform(-1, 1, 4) * [0.1, 0.05, 0.02, 0.01]), (W, H)
+    if model == "atan":
+        return intr4, [float(rng.choice([0.0, 1e-8, rng.uniform(0.1, 1.2)]))], (W, H)
+    if model == "omnidir":
+        return intr4 + [float(rng.uniform(0.5, 2.0))], list(rng.uniform(-1, 1, 4) * [0.3, 0.1, 5e-3, 5e-3]), (W, H)
+    W2 = int(rng.integers(512, 4097))
+    return [float(W2), float(W2 // 2)], [], (W2, W2 // 2)
+
+
+@pytest.mark.parametrize("model", util.MODELS)
+def test_filter_bound_fuzz_over_random_cameras(gpu, model):
+    rng = np.random.default_rng(1234 + util.MODELS.index(model))
+    checked = 0
+    for trial in range(12):
+        intr, dist, (W, H) = _random_camera(model, rng)
+        pr = _adversarial_problem(model, 60000, seed=int(rng.integers(1 << 30)))
+        pr.update(intrinsics=intr, distortion=dist, W=W, H=H, image=rng.integers(0, 256, (H, W), dtype=np.uint8))
+        cost = _cost(gpu, pr)
+        if not cost.filter_enabled:
+            continue  # e.g. a pinhole whose estimated FoV reaches 87 degrees: exact kernel, nothing to check
+        Ts = util.random_poses(pr["T"], 8, seed=trial, rot_deg=float(rng.choice([0.3, 5.0, 60.0])), trans=float(rng.choice([0.01, 0.5, 3.0])))
+        n_pp, deferred, mismatches, ratio = cost.debug_filter_check(Ts)
+        assert mismatches == 0, (model, intr, dist, mismatches)
+        assert ratio < 1.0, (model, intr, dist, ratio)
+        # and the two kernels agree on the histograms themselves
+        h_f = cost.calculate_batch(Ts, return_hist=True)[1]
+        cost.set_kernel_variant(1)
+        h_e = cost.calculate_batch(Ts, return_hist=True)[1]
+        assert np.array_equal(h_f, h_e)
+        checked += 1
+    assert checked >= 6
