@@ -268,7 +268,8 @@ static int launch_geometry(NidKernel kernel, int n_poses, int nb, int bins, Laun
   g->copies = copies;
   g->smem = per_copy * copies;
   // room for nid_finalize to split one pose over several warps: 8 pose slots x (nb doubles + 2*bins ints)
-  const size_t split_need = static_cast<size_t>(NID_THREADS / 32) * (static_cast<size_t>(nb) * 8 + static_cast<size_t>(bins) * 8);
+  // 8 pose slots x (nb + 2*bins staged doubles + 2*bins marginal counts)
+  const size_t split_need = static_cast<size_t>(NID_THREADS / 32) * (static_cast<size_t>(nb + 2 * bins) * 8 + static_cast<size_t>(bins) * 8);
   g->finalize_split = nb <= 1024;
   if (g->finalize_split) g->smem = std::max(g->smem, split_need);
   std::lock_guard<std::mutex> lock(g_geom_mu);

@@ -313,7 +313,8 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
   const int wpp = a.finalize_split ? max(1, n_warps / n_poses) : 1;  // warps per pose
   const int ppr = n_warps / wpp;                                     // poses per round
   double* s_term = reinterpret_cast<double*>(smem_i);                // [ppr][nb] staged p*log(p+1e-6) terms (wpp > 1)
-  int* s_marg = smem_i + (wpp > 1 ? 2 * ppr * a.nb : 0);             // [ppr][2*bins] marginal counts
+  double* s_mterm = s_term + ppr * a.nb;                             // [ppr][2*bins] staged marginal terms (wpp > 1)
+  int* s_marg = smem_i + (wpp > 1 ? 2 * ppr * (a.nb + 2 * a.bins) : 0);  // [ppr][2*bins] marginal counts
   for (int p0 = 0; p0 < n_poses; p0 += ppr) {
     const int slot = warp / wpp, sub = warp % wpp;  // pose slot of this warp within the round, rank within the pose
     const int p = p0 + slot;
@@ -381,17 +382,28 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
         }
       }
     }
+    if (wpp > 1 && active) {  // marginal terms too are spread over the pose's warps (same arithmetic per term)
+      for (int f = sub * 32 + lane; f < 2 * a.bins; f += span) {
+        const double pm = static_cast<double>(f < a.bins ? h_image[f] : h_points[f - a.bins]) / sum;
+        s_mterm[slot * 2 * a.bins + f] = pm * log(pm + 1e-6);
+      }
+    }
     if (wpp > 1) __syncthreads();
     if (active && sub == 0) {  // one warp per pose: canonical reductions
+      double t_r = 0.0, t_s = 0.0;
       if (wpp > 1) {
         for (int k = lane; k < a.nb; k += 32) t_rs += s_term[slot * a.nb + k];
-      }
-      double t_r = 0.0, t_s = 0.0;
-      for (int k = lane; k < a.bins; k += 32) {
-        const double pi = static_cast<double>(h_image[k]) / sum;
-        const double pp = static_cast<double>(h_points[k]) / sum;
-        t_r += pi * log(pi + 1e-6);
-        t_s += pp * log(pp + 1e-6);
+        for (int k = lane; k < a.bins; k += 32) {
+          t_r += s_mterm[slot * 2 * a.bins + k];
+          t_s += s_mterm[slot * 2 * a.bins + a.bins + k];
+        }
+      } else {
+        for (int k = lane; k < a.bins; k += 32) {
+          const double pi = static_cast<double>(h_image[k]) / sum;
+          const double pp = static_cast<double>(h_points[k]) / sum;
+          t_r += pi * log(pi + 1e-6);
+          t_s += pp * log(pp + 1e-6);
+        }
       }
       const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);
       if (lane == 0) {
@@ -506,8 +518,19 @@ __device__ __forceinline__ void filter_drain32(const NidArgs& a, FilterWarp& w, 
 // one tile = 32*K consecutive points starting at `tile` (K per lane, warp-coalesced rows), swept over all P poses.
 // Software pipeline over the poses: the image-bin gathers of pose p are issued unconditionally (clamped address), stay
 // in flight while pose p+1 is classified, and are consumed by the histogram atomics one iteration later.
+// the K rows of a tile, one float4 per lane and row (rows beyond `end` come back as a point behind the camera)
+template <int K>
+__device__ __forceinline__ void filter_load_tile(const float4* __restrict__ pts, unsigned int tile, unsigned int end, int lane, float4 (&q)[K]) {
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const unsigned int i = tile + j * 32 + lane;
+    q[j] = make_float4(0.f, 0.f, -1.f, 0.f);
+    if (i < end) q[j] = __ldg(pts + i);
+  }
+}
+
 template <int MODEL, int K, bool DEVLOOP>
-__device__ __forceinline__ void filter_tile(const NidArgs& a, int n_poses, FilterWarp& w, const float4* __restrict__ pts, unsigned int tile, unsigned int end) {
+__device__ __forceinline__ void filter_tile(const NidArgs& a, int n_poses, FilterWarp& w, const float4* __restrict__ pts, unsigned int tile, unsigned int end, const float4 (&q)[K]) {
   float px[K], py[K], pz[K], pa[K];
   int lboff[K];
   unsigned int idx[K];
@@ -515,13 +538,10 @@ __device__ __forceinline__ void filter_tile(const NidArgs& a, int n_poses, Filte
 #pragma unroll
   for (int j = 0; j < K; j++) {
     idx[j] = tile + j * 32 + w.lane;
-    const bool valid = idx[j] < end;
-    float4 q = make_float4(0.f, 0.f, -1.f, 0.f);
-    if (valid) q = __ldg(pts + idx[j]);
-    valid_bits |= (valid ? 1u : 0u) << j;
-    px[j] = q.x, py[j] = q.y, pz[j] = q.z;
-    pa[j] = fabsf(q.x) + fabsf(q.y) + fabsf(q.z);
-    lboff[j] = lidar_bin_of(q.w, a.bins) * a.bins;
+    valid_bits |= (idx[j] < end ? 1u : 0u) << j;
+    px[j] = q[j].x, py[j] = q[j].y, pz[j] = q[j].z;
+    pa[j] = fabsf(q[j].x) + fabsf(q[j].y) + fabsf(q[j].z);
+    lboff[j] = lidar_bin_of(q[j].w, a.bins) * a.bins;
   }
   int pend_bin[K];
   unsigned int pend_ok = 0;
@@ -594,8 +614,6 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   if (n_poses == 0) return;  // device-resident loop: the solver has finished
   const int per_copy = n_poses * a.nb;
   if (a.timeline && threadIdx.x == 0 && blockIdx.x == 0) a.timeline[0] = global_ns();
-  for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
-  __syncthreads();
   const int warp = threadIdx.x >> 5;
   FilterWarp w;
   w.lane = threadIdx.x & 31;
@@ -611,11 +629,38 @@ __global__ void __launch_bounds__(NID_THREADS) nid_hist_filter_kernel(const __gr
   const unsigned int warp_global = blockIdx.x * (NID_THREADS / 32) + warp;
   const unsigned int chunk = ((n + warps_total - 1) / warps_total + 31u) & ~31u;  // points per warp, multiple of 32
   const unsigned long long lo = static_cast<unsigned long long>(warp_global) * chunk;
-  if (lo < n) {
-    const unsigned int end = static_cast<unsigned int>(min(static_cast<unsigned long long>(n), lo + chunk));
-    unsigned int t = static_cast<unsigned int>(lo);
-    for (; t + 32u * NID_KPT <= end; t += 32u * NID_KPT) filter_tile<MODEL, NID_KPT, DEVLOOP>(a, n_poses, w, pts, t, end);
-    for (; t < end; t += 32u) filter_tile<MODEL, 1, DEVLOOP>(a, n_poses, w, pts, t, end);
+  const bool has_work = lo < n;
+  const unsigned int end = has_work ? static_cast<unsigned int>(min(static_cast<unsigned long long>(n), lo + chunk)) : 0u;
+  unsigned int t = static_cast<unsigned int>(has_work ? lo : 0ull);
+  // the first tile's points are requested before the histogram copies are zeroed, so that their L2 latency overlaps it
+  float4 q4[NID_KPT];
+  const bool first_is_k4 = has_work && t + 32u * NID_KPT <= end;
+  if (first_is_k4) filter_load_tile<NID_KPT>(pts, t, end, w.lane, q4);
+  for (int i = threadIdx.x; i < a.copies * per_copy; i += blockDim.x) smem_hist[i] = 0;
+  __syncthreads();
+  if (has_work) {
+    // NID_KPT-row tiles, the next tile's rows in flight while the current one is swept over the poses
+    while (t + 32u * NID_KPT <= end) {
+      float4 nxt[NID_KPT];
+      const bool more = t + 64u * NID_KPT <= end;
+      if (more) filter_load_tile<NID_KPT>(pts, t + 32u * NID_KPT, end, w.lane, nxt);
+      filter_tile<MODEL, NID_KPT, DEVLOOP>(a, n_poses, w, pts, t, end, q4);
+      t += 32u * NID_KPT;
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < NID_KPT; j++) q4[j] = nxt[j];
+      }
+    }
+    // one-row tiles for what is left of the range, pipelined the same way
+    float4 q1[1], n1[1];
+    if (t < end) filter_load_tile<1>(pts, t, end, w.lane, q1);
+    while (t < end) {
+      const bool more = t + 32u < end;
+      if (more) filter_load_tile<1>(pts, t + 32u, end, w.lane, n1);
+      filter_tile<MODEL, 1, DEVLOOP>(a, n_poses, w, pts, t, end, q1);
+      t += 32u;
+      if (more) q1[0] = n1[0];
+    }
   }
   if (w.qn > 0) filter_drain32<MODEL, DEVLOOP>(a, w, pts, 0, w.qn);
   nid_block_epilogue<DEVLOOP>(a, n_poses, smem_hist, &s_is_last);
