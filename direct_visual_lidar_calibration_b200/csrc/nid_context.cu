@@ -157,37 +157,54 @@ int upload_cloud(int device, const double* points_xyzw, const double* intensitie
     const int rc = g_stage.reserve(static_cast<size_t>(n) * 32);
     if (rc != VLCAL_OK) return rc;
   }
-  // float4 (x,y,z,intensity) is lossless when the doubles came from a float32 PLY and intensity = k/256
+  // float4 (x,y,z,intensity) is lossless when the doubles came from a float32 PLY and intensity = k/256.
+  // Convert in a few chunks so that the H2D copy of chunk c overlaps the conversion of chunk c+1.
   float4* stage = static_cast<float4*>(g_stage.ptr);
   int lossless = 1, w_is_one = 1;
   // memory-bound copy-convert: a dozen threads saturate it; waking every core of a 128-core host costs more than it saves
   const int conv_threads = std::max(1, std::min(16, omp_get_max_threads()));
+  VL_CUDA(MemPool::instance().device_alloc(device, static_cast<size_t>(n) * 16, &cloud->d_points));
+  constexpr int64_t CHUNK = 1 << 18;
+  for (int64_t c0 = 0; c0 < n; c0 += CHUNK) {
+    const int64_t c1 = std::min<int64_t>(n, c0 + CHUNK);
 #pragma omp parallel for schedule(static) reduction(&& : lossless, w_is_one) num_threads(conv_threads)
-  for (int64_t i = 0; i < n; i++) {
-    const double* p = points_xyzw + 4 * i;
-    const float4 q = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(p[2]), static_cast<float>(intensities[i]));
-    stage[i] = q;
-    lossless = lossless && (static_cast<double>(q.x) == p[0] || p[0] != p[0]) && (static_cast<double>(q.y) == p[1] || p[1] != p[1]) &&
-               (static_cast<double>(q.z) == p[2] || p[2] != p[2]) && (static_cast<double>(q.w) == intensities[i] || intensities[i] != intensities[i]);
-    w_is_one = w_is_one && (p[3] == 1.0);
+    for (int64_t i = c0; i < c1; i++) {
+      const double* p = points_xyzw + 4 * i;
+      const float4 q = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(p[2]), static_cast<float>(intensities[i]));
+      stage[i] = q;
+      lossless = lossless && (static_cast<double>(q.x) == p[0] || p[0] != p[0]) && (static_cast<double>(q.y) == p[1] || p[1] != p[1]) &&
+                 (static_cast<double>(q.z) == p[2] || p[2] != p[2]) && (static_cast<double>(q.w) == intensities[i] || intensities[i] != intensities[i]);
+      w_is_one = w_is_one && (p[3] == 1.0);
+    }
+    if (!lossless || !w_is_one) break;
+    VL_CUDA(cudaMemcpyAsync(static_cast<float4*>(cloud->d_points) + c0, stage + c0, sizeof(float4) * static_cast<size_t>(c1 - c0), cudaMemcpyHostToDevice, stream));
   }
+  VL_CUDA(cudaStreamSynchronize(stream));  // staging buffer is shared
   if (!w_is_one) {
     set_last_error("points_xyzw: homogeneous coordinate w must be 1 for every point (Frame::points, frame.hpp:66)");
     return VLCAL_ERR_INVALID_ARGUMENT;
   }
   cloud->f32 = lossless != 0;
-  if (!cloud->f32) {
+  if (!cloud->f32) {  // not float32-representable: 32-byte double layout (exact kernel only)
+    for (int64_t i = 0; i < n; i++) {
+      if (points_xyzw[4 * i + 3] != 1.0) {
+        set_last_error("points_xyzw: homogeneous coordinate w must be 1 for every point (Frame::points, frame.hpp:66)");
+        return VLCAL_ERR_INVALID_ARGUMENT;
+      }
+    }
+    MemPool::instance().device_free(device, cloud->d_points);
+    cloud->d_points = nullptr;
     double4* stage64 = static_cast<double4*>(g_stage.ptr);
 #pragma omp parallel for schedule(static) num_threads(conv_threads)
     for (int64_t i = 0; i < n; i++) {
       const double* p = points_xyzw + 4 * i;
       stage64[i] = make_double4(p[0], p[1], p[2], intensities[i]);
     }
+    const size_t bytes = static_cast<size_t>(n) * 32;
+    VL_CUDA(MemPool::instance().device_alloc(device, bytes, &cloud->d_points));
+    VL_CUDA(cudaMemcpyAsync(cloud->d_points, g_stage.ptr, bytes, cudaMemcpyHostToDevice, stream));
+    VL_CUDA(cudaStreamSynchronize(stream));
   }
-  const size_t bytes = static_cast<size_t>(n) * cloud->bytes_per_point();
-  VL_CUDA(MemPool::instance().device_alloc(device, bytes, &cloud->d_points));
-  VL_CUDA(cudaMemcpyAsync(cloud->d_points, g_stage.ptr, bytes, cudaMemcpyHostToDevice, stream));
-  VL_CUDA(cudaStreamSynchronize(stream));  // staging buffer is shared
   *out = cloud;
   return VLCAL_OK;
 }
