@@ -3,14 +3,18 @@
 // Replaces the serial loop of CostCalculatorNID::calculate (reference:
 // src/vlcal/calib/cost_calculator_nid.cpp:30-52) and its entropy/NID tail (:54-64) for P candidate
 // poses in ONE pass over the cloud:
-//   per point  : one coalesced 16-byte load (x,y,z,intensity as float4 -- lossless)
+//   per point  : one coalesced 16-byte load (x,y,z,intensity as float4 -- lossless), prefetched one tile ahead
 //   per pose   : SE3 transform, FoV test, camera projection, truncation, bounds test, 1-byte gather from the
-//                pre-binned image, one shared-memory histogram increment
-//   per block  : warp-privatised P x bins x bins int32 histograms in shared memory, merged into the global
-//                accumulator with one red.global.add per non-zero bin
-//   last block : marginals (row/column sums), the three entropies, MI and NID for every pose; accumulators are
-//                zeroed again so the next launch needs no memset.
-// HBM-bound shape: 16 B/point + W*H B of image per pass regardless of P (DESIGN.md, section "roofline").
+//                pre-binned image, one shared-memory histogram increment.  Default kernel: fp32 with a rigorous
+//                per-point error bound, anything within the bound of a decision edge re-decided by the exact fp64
+//                path (bit-identical histograms); nid_hist_exact_kernel does everything in fp64.
+//   per block  : P x bins x bins int32 histogram copies in shared memory, merged into the global accumulator with
+//                one red.global.add per non-zero bin
+//   last block : marginals (row/column sums), the three entropies, MI and NID for every pose; optionally the sum over
+//                ranks (NVLink peer-memory exchange) and the next Nelder-Mead batch (device-resident loop); results
+//                published to mapped host memory; accumulators zeroed again so the next launch needs no memset.
+// Algorithmic traffic: 16 B/point + W*H B of image per pass regardless of P; the active bound is
+// instruction issue (108 warp-instructions per point-pose) and, for Nelder-Mead sized batches, the serial tail.
 #pragma once
 
 #include <cstdint>
