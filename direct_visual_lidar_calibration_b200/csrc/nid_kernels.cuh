@@ -225,10 +225,10 @@ static __device__ void nid_peer_allreduce(const NidArgs& a, int n_poses) {
   if (t < n_poses * a.p2p_world) {  // one thread per (peer, pose): remote stores over NVLink
     const int g = t / n_poses, p = t % n_poses;
     a.peer_box[g]->vals[a.p2p_rank][slot][p] = a.nid_out[p];
-    __threadfence_system();
   }
   __syncthreads();
-  if (t < a.p2p_world) {  // sequence word after the payload (system-scope fence above orders them)
+  if (t < a.p2p_world) {  // one system-scope fence per peer (cumulative over the barrier), then the sequence word
+    __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(&a.peer_box[t]->seq[a.p2p_rank][slot]) = seq;
     // wait for rank t's contribution to land in OUR mailbox
     volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(&a.peer_box[a.p2p_rank]->seq[t][slot]);
