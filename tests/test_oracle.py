@@ -257,3 +257,52 @@ def test_calibrate_recovers_ground_truth(oracle):
     c1 = oracle.nid_calculate(cam, bag["image"], bag["points"], bag["intensities"], 16, fov, r["T"])[0]
     assert c1 < c0  # the solve improves the NID
     assert r["outer_iterations"] >= 1 and r["total_evaluations"] == r["trace"].shape[0]
+
+
+def _numpy_nid_plumb_bob(image, pts, inten, intr, dist, bins, max_fov, T):
+    """Independent restatement of cost_calculator_nid.cpp:21-67 + pinhole.hpp in vectorised numpy (same operation order)."""
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    pc = [((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3] for r in range(3)]
+    n2 = (pc[0] * pc[0] + pc[1] * pc[1]) + pc[2] * pc[2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nz = np.where(n2 > 0, pc[2] / np.sqrt(n2), pc[2])
+        keep = ~(nz < math.cos(max_fov))
+        px, py = pc[0] / pc[2], pc[1] / pc[2]
+        k1, k2, p1, p2, k3 = dist
+        x2, y2 = px * px, py * py
+        r2 = x2 + y2
+        r4 = r2 * r2
+        r6 = r2 * r4
+        rc = 1.0 + k1 * r2 + k2 * r4 + k3 * r6
+        t1, t2, t3 = 2.0 * px * py, r2 + 2.0 * x2, r2 + 2.0 * y2
+        u = intr[0] * (rc * px + p1 * t1 + p2 * t2) + intr[2]
+        v = intr[1] * (rc * py + p1 * t3 + p2 * t1) + intr[3]
+        ok = np.isfinite(u) & np.isfinite(v) & (np.abs(u) < 2e9) & (np.abs(v) < 2e9)
+        ix = np.where(ok, np.trunc(np.where(ok, u, 0)), -1).astype(np.int64)
+        iy = np.where(ok, np.trunc(np.where(ok, v, 0)), -1).astype(np.int64)
+    H, W = image.shape
+    keep &= ok & (ix >= 0) & (iy >= 0) & (ix < W) & (iy < H)
+    pixel = image[iy[keep], ix[keep]] / 255.0
+    ib = np.clip((pixel * bins).astype(np.int64), 0, bins - 1)
+    lb = np.clip((inten[keep] * bins).astype(np.int64), 0, bins - 1)
+    hist = np.zeros((bins, bins), dtype=np.int64)
+    np.add.at(hist, (ib, lb), 1)
+    return hist
+
+
+def test_oracle_agrees_with_an_independent_numpy_restatement(oracle):
+    """Guards the C oracle against transcription slips: a second, vectorised restatement of the same reference lines."""
+    for seed, bins in ((1, 16), (2, 8), (3, 32)):
+        pr = util.random_problem("plumb_bob", n=40000, seed=seed)
+        cam = oracle.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
+        fov = oracle.estimate_camera_fov(cam, pr["W"], pr["H"])
+        for T in util.random_poses(pr["T"], 3, seed=seed):
+            _, h = oracle.nid_calculate(cam, pr["image"], pr["points"], pr["intensities"], bins, fov, T)
+            h_np = _numpy_nid_plumb_bob(pr["image"], pr["points"], pr["intensities"], pr["intrinsics"], pr["distortion"], bins, fov, T)
+            assert np.array_equal(h, h_np)
+            # entropy tail, independently
+            s = h_np.sum()
+            Hf = lambda p: -(p * np.log(p + 1e-6)).sum()  # noqa: E731
+            Hr, Hs, Hrs = Hf(h_np.sum(1) / s), Hf(h_np.sum(0) / s), Hf(h_np / s)
+            nid_np = (Hrs - (Hr + Hs - Hrs)) / Hrs
+            assert abs(nid_np - oracle.nid_from_hist(h)[0]) < 1e-13
