@@ -496,6 +496,7 @@ def test_fused_peer_exchange_matches_nccl_and_single_gpu(gpu):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "P2P_CHECK world=2 fused_close_to_nccl=True fused_equals_nccl=True" in out.stdout
     assert "DIST_CHECK world=2 identical=True close=True fused_identical_to_single_gpu=True" in out.stdout
+    assert "POSE_SHARD_CHECK world=2" in out.stdout and "identical=True" in out.stdout.split("POSE_SHARD_CHECK")[1]
 
 
 def test_pose_grid_search_finds_the_basin(gpu, oracle):

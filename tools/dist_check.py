@@ -72,6 +72,16 @@ if rank == 0:
     fused_same = np.array_equal(T1, Tp) and r1["y"] == rp["y"] and r1["num_iterations"] == rp["num_iterations"]
     print(f"DIST_CHECK world={world} identical={same} close={close} fused_identical_to_single_gpu={fused_same} iters={r['num_iterations']} y={r['y']:.12f} y_single={r1['y']:.12f}")
     assert close and r1["num_iterations"] == r["num_iterations"] and fused_same
+# axis (ii): pose-batch sharding -- every rank scores poses[rank::world] on its replica of bag 0, host-side gather
+from direct_visual_lidar_calibration_b200 import initial_guess as IG
+
+rep = V.CostCalculatorNID(cam, V.VisualLiDARData(bags[0]["image"], bags[0]["points"], bags[0]["intensities"]), device=local)
+grid = IG.pose_grid(T0, n_rot=(3, 3, 3), n_trans=(1, 2, 2), rot_half_deg=1.0, trans_half=0.02)
+sharded = IG.score_poses(rep, grid, rank, world)
+if rank == 0:
+    full = IG.score_poses(rep, grid)
+    print(f"POSE_SHARD_CHECK world={world} poses={len(grid)} identical={bool(np.array_equal(sharded, full, equal_nan=True))}")
+    assert np.array_equal(sharded, full, equal_nan=True)
 dist.barrier()
 px.close()
 dist.destroy_process_group()
