@@ -874,7 +874,7 @@ int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant) {
   return VLCAL_OK;
 }
 
-int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double out_us[8]) {
+int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double out_us[12]) {
   if (!ctx || !T_camera_lidar || n_poses <= 0 || n_poses > NID_MAX_POSES || !out_us) {
     set_last_error("invalid arguments (one launch: n_poses <= 8)");
     return VLCAL_ERR_INVALID_ARGUMENT;
@@ -900,7 +900,10 @@ int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, i
   out_us[4] = (static_cast<double>(t[5]) - base) * 1e-3;  // published
   out_us[5] = ((ts1.tv_sec - ts0.tv_sec) * 1e9 + (ts1.tv_nsec - ts0.tv_nsec)) * 1e-3;  // host: launch call
   out_us[6] = ((ts2.tv_sec - ts0.tv_sec) * 1e9 + (ts2.tv_nsec - ts0.tv_nsec)) * 1e-3;  // host: launch -> results visible
-  out_us[7] = 0.0;
+  out_us[7] = (static_cast<double>(t[7]) - base) * 1e-3;   // finalize: fence + scratch zeroed
+  out_us[8] = (static_cast<double>(t[8]) - base) * 1e-3;   // finalize: marginals + inlier count known
+  out_us[9] = (static_cast<double>(t[9]) - base) * 1e-3;   // finalize: entropy terms staged
+  out_us[10] = out_us[11] = 0.0;
   MemPool::instance().pinned_free(ctx->h_timeline);
   ctx->h_timeline = nullptr;
   return rc;

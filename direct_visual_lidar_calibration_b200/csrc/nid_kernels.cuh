@@ -146,8 +146,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// timeline slots: 0 first block start (min), 1 last-block: main loop done, 2 merged+fenced, 3 ticket known,
-// 4 finalize math done, 5 results published (after the system fence), 6 last block start
+// timeline slots: 0 first block start, 1 last-block: main loop done, 2 merged+fenced, 3 ticket known, 4 finalize done,
+// 5 results published (after the system fence); inside finalize: 7 scratch zeroed, 8 marginals + count known,
+// 9 entropy terms staged
 __device__ __forceinline__ void stamp(const NidArgs& a, int slot) {
   if (a.timeline && threadIdx.x == 0) a.timeline[slot] = global_ns();
 }
@@ -207,6 +208,29 @@ __device__ __forceinline__ double warp_sum(double v) {
 // different P; equal histograms must give equal bits): the p*log(p) terms are therefore staged in shared memory and
 // reduced by one warp in a canonical order -- lane l adds terms l, l+32, ... in ascending order, then a fixed xor tree.
 constexpr int FIN_CH = 8;
+
+// natural logarithm for normal, positive, finite arguments (here p + 1e-6 in [1e-6, 1 + 1e-6]), without the special-case
+// branches of the library routine, so that the independent terms a lane evaluates interleave instead of serialising
+// (the library log cost 0.5 us per term in the launch's serial tail).  Algorithm of fdlibm's __ieee754_log (argument
+// reduction to [sqrt(1/2), sqrt(2)), s = f/(2+f), degree-14 even/odd polynomial split, hi/lo ln2), error < 1 ulp.
+__device__ __forceinline__ double log_pos_normal(double x) {
+  const long long bits = __double_as_longlong(x);
+  int k = static_cast<int>((bits >> 52) & 0x7ff) - 1023;
+  double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);  // [1, 2)
+  const bool hi = m > 1.4142135623730951;
+  m = hi ? m * 0.5 : m;
+  k += hi ? 1 : 0;
+  const double f = m - 1.0;
+  const double s = f / (2.0 + f);
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
+  const double R = t1 + t2;
+  const double hfsq = 0.5 * f * f;
+  const double dk = static_cast<double>(k);
+  return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
 
 __device__ __forceinline__ double warp_tree_sum(double v) {
 #pragma unroll
@@ -327,6 +351,7 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
     int* h_points = h_image + a.bins;           // [bins]
     for (int i = threadIdx.x; i < ppr * 2 * a.bins; i += blockDim.x) s_marg[i] = 0;
     __syncthreads();
+    stamp(a, 7);
     int* g = a.ghist + static_cast<size_t>(active ? p : 0) * a.nb;
     const int span = wpp * 32;  // joint bins covered per step by the warps of one pose
     int part = 0;
@@ -354,6 +379,7 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) s_cnt[warp] = part;
     __syncthreads();
+    stamp(a, 8);
     double t_rs = 0.0;  // canonical per-lane partial of the joint entropy (only meaningful when wpp == 1)
     double sum = 0.0;
     if (active) {
@@ -374,7 +400,7 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
           const int k = k0 + m * span + sub * 32 + lane;
           if (k < a.nb) {
             const double pr = static_cast<double>(c[m]) / sum;
-            const double term = pr * log(pr + 1e-6);
+            const double term = pr * log_pos_normal(pr + 1e-6);
             if (wpp > 1) {
               s_term[slot * a.nb + k] = term;
             } else {
@@ -389,10 +415,11 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
     if (wpp > 1 && active) {  // marginal terms too are spread over the pose's warps (same arithmetic per term)
       for (int f = sub * 32 + lane; f < 2 * a.bins; f += span) {
         const double pm = static_cast<double>(f < a.bins ? h_image[f] : h_points[f - a.bins]) / sum;
-        s_mterm[slot * 2 * a.bins + f] = pm * log(pm + 1e-6);
+        s_mterm[slot * 2 * a.bins + f] = pm * log_pos_normal(pm + 1e-6);
       }
     }
     if (wpp > 1) __syncthreads();
+    stamp(a, 9);
     if (active && sub == 0) {  // one warp per pose: canonical reductions
       double t_r = 0.0, t_s = 0.0;
       if (wpp > 1) {
@@ -405,8 +432,8 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
         for (int k = lane; k < a.bins; k += 32) {
           const double pi = static_cast<double>(h_image[k]) / sum;
           const double pp = static_cast<double>(h_points[k]) / sum;
-          t_r += pi * log(pi + 1e-6);
-          t_s += pp * log(pp + 1e-6);
+          t_r += pi * log_pos_normal(pi + 1e-6);
+          t_s += pp * log_pos_normal(pp + 1e-6);
         }
       }
       const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);

@@ -145,8 +145,9 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
 
 /* measurement hook: one launch (n_poses <= 8) with %globaltimer stamps; out_us = {main loop done, merged, ticket, finalize done,
- * published} in microseconds since the first block started, then host-side {launch call, launch->results visible} */
-int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double out_us[8]);
+ * published} in microseconds since the first block started, host-side {launch call, launch->results visible}, then inside the
+ * finalize {scratch zeroed, marginals known, entropy terms staged}; 12 doubles */
+int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, double out_us[12]);
 /* permutes the context's cloud so that points projecting to the same 32x8-pixel image tile at pose T are adjacent (GPU
  * counting sort).  The integer histogram -- hence every NID value -- is invariant under this permutation; it only makes
  * the per-point image gathers of later evaluations near T coalesce.  Contexts built by vlcal_estimate_pose_nelder_mead /
