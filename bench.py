@@ -384,6 +384,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "dtype_note": "geometry decided in f64 semantics: fp32 filter with a rigorous error bound + exact f64 recheck (integer histograms identical to the all-f64 kernel); histogram int32; entropies f64",
         "config": {
             "workload": WORKLOAD, "points": data.size(), "culled_points": n_culled, "image": f"{W}x{H}", "bags": world, "parallelism": f"bags{world}" if world > 1 else "single", "exchange": (args.exchange if world > 1 else None),
             "l2": "flushed (256 MiB write) between steps; within a step the culled cloud is re-read every NM iteration by the algorithm itself",
