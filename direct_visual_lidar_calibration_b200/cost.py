@@ -108,8 +108,8 @@ class CostCalculatorNID:
         Tc = T_to_colmajor(Ts)
         out = np.zeros(12)
         _lib.check(self._L.vlcal_nid_debug_timeline(self._ctx, _dp(Tc), Tc.shape[0], _dp(out)))
-        keys = ["main_done", "merged", "ticket", "finalize_done", "published", "host_launch_call", "host_total", "fin_zeroed", "fin_marginals", "fin_terms"]
-        return dict(zip(keys, out[:10]))
+        keys = ["main_done", "merged", "ticket", "finalize_done", "published", "host_launch_call", "host_total", "fin_zeroed", "fin_marginals", "fin_terms", "p2p_enter", "p2p_arrived"]
+        return dict(zip(keys, out[:12]))
 
     @property
     def filter_enabled(self) -> bool:

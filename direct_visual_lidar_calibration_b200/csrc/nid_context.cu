@@ -903,7 +903,8 @@ int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, i
   out_us[7] = (static_cast<double>(t[7]) - base) * 1e-3;   // finalize: fence + scratch zeroed
   out_us[8] = (static_cast<double>(t[8]) - base) * 1e-3;   // finalize: marginals + inlier count known
   out_us[9] = (static_cast<double>(t[9]) - base) * 1e-3;   // finalize: entropy terms staged
-  out_us[10] = out_us[11] = 0.0;
+  out_us[10] = t[10] ? (static_cast<double>(t[10]) - base) * 1e-3 : 0.0;  // peer exchange entered
+  out_us[11] = t[11] ? (static_cast<double>(t[11]) - base) * 1e-3 : 0.0;  // all peers' contributions arrived
   MemPool::instance().pinned_free(ctx->h_timeline);
   ctx->h_timeline = nullptr;
   return rc;

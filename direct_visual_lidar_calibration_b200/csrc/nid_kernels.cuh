@@ -241,6 +241,7 @@ __device__ __forceinline__ double warp_tree_sum(double v) {
 // called by the finalizing block after every pose's local score sits in a.nid_out (block-synchronised)
 static __device__ void nid_peer_allreduce(const NidArgs& a, int n_poses) {
   __shared__ unsigned long long s_seq;
+  stamp(a, 10);
   const int t = threadIdx.x;
   if (t == 0) s_seq = ++(*a.p2p_counter);  // every rank performs the same sequence of exchanges
   __syncthreads();
@@ -267,6 +268,7 @@ static __device__ void nid_peer_allreduce(const NidArgs& a, int n_poses) {
     __threadfence_system();
   }
   __syncthreads();
+  stamp(a, 11);
   if (t < n_poses) {
     double total = 0.0;
     for (int r = 0; r < a.p2p_world; r++) total += __ldcv(&a.peer_box[a.p2p_rank]->vals[r][slot][t]);  // rank order: identical on every rank
