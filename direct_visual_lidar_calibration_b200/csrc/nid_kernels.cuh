@@ -32,13 +32,14 @@ constexpr int NID_MAX_BINS = 128;  // bins*bins*4 B must fit shared memory at le
 // ---- fused bag all-reduce over NVLink peer memory (multi-GPU, one bag per rank) -------------------------------
 // The joint objective is sum_bags NID (visual_camera_calibration.cpp:105-110).  With one process per GPU and one bag
 // per process, the finalizing block of every rank stores its P scores straight into every peer's mailbox (P2P stores
-// through NVLink / NVSwitch, buffers shared with cudaIpc), bumps a sequence word, waits for the other ranks' words and
-// adds the G contributions in rank order -- so all ranks publish bit-identical sums without a separate collective
+// through NVLink / NVSwitch, buffers shared with cudaIpc; data words carry a sequence tag), waits for the other ranks'
+// words and adds the G contributions in rank order -- so all ranks publish bit-identical sums without a separate collective
 // launch and without leaving the kernel.  Two slots (seq & 1) because a rank can be at most one exchange ahead.
 constexpr int P2P_MAX_RANKS = 8;
+// Each double travels as two 8-byte words {32 data bits | 32-bit sequence tag}: an aligned 8-byte store is never torn,
+// so the data IS its own arrival flag -- no fence + separate flag store (one NVLink round trip less per exchange).
 struct P2PMailbox {
-  double vals[P2P_MAX_RANKS][2][8];        // [sender][slot][pose]
-  unsigned long long seq[P2P_MAX_RANKS][2];  // [sender][slot]
+  unsigned long long ll[P2P_MAX_RANKS][2][8][2];  // [sender][slot][pose][lo, hi]
 };
 
 // ---- device-resident Nelder-Mead loop ---------------------------------------------------------------------
@@ -241,37 +242,43 @@ __device__ __forceinline__ double warp_tree_sum(double v) {
 // called by the finalizing block after every pose's local score sits in a.nid_out (block-synchronised)
 static __device__ void nid_peer_allreduce(const NidArgs& a, int n_poses) {
   __shared__ unsigned long long s_seq;
+  __shared__ double s_part[P2P_MAX_RANKS][8];
   stamp(a, 10);
   const int t = threadIdx.x;
   if (t == 0) s_seq = ++(*a.p2p_counter);  // every rank performs the same sequence of exchanges
   __syncthreads();
   const unsigned long long seq = s_seq;
   const int slot = static_cast<int>(seq & 1ull);
-  if (t < n_poses * a.p2p_world) {  // one thread per (peer, pose): remote stores over NVLink
+  const unsigned long long tag = ((seq & 0x7fffffffull) | 0x80000000ull) << 32;  // never 0 (the mailbox starts zeroed)
+  if (t < n_poses * a.p2p_world) {  // one thread per (peer, pose)
     const int g = t / n_poses, p = t % n_poses;
-    a.peer_box[g]->vals[a.p2p_rank][slot][p] = a.nid_out[p];
-  }
-  __syncthreads();
-  if (t < a.p2p_world) {  // one system-scope fence per peer (cumulative over the barrier), then the sequence word
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long*>(&a.peer_box[t]->seq[a.p2p_rank][slot]) = seq;
-    // wait for rank t's contribution to land in OUR mailbox
-    volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(&a.peer_box[a.p2p_rank]->seq[t][slot]);
-    const unsigned long long t0 = global_ns();
-    unsigned int spins = 0;
-    while (*w != seq) {
-      if ((++spins & 1023u) == 0 && global_ns() - t0 > 2000000000ull) {  // 2 s: a peer died or fell out of lockstep
-        if (a.p2p_error) *a.p2p_error = 1;
-        break;
-      }
+    {  // remote stores over NVLink: our partial sum -> rank g's mailbox
+      const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(a.nid_out[p]));
+      volatile unsigned long long* dst = a.peer_box[g]->ll[a.p2p_rank][slot][p];
+      dst[0] = tag | (bits & 0xffffffffull);
+      dst[1] = tag | (bits >> 32);
     }
-    __threadfence_system();
+    {  // wait for rank g's partial sum of pose p to land in OUR mailbox
+      volatile unsigned long long* src = a.peer_box[a.p2p_rank]->ll[g][slot][p];
+      const unsigned long long t0 = global_ns();
+      unsigned int spins = 0;
+      unsigned long long lo, hi;
+      for (;;) {
+        lo = src[0], hi = src[1];
+        if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+        if ((++spins & 1023u) == 0 && global_ns() - t0 > 2000000000ull) {  // 2 s: a peer died or fell out of lockstep
+          if (a.p2p_error) *a.p2p_error = 1;
+          break;
+        }
+      }
+      s_part[g][p] = __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffull)));
+    }
   }
   __syncthreads();
   stamp(a, 11);
   if (t < n_poses) {
     double total = 0.0;
-    for (int r = 0; r < a.p2p_world; r++) total += __ldcv(&a.peer_box[a.p2p_rank]->vals[r][slot][t]);  // rank order: identical on every rank
+    for (int r = 0; r < a.p2p_world; r++) total += s_part[r][t];  // rank order: identical on every rank
     a.nid_out[t] = total;
     if (a.nid_host) a.nid_host[t] = total;
   }
