@@ -1,0 +1,143 @@
+// ref_shim.cpp -- C entry points over the REFERENCE's own sources of the NID path (test infrastructure, NOT product).
+//
+// oracle/Makefile (target `ref`) compiles, from where they lie under /root/reference,
+//     src/camera/create_camera.cpp            (+ include/camera/*.hpp: the six projection models)
+//     src/vlcal/common/estimate_fov.cpp       (estimate_direction / estimate_camera_fov, dfo::NelderMead<2>)
+//     src/vlcal/calib/cost_calculator_nid.cpp (CostCalculatorNID::calculate, the hot path itself)
+//     src/vlcal/calib/view_culling.cpp        (ViewCulling::cull)
+//     include/dfo/nelder_mead.hpp             (instantiated below for N = 2, 3, 6)
+// against the stand-in headers in oracle/ref_standin/ (Eigen, OpenCV's cv::Mat, ceres::Jet, pcl: none of them is
+// installed here), and links them with this file into oracle/_ref/libvlcal_ref.so.  tests/ use it to pin
+// oracle/vlcal_oracle.c: same inputs through the reference's code and through the restatement.  No reference source is
+// copied into this repository; /root/reference is needed at build time only.
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <camera/create_camera.hpp>
+#include <dfo/nelder_mead.hpp>
+#include <vlcal/calib/cost_calculator_nid.hpp>
+#include <vlcal/calib/view_culling.hpp>
+#include <vlcal/common/estimate_fov.hpp>
+
+namespace vlcal {
+// Members whose reference translation units are not compiled (frame_cpu.cpp needs boost::filesystem and much more of
+// Eigen, visual_lidar_data.cpp needs the PLY / image readers).  Nothing numerical lives in them.
+FrameCPU::FrameCPU() {}
+FrameCPU::~FrameCPU() {}
+VisualLiDARData::~VisualLiDARData() {}
+
+static thread_local std::vector<int> g_sampled_indices;
+// frame_cpu.cpp: sample() gathers the listed points into a new frame; ViewCulling::cull (view_culling.cpp:32) ends with
+// it.  The stand-in only records the indices, which is what the pin test compares.
+FrameCPU::Ptr sample(const Frame::ConstPtr&, const std::vector<int>& indices) {
+  g_sampled_indices = indices;
+  return std::make_shared<FrameCPU>();
+}
+}  // namespace vlcal
+
+namespace {
+
+struct RefCamera {
+  camera::GenericCameraBase::ConstPtr proj;
+};
+
+Eigen::Isometry3d isometry_from_colmajor(const double* T) {
+  Eigen::Isometry3d iso;
+  for (int c = 0; c < 4; c++) {
+    for (int r = 0; r < 4; r++) iso.matrix()(r, c) = T[r + 4 * c];
+  }
+  return iso;
+}
+
+// a frame over caller-owned (x, y, z, w) doubles: Eigen::Vector4d is four packed doubles
+std::shared_ptr<vlcal::FrameCPU> frame_over(const double* points_xyzw, const double* intensities, int64_t n) {
+  static_assert(sizeof(Eigen::Vector4d) == 4 * sizeof(double), "Vector4d layout");
+  auto frame = std::make_shared<vlcal::FrameCPU>();
+  frame->num_points = static_cast<size_t>(n);
+  frame->points = reinterpret_cast<Eigen::Vector4d*>(const_cast<double*>(points_xyzw));
+  frame->intensities = const_cast<double*>(intensities);
+  return frame;
+}
+
+typedef double (*ref_nm_function)(const double* x, void* user);
+
+template <int N>
+void run_nelder_mead(ref_nm_function f, void* user, const double* x0, const double* p, double* out_x, double* out_y, int* out_converged, int* out_iterations) {
+  typename dfo::NelderMead<N>::Params params;
+  params.init_step = p[0], params.alpha = p[1], params.gamma = p[2], params.rho = p[3], params.sigma = p[4];
+  params.max_iterations = static_cast<int>(p[5]);
+  params.convergence_var_thresh = p[6];
+  dfo::NelderMead<N> optimizer(params);
+  Eigen::Matrix<double, N, 1> start;
+  for (int i = 0; i < N; i++) start[i] = x0[i];
+  const auto result = optimizer.optimize([&](const Eigen::Matrix<double, N, 1>& x) { return f(x.data(), user); }, start);
+  for (int i = 0; i < N; i++) out_x[i] = result.x[i];
+  *out_y = result.y;
+  *out_converged = result.converged ? 1 : 0;
+  *out_iterations = result.num_iterations;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* ref_create_camera(const char* camera_model, const double* intrinsics, int n_intr, const double* distortion, int n_dist) {
+  const auto proj = camera::create_camera(camera_model, std::vector<double>(intrinsics, intrinsics + n_intr), std::vector<double>(distortion, distortion + n_dist));
+  if (!proj) return nullptr;
+  return new RefCamera{proj};
+}
+
+void ref_free_camera(void* cam) { delete static_cast<RefCamera*>(cam); }
+
+void ref_project(const void* cam, int64_t n, const double* points_xyz, double* uv) {
+  const auto& proj = static_cast<const RefCamera*>(cam)->proj;
+  for (int64_t i = 0; i < n; i++) {
+    const Eigen::Vector2d p = proj->project(Eigen::Vector3d(points_xyz[3 * i], points_xyz[3 * i + 1], points_xyz[3 * i + 2]));
+    uv[2 * i] = p[0], uv[2 * i + 1] = p[1];
+  }
+}
+
+double ref_estimate_camera_fov(const void* cam, int width, int height) {
+  return vlcal::estimate_camera_fov(static_cast<const RefCamera*>(cam)->proj, Eigen::Vector2i(width, height));
+}
+
+// params = {init_step, alpha, gamma, rho, sigma, max_iterations, convergence_var_thresh}
+int ref_nelder_mead(int n, ref_nm_function f, void* user, const double* x0, const double* params, double* out_x, double* out_y, int* out_converged, int* out_iterations) {
+  switch (n) {
+    case 2: run_nelder_mead<2>(f, user, x0, params, out_x, out_y, out_converged, out_iterations); return 0;
+    case 3: run_nelder_mead<3>(f, user, x0, params, out_x, out_y, out_converged, out_iterations); return 0;
+    case 6: run_nelder_mead<6>(f, user, x0, params, out_x, out_y, out_converged, out_iterations); return 0;
+    default: return -1;
+  }
+}
+
+// one CostCalculatorNID (its constructor runs estimate_camera_fov), scored at n_poses column-major 4x4 poses
+int ref_nid_calculate(
+  const void* cam, const uint8_t* image, int width, int height, int row_stride, const double* points_xyzw, const double* intensities, int64_t n, int bins,
+  int n_poses, const double* T_camera_lidar, double* nid_out) {
+  auto data = std::make_shared<vlcal::VisualLiDARData>();
+  data->image = cv::Mat(height, width, CV_8UC1, const_cast<uint8_t*>(image), static_cast<size_t>(row_stride));
+  data->points = frame_over(points_xyzw, intensities, n);
+  vlcal::NIDCostParams params;
+  params.bins = bins;
+  vlcal::CostCalculatorNID cost(static_cast<const RefCamera*>(cam)->proj, data, params);
+  for (int k = 0; k < n_poses; k++) nid_out[k] = cost.calculate(isometry_from_colmajor(T_camera_lidar + 16 * k));
+  return 0;
+}
+
+// ViewCulling::cull; returns the number of kept points, their indices in indices_out (capacity n)
+int64_t ref_view_cull(
+  const void* cam, int width, int height, int enable_depth_buffer_culling, const double* points_xyzw, int64_t n, const double* T_camera_lidar, int32_t* indices_out) {
+  vlcal::ViewCullingParams params;
+  params.enable_depth_buffer_culling = enable_depth_buffer_culling != 0;
+  const vlcal::ViewCulling culling(static_cast<const RefCamera*>(cam)->proj, Eigen::Vector2i(width, height), params);
+  culling.cull(frame_over(points_xyzw, nullptr, n), isometry_from_colmajor(T_camera_lidar));
+  const auto& kept = vlcal::g_sampled_indices;
+  for (size_t i = 0; i < kept.size(); i++) indices_out[i] = kept[i];
+  return static_cast<int64_t>(kept.size());
+}
+
+}  // extern "C"

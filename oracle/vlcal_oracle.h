@@ -7,16 +7,20 @@
  * cpu_baseline / --impl reference legs may link or call this.  The product library
  * (direct_visual_lidar_calibration_b200/csrc) never includes or links it.
  *
- * PARITY STATUS: "parity unpinned" against the reference binary itself -- the reference
- * cannot be compiled here (no Eigen/OpenCV/Ceres/GTSAM/Boost/Iridescence/PCL in this image)
- * and ships no tests or golden vectors.  The pins that exist are
- * ours: known-answer vectors derived by hand from the reference formulas (tests/golden/),
- * OpenCV cross-checks of the camera models the reference declares OpenCV-compatible, and
- * property tests.  Third-party arithmetic restated from published semantics:
- *   - GTSAM 4.2a9 Pose3::Expmap / SO3::Expmap (docs/installation.md:27)
- *   - Eigen 3.4 Isometry3d*Vector4d, normalized(), cast<int>(), AngleAxisd(Matrix3d)
- *   - libstdc++ std::sort insertion-sort branch for n <= 16
+ * PARITY STATUS: pinned against the reference's OWN sources of the path (camera models,
+ * dfo::NelderMead, estimate_camera_fov, CostCalculatorNID::calculate, ViewCulling::cull), compiled
+ * from /root/reference against stand-in third-party headers -- oracle/ref_shim.cpp,
+ * oracle/ref_standin/, tests/test_reference_pin.py: bit-exact on every comparison.  The reference
+ * cannot be built as it ships (no Eigen/OpenCV/Ceres/GTSAM/Boost/Iridescence/PCL in this image) and
+ * has no tests or golden vectors, so what stays "parity unpinned" is the
+ * third-party arithmetic itself, restated from published semantics here and in the stand-ins alike:
+ *   - GTSAM 4.2a9 Pose3::Expmap / SO3::Expmap (docs/installation.md:27); visual_camera_calibration.cpp
+ *     (the caller of Expmap) is not among the compiled reference sources
+ *   - Eigen 3.4 Isometry3d*Vector4d, normalized(), reduction orders, cast<int>(), AngleAxisd(Matrix3d)
+ *   - libstdc++ std::sort insertion-sort branch for n <= 16 (pinned: the reference build uses the real std::sort)
  *   - Sophus SO3/SE3 point action (thirdparty/Sophus/sophus/so3.hpp:408-417, se3.hpp:319-322)
+ * Further pins of ours: hand-derived known answers (tests/golden/), OpenCV cross-checks of the
+ * camera models the reference declares OpenCV-compatible, property tests.
  *
  * Build: see oracle/Makefile (gcc -O2 -g -ffp-contract=off, the reference's RelWithDebInfo
  * without -march, CMakeLists.txt:7-10).

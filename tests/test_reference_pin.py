@@ -1,0 +1,170 @@
+"""Pins the oracle (oracle/vlcal_oracle.c) against the REFERENCE's own sources of the path, compiled here from
+/root/reference (oracle/ref_shim.cpp + oracle/ref_standin/ -> oracle/_ref/libvlcal_ref.so).
+
+What runs on the reference side is the reference's code: create_camera.cpp + camera/*.hpp, dfo/nelder_mead.hpp,
+estimate_fov.cpp, cost_calculator_nid.cpp, view_culling.cpp.  Third-party headers (Eigen, cv::Mat, ...) are stand-ins,
+so Eigen's own reduction orders are restated, not pinned (oracle/ref_standin/Eigen/Core lists the conventions); the
+comparisons below are therefore bit-exact, and the NID tolerance of the GPU tests (1e-12 on the entropy tail) covers
+what the stand-in cannot pin.  CPU-only; skipped where neither /root/reference nor a prebuilt library exists."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import util as U
+from oracle import oracle as O
+from oracle import reference as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if R.build() is None:
+        pytest.skip("oracle/_ref/libvlcal_ref.so not built and /root/reference not present")
+    return R
+
+
+def cameras(model):
+    intr, dist, (W, H) = U.CAMERAS[model]
+    return O.create_camera(model, intr, dist), R.Camera(model, intr, dist), W, H
+
+
+def special_points():
+    e = 1e-300
+    return np.array(
+        [[0, 0, 0], [0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [0, -1, 0], [1e-4, 0, 1e-4], [0, 1e-2, 1e-2], [3, 4, 1e-9], [1e-3, 1e-3, 1.0], [e, e, e], [1e200, 1e200, 1e200],
+         [np.nan, 0, 1], [np.inf, 0, 1], [0.5, -0.25, 2.0], [-7.0, 3.0, 0.1], [2.0, 2.0, -0.5], [0.0, 0.0, 1e-320]], dtype=np.float64)
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+def test_projection_bit_exact(ref, model):
+    oc, rc, W, H = cameras(model)
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([rng.normal(size=(30000, 3)) * rng.uniform(0.01, 40.0, (30000, 1)), special_points()])
+    uv_o = np.array([O.project(oc, p) for p in pts])
+    uv_r = ref.project(rc, pts)
+    assert np.array_equal(uv_o.view(np.uint64), uv_r.view(np.uint64)) or np.array_equal(uv_o, uv_r, equal_nan=True)
+    finite = np.isfinite(uv_o).all(axis=1)
+    assert np.array_equal(uv_o[finite].view(np.uint64), uv_r[finite].view(np.uint64))  # signed zeros included
+
+
+def test_create_camera_rejections(ref):
+    assert ref.Camera("no_such_model", [1, 1, 1, 1], []).handle is None  # create_camera.cpp:49-50
+    assert ref.Camera("plumb_bob", [1, 1, 1], []).handle is None  # :19-22
+    assert O.create_camera("no_such_model", [1, 1, 1, 1], []) is None
+    assert O.create_camera("plumb_bob", [1, 1, 1], []) is None
+    # short distortion lists are zero-padded, long ones truncated (:24-27)
+    for dist in ([], [-0.04], [-0.04, 0.08, 1e-4, -3e-4, -0.04, 9.0, 9.0]):
+        oc, rc = O.create_camera("plumb_bob", [400, 410, 320, 240], dist), ref.Camera("plumb_bob", [400, 410, 320, 240], dist)
+        p = np.array([[0.3, -0.2, 1.5]])
+        assert np.array_equal(np.array([O.project(oc, p[0])]), ref.project(rc, p))
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+def test_estimate_camera_fov_bit_exact(ref, model):
+    oc, rc, W, H = cameras(model)
+    assert O.estimate_camera_fov(oc, W, H) == ref.estimate_camera_fov(rc, W, H)
+    assert O.estimate_camera_fov(oc, W // 2 + 1, H // 3) == ref.estimate_camera_fov(rc, W // 2 + 1, H // 3)  # odd sizes: integer halves (:37)
+
+
+def _objectives():
+    def rosenbrock(x):
+        return float(100.0 * (x[1] - x[0] ** 2) ** 2 + (1.0 - x[0]) ** 2)
+
+    def bowl(x):
+        return float(np.sum((x - np.arange(len(x)) * 0.1) ** 2))
+
+    def plateau(x):  # many exact ties: the sort / comparison order decides the trajectory
+        return float(np.floor(4.0 * np.abs(x).sum()) / 4.0)
+
+    def with_nan(x):  # NaN scores take the reference's comparison path
+        return float("nan") if x[0] > 0.15 else float(np.sum(x * x) + np.sin(5.0 * x[-1]))
+
+    def ridge(x):
+        return float(abs(x[0] - x[1]) + 0.01 * np.sum(x * x))
+
+    return {"rosenbrock": rosenbrock, "bowl": bowl, "plateau": plateau, "with_nan": with_nan, "ridge": ridge}
+
+
+@pytest.mark.parametrize("n", [2, 3, 6])
+@pytest.mark.parametrize("name", list(_objectives().keys()))
+def test_nelder_mead_trajectory_identical(ref, n, name):
+    f = _objectives()[name]
+    rng = np.random.default_rng(5 + n)
+    for trial, kw in enumerate([dict(), dict(init_step=1e-3, convergence_var_thresh=1e-10, max_iterations=60), dict(init_step=0.5, max_iterations=7)]):
+        x0 = rng.uniform(-0.3, 0.3, n) if trial else np.zeros(n)
+        a = O.nelder_mead(f, x0, **kw)
+        b = ref.nelder_mead(f, x0, **kw)
+        assert len(a["calls"]) == len(b["calls"]), (name, n, trial)
+        for (xa, ya), (xb, yb) in zip(a["calls"], b["calls"]):
+            assert np.array_equal(xa, xb) and (ya == yb or (np.isnan(ya) and np.isnan(yb)))
+        assert a["converged"] == b["converged"] and a["num_iterations"] == b["num_iterations"]
+        assert np.array_equal(a["x"], b["x"]) and (a["y"] == b["y"] or (np.isnan(a["y"]) and np.isnan(b["y"])))
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+@pytest.mark.parametrize("bins", [16, 8])
+def test_nid_calculate_bit_exact(ref, model, bins):
+    oc, rc, W, H = cameras(model)
+    fov = O.estimate_camera_fov(oc, W, H)
+    pr = U.random_problem(model, n=30000, seed=21, f32=(bins == 16))
+    Ts = U.random_poses(pr["T"], 4, seed=3)
+    got = ref.nid_calculate(rc, pr["image"], pr["points"], pr["intensities"], bins, Ts)
+    want = np.array([O.nid_calculate(oc, pr["image"], pr["points"], pr["intensities"], bins, fov, T)[0] for T in Ts])
+    assert np.array_equal(got, want), (got, want)
+
+
+def test_nid_calculate_edge_cases(ref):
+    oc, rc, W, H = cameras("plumb_bob")
+    fov = O.estimate_camera_fov(oc, W, H)
+    pr = U.random_problem("plumb_bob", n=2000, seed=2)
+    T = pr["T"]
+    # no inliers -> 0/0 (cost_calculator_nid.cpp:54-57): NaN on both sides
+    behind = pr["points"].copy()
+    behind[:, 0] = -np.abs(behind[:, 0]) - 1.0
+    a = ref.nid_calculate(rc, pr["image"], behind, pr["intensities"], 16, [T])[0]
+    b = O.nid_calculate(oc, pr["image"], behind, pr["intensities"], 16, fov, T)[0]
+    assert np.isnan(a) and np.isnan(b)
+    # intensities outside [0, 1), NaN intensity, NaN / huge coordinates
+    ins = pr["intensities"].copy()
+    ins[::7] = 1.0
+    ins[1::7] = -0.5
+    ins[2::7] = 3.0
+    ins[3::97] = np.nan
+    pts = pr["points"].copy()
+    pts[5::211, 1] = np.nan
+    pts[6::211, 2] = 1e30
+    a = ref.nid_calculate(rc, pr["image"], pts, ins, 16, [T])[0]
+    b = O.nid_calculate(oc, pr["image"], pts, ins, 16, fov, T)[0]
+    assert a == b
+    # a single point
+    a = ref.nid_calculate(rc, pr["image"], pr["points"][:1], pr["intensities"][:1], 16, [T])[0]
+    b = O.nid_calculate(oc, pr["image"], pr["points"][:1], pr["intensities"][:1], 16, fov, T)[0]
+    assert a == b or (np.isnan(a) and np.isnan(b))
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+@pytest.mark.parametrize("depth", [True, False])
+def test_view_culling_indices_identical(ref, model, depth):
+    oc, rc, W, H = cameras(model)
+    fov = O.estimate_camera_fov(oc, W, H)
+    pr = U.random_problem(model, n=40000, seed=33)
+    for T in U.random_poses(pr["T"], 2, seed=8):
+        assert np.array_equal(O.view_cull(oc, W, H, fov, depth, pr["points"], T), ref.view_cull(rc, W, H, depth, pr["points"], T))
+
+
+def test_golden_fixtures_match_the_reference(ref):
+    """The committed fixtures (made from the oracle, tests/golden/make_golden.py) are what the reference's code returns."""
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "mode_a_*.npz")))
+    assert len(files) == len(U.MODELS)
+    for path in files:
+        model = os.path.basename(path)[len("mode_a_"):-len(".npz")]
+        g = np.load(path)
+        H, W = g["image"].shape
+        rc = ref.Camera(model, g["intrinsics"], g["distortion"])
+        assert ref.estimate_camera_fov(rc, W, H) == float(g["max_fov"])
+        pts, ins = g["points"].astype(np.float64), g["intensities"].astype(np.float64)
+        assert np.array_equal(ref.nid_calculate(rc, g["image"], pts, ins, 16, g["poses"]), g["nid"])
+        assert np.array_equal(ref.view_cull(rc, W, H, True, pts, g["poses"][0]), g["cull_indices"])
