@@ -11,7 +11,9 @@ counting the evaluations the serial reference would have made (speculatively sco
   e2e   : the same step through the host-buffer C ABI (vlcal_estimate_pose_nelder_mead): upload, GPU view culling,
           cost-object construction, solve, result -- host<->device copies inside the timed region
   --impl reference : the CPU oracle (line-by-line restatement of the reference, oracle/vlcal_oracle.c) on a bounded
-          sample of the same step (the reference itself cannot be compiled in this image: no Eigen/OpenCV/GTSAM)
+          sample of the same step (the reference cannot be built as it ships: no Eigen/OpenCV/GTSAM in the image;
+          oracle/_ref holds its NID sources compiled against stand-in headers -- used to pin the oracle and timed
+          beside it in cpu_baseline.reference_build)
 
 N > 1 (torchrun, one rank per GPU): weak scaling over bags -- rank r owns bag r and the joint objective sum_bags NID
 (visual_camera_calibration.cpp:105-110) is formed INSIDE the histogram kernel: the finalizing block of every rank
@@ -183,8 +185,23 @@ def cpu_baseline(bag, culled_points, culled_intens, max_fov):
         O.nid_calculate(cam, bag["image"], culled_points, culled_intens, 16, max_fov, T, omp=True)
     t_o = (time.perf_counter() - t0) / n_omp
     n = culled_points.shape[0]
+    ref_build = None
+    try:  # the reference's own cost_calculator_nid.cpp (oracle/_ref, built where /root/reference exists), same sample
+        from oracle import reference as R
+
+        if R.available():
+            rcam = R.Camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+            Ts = [T] * 20
+            R.nid_calculate(rcam, bag["image"], culled_points, culled_intens, 16, Ts[:1])
+            t0 = time.perf_counter()
+            R.nid_calculate(rcam, bag["image"], culled_points, culled_intens, 16, Ts)
+            t_r = (time.perf_counter() - t0) / len(Ts)
+            ref_build = {"value": 1.0 / t_r, "unit": UNIT, "cores": 1, "ms_per_eval": 1e3 * t_r,
+                         "note": "CostCalculatorNID::calculate from the reference's own source, compiled against the stand-in Eigen/cv::Mat headers of oracle/ref_standin (-O2, no -march); one thread per bag as in the reference"}
+    except Exception as e:  # a missing prebuilt library only removes this cross-check
+        ref_build = {"unavailable": repr(e)}
     return {
-        "value": 1.0 / t_f, "unit": UNIT, "cores": 1, "kind": "port",
+        "value": 1.0 / t_f, "unit": UNIT, "cores": 1, "kind": "port", "reference_build": ref_build,
         "sample": f"{n_faithful} evaluations of CostCalculatorNID::calculate on the culled C2 cloud ({n} points), serial over points as in the reference",
         "ms_per_eval": 1e3 * t_f, "mpoints_per_s": n / t_f * 1e-6,
         "best_effort": {"value": 1.0 / t_o, "unit": UNIT, "cores": cores, "note": "OpenMP over points with thread-private histograms -- NOT what the reference does", "ms_per_eval": 1e3 * t_o},
