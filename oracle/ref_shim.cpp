@@ -6,6 +6,7 @@
 //     src/vlcal/calib/cost_calculator_nid.cpp (CostCalculatorNID::calculate, the hot path itself)
 //     src/vlcal/calib/view_culling.cpp        (ViewCulling::cull)
 //     include/dfo/nelder_mead.hpp             (instantiated below for N = 2, 3, 6)
+//     include/vlcal/costs/nid_cost.hpp        (NIDCost::operator()<double>, the B-spline NID value of the BFGS branch)
 // against the stand-in headers in oracle/ref_standin/ (Eigen, OpenCV's cv::Mat, ceres::Jet, pcl: none of them is
 // installed here), and links them with this file into oracle/_ref/libvlcal_ref.so.  tests/ use it to pin
 // oracle/vlcal_oracle.c: same inputs through the reference's code and through the restatement.  No reference source is
@@ -16,11 +17,14 @@
 #include <string>
 #include <vector>
 
+#include <ceres/jet.h>  // GenericCameraBase has a Jet overload; its callers in the reference include ceres too
+
 #include <camera/create_camera.hpp>
 #include <dfo/nelder_mead.hpp>
 #include <vlcal/calib/cost_calculator_nid.hpp>
 #include <vlcal/calib/view_culling.hpp>
 #include <vlcal/common/estimate_fov.hpp>
+#include <vlcal/costs/nid_cost.hpp>
 
 namespace vlcal {
 // Members whose reference translation units are not compiled (frame_cpu.cpp needs boost::filesystem and much more of
@@ -138,6 +142,19 @@ int64_t ref_view_cull(
   const auto& kept = vlcal::g_sampled_indices;
   for (size_t i = 0; i < kept.size(); i++) indices_out[i] = kept[i];
   return static_cast<int64_t>(kept.size());
+}
+
+// NIDCost(proj, normalized_image, points, bins)(T_params[7], &residual); image64 = pixel / 255 as CV_64FC1
+// (visual_camera_calibration.cpp:148-149).  Returns the functor's bool.
+int ref_nid_cost_bspline(
+  const void* cam, const double* image64, int width, int height, const double* points_xyzw, const double* intensities, int64_t n, int bins, const double* T_params7,
+  double* nid_out) {
+  const cv::Mat image(height, width, CV_64FC1, const_cast<double*>(image64), sizeof(double) * static_cast<size_t>(width));
+  const vlcal::NIDCost cost(static_cast<const RefCamera*>(cam)->proj, image, frame_over(points_xyzw, intensities, n), bins);
+  double residual = 0.0;
+  const bool ok = cost(T_params7, &residual);
+  *nid_out = residual;
+  return ok ? 1 : 0;
 }
 
 }  // extern "C"

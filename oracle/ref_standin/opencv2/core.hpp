@@ -11,6 +11,7 @@
 #define CV_8UC1 0
 #define CV_32SC1 4
 #define CV_32FC1 5
+#define CV_64FC1 6
 
 namespace cv {
 
@@ -49,6 +50,13 @@ public:
   // header over caller-owned pixels
   Mat(int rows, int cols, int /*type*/, void* ext, size_t step) : rows(rows), cols(cols), data(static_cast<unsigned char*>(ext)), step(step) {}
 
+  Mat clone() const {
+    Mat o;
+    o.rows = rows, o.cols = cols, o.step = step;
+    o.own = std::make_shared<std::vector<unsigned char>>(data, data + step * rows);
+    o.data = o.own->data();
+    return o;
+  }
   template <class T>
   T& at(int r, int c) {
     return *reinterpret_cast<T*>(data + r * step + c * sizeof(T));
@@ -59,7 +67,7 @@ public:
   }
 
 private:
-  static size_t elem_size(int type) { return type == CV_8UC1 ? 1 : 4; }
+  static size_t elem_size(int type) { return type == CV_8UC1 ? 1 : (type == CV_64FC1 ? 8 : 4); }
   std::shared_ptr<std::vector<unsigned char>> own;
 };
 

@@ -48,6 +48,8 @@ def lib():
         L.ref_nid_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_view_cull.restype = C.c_int64
         L.ref_view_cull.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.ref_nid_cost_bspline.restype = C.c_int
+        L.ref_nid_cost_bspline.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -122,3 +124,15 @@ def view_cull(cam: Camera, width, height, enable_depth, points_xyzw, T) -> np.nd
     t = _colmajor(T)
     m = lib().ref_view_cull(cam.handle, int(width), int(height), int(bool(enable_depth)), pts.ctypes.data, pts.shape[0], t.ctypes.data, idx.ctypes.data)
     return idx[:m].copy()
+
+
+def nid_cost_bspline(cam: Camera, image_u8, points_xyzw, intensities, bins, T_params7):
+    """NIDCost(proj, image / 255 as CV_64FC1, points, bins)(T_params7, &residual) -> (ok, residual)."""
+    image = np.ascontiguousarray(image_u8, dtype=np.uint8)
+    img64 = np.ascontiguousarray(image.astype(np.float64) * (1.0 / 255.0))  # convertTo(CV_64FC1, 1 / 255.0)
+    pts, ins = _f64(points_xyzw).reshape(-1, 4), _f64(intensities).reshape(-1)
+    tp = _f64(T_params7).reshape(7)
+    out = C.c_double(float("nan"))
+    H, W = image.shape
+    ok = lib().ref_nid_cost_bspline(cam.handle, img64.ctypes.data, W, H, pts.ctypes.data, ins.ctypes.data, pts.shape[0], int(bins), tp.ctypes.data, C.byref(out))
+    return bool(ok), float(out.value)

@@ -8,7 +8,7 @@
  * (direct_visual_lidar_calibration_b200/csrc) never includes or links it.
  *
  * PARITY STATUS: pinned against the reference's OWN sources of the path (camera models,
- * dfo::NelderMead, estimate_camera_fov, CostCalculatorNID::calculate, ViewCulling::cull), compiled
+ * dfo::NelderMead, estimate_camera_fov, CostCalculatorNID::calculate, ViewCulling::cull, NIDCost<double>), compiled
  * from /root/reference against stand-in third-party headers -- oracle/ref_shim.cpp,
  * oracle/ref_standin/, tests/test_reference_pin.py: bit-exact on every comparison.  The reference
  * cannot be built as it ships (no Eigen/OpenCV/Ceres/GTSAM/Boost/Iridescence/PCL in this image) and

@@ -168,3 +168,32 @@ def test_golden_fixtures_match_the_reference(ref):
         pts, ins = g["points"].astype(np.float64), g["intensities"].astype(np.float64)
         assert np.array_equal(ref.nid_calculate(rc, g["image"], pts, ins, 16, g["poses"]), g["nid"])
         assert np.array_equal(ref.view_cull(rc, W, H, True, pts, g["poses"][0]), g["cull_indices"])
+
+
+def _sophus_params(T):
+    from scipy.spatial.transform import Rotation
+
+    q = Rotation.from_matrix(T[:3, :3]).as_quat()  # x y z w
+    return np.concatenate([q, T[:3, 3]])
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+def test_bspline_nid_value_bit_exact(ref, model):
+    """NIDCost::operator()<double> (include/vlcal/costs/nid_cost.hpp:36-107), the value half of the BFGS branch."""
+    oc, rc, W, H = cameras(model)
+    pr = U.random_problem(model, n=8000, seed=71)
+    for bins, T in zip((16, 16, 8), U.random_poses(pr["T"], 3, seed=5)):
+        tp = _sophus_params(T)
+        ok_r, nid_r = ref.nid_cost_bspline(rc, pr["image"], pr["points"], pr["intensities"], bins, tp)
+        ok_o, nid_o, _ = O.nid_cost_bspline(oc, pr["image"], pr["points"], pr["intensities"], bins, tp)
+        assert ok_r and ok_o and nid_r == nid_o, (nid_r, nid_o)
+
+
+def test_bspline_failure_flag(ref):
+    oc, rc, W, H = cameras("plumb_bob")
+    pr = U.random_problem("plumb_bob", n=100, seed=72)
+    far = np.array([[1.0, 5e3, 0.0, 1.0]] * 10)  # far off to the side: every projection lands outside the image
+    tp = _sophus_params(pr["T"])
+    ok_r, _ = ref.nid_cost_bspline(rc, pr["image"], far, np.full(10, 0.5), 16, tp)
+    ok_o, _, _ = O.nid_cost_bspline(oc, pr["image"], far, np.full(10, 0.5), 16, tp)
+    assert ok_r is False and ok_o is False  # no inliers -> NaN -> the functor returns false (nid_cost.hpp:98-102)
