@@ -7,6 +7,8 @@
 //     src/vlcal/calib/view_culling.cpp        (ViewCulling::cull)
 //     include/dfo/nelder_mead.hpp             (instantiated below for N = 2, 3, 6)
 //     include/vlcal/costs/nid_cost.hpp        (NIDCost::operator()<double>, the B-spline NID value of the BFGS branch)
+//     src/vlcal/calib/visual_camera_calibration.cpp (calibrate + estimate_pose_nelder_mead; the BFGS branch compiles
+//                                              against a solver-less ceres stand-in and is never run)
 // against the stand-in headers in oracle/ref_standin/ (Eigen, OpenCV's cv::Mat, ceres::Jet, pcl: none of them is
 // installed here), and links them with this file into oracle/_ref/libvlcal_ref.so.  tests/ use it to pin
 // oracle/vlcal_oracle.c: same inputs through the reference's code and through the restatement.  No reference source is
@@ -23,6 +25,7 @@
 #include <dfo/nelder_mead.hpp>
 #include <vlcal/calib/cost_calculator_nid.hpp>
 #include <vlcal/calib/view_culling.hpp>
+#include <vlcal/calib/visual_camera_calibration.hpp>
 #include <vlcal/common/estimate_fov.hpp>
 #include <vlcal/costs/nid_cost.hpp>
 
@@ -35,10 +38,22 @@ VisualLiDARData::~VisualLiDARData() {}
 
 static thread_local std::vector<int> g_sampled_indices;
 // frame_cpu.cpp: sample() gathers the listed points into a new frame; ViewCulling::cull (view_culling.cpp:32) ends with
-// it.  The stand-in only records the indices, which is what the pin test compares.
-FrameCPU::Ptr sample(const Frame::ConstPtr&, const std::vector<int>& indices) {
+// it.  The stand-in gathers the two attributes the NID path reads (points, intensities) and records the indices for the
+// culling pin test.
+FrameCPU::Ptr sample(const Frame::ConstPtr& frame, const std::vector<int>& indices) {
   g_sampled_indices = indices;
-  return std::make_shared<FrameCPU>();
+  auto out = std::make_shared<FrameCPU>();
+  const size_t count = indices.size();
+  out->num_points = count;
+  out->points_storage.reserve(count);
+  for (size_t k = 0; k < count; k++) out->points_storage.push_back(frame->points[indices[k]]);
+  out->points = out->points_storage.data();
+  if (frame->intensities != nullptr) {
+    out->intensities_storage.reserve(count);
+    for (size_t k = 0; k < count; k++) out->intensities_storage.push_back(frame->intensities[indices[k]]);
+    out->intensities = out->intensities_storage.data();
+  }
+  return out;
 }
 }  // namespace vlcal
 
@@ -155,6 +170,48 @@ int ref_nid_cost_bspline(
   const bool ok = cost(T_params7, &residual);
   *nid_out = residual;
   return ok ? 1 : 0;
+}
+
+// VisualCameraCalibration(proj, dataset, params).calibrate(init_T) with registration_type = NID_NELDER_MEAD.
+// max_outer_iterations = 1 is exactly one estimate_pose_nelder_mead (visual_camera_calibration.cpp:35-68).
+// calib = {max_outer_iterations, max_inner_iterations, delta_trans_thresh, delta_rot_thresh, disable_z_buffer_culling,
+//          nid_bins, nelder_mead_init_step, nelder_mead_convergence_criteria}
+// callback_T (capacity callback_capacity x 16 doubles, column-major) receives every pose passed to params.callback.
+int ref_calibrate_nelder_mead(
+  const void* cam, int n_bags, const uint8_t* const* images, int width, int height, const int* row_strides, const double* const* points_xyzw,
+  const double* const* intensities, const int64_t* counts, const double* calib, const double* init_T_camera_lidar, double* T_out, double* callback_T,
+  int callback_capacity, int* callback_count) {
+  std::vector<vlcal::VisualLiDARData::ConstPtr> dataset;
+  for (int b = 0; b < n_bags; b++) {
+    const cv::Mat image(height, width, CV_8UC1, const_cast<uint8_t*>(images[b]), static_cast<size_t>(row_strides[b]));
+    dataset.push_back(std::make_shared<vlcal::VisualLiDARData>(image, frame_over(points_xyzw[b], intensities[b], counts[b])));
+  }
+  vlcal::VisualCameraCalibrationParams params;
+  params.max_outer_iterations = static_cast<int>(calib[0]);
+  params.max_inner_iterations = static_cast<int>(calib[1]);
+  params.delta_trans_thresh = calib[2];
+  params.delta_rot_thresh = calib[3];
+  params.disable_z_buffer_culling = calib[4] != 0.0;
+  params.nid_bins = static_cast<int>(calib[5]);
+  params.nelder_mead_init_step = calib[6];
+  params.nelder_mead_convergence_criteria = calib[7];
+  params.registration_type = vlcal::RegistrationType::NID_NELDER_MEAD;
+  int count = 0;
+  params.callback = [&](const Eigen::Isometry3d& T) {
+    if (count < callback_capacity) {
+      for (int c = 0; c < 4; c++) {
+        for (int r = 0; r < 4; r++) callback_T[16 * count + r + 4 * c] = T.matrix()(r, c);
+      }
+    }
+    count++;
+  };
+  vlcal::VisualCameraCalibration calibration(static_cast<const RefCamera*>(cam)->proj, dataset, params);
+  const Eigen::Isometry3d T = calibration.calibrate(isometry_from_colmajor(init_T_camera_lidar));
+  for (int c = 0; c < 4; c++) {
+    for (int r = 0; r < 4; r++) T_out[r + 4 * c] = T.matrix()(r, c);
+  }
+  *callback_count = count;
+  return 0;
 }
 
 }  // extern "C"

@@ -50,6 +50,13 @@ public:
   // header over caller-owned pixels
   Mat(int rows, int cols, int /*type*/, void* ext, size_t step) : rows(rows), cols(cols), data(static_cast<unsigned char*>(ext)), step(step) {}
 
+  // u8 -> f64 with a scale (the one conversion the reference's BFGS branch asks for)
+  void convertTo(Mat& out, int type, double scale) const {
+    out = Mat(rows, cols, type, Scalar::all(0.0));
+    for (int r = 0; r < rows; r++) {
+      for (int c = 0; c < cols; c++) out.at<double>(r, c) = at<unsigned char>(r, c) * scale;
+    }
+  }
   Mat clone() const {
     Mat o;
     o.rows = rows, o.cols = cols, o.step = step;

@@ -50,6 +50,8 @@ def lib():
         L.ref_view_cull.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.ref_nid_cost_bspline.restype = C.c_int
         L.ref_nid_cost_bspline.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_calibrate_nelder_mead.restype = C.c_int
+        L.ref_calibrate_nelder_mead.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -136,3 +138,30 @@ def nid_cost_bspline(cam: Camera, image_u8, points_xyzw, intensities, bins, T_pa
     H, W = image.shape
     ok = lib().ref_nid_cost_bspline(cam.handle, img64.ctypes.data, W, H, pts.ctypes.data, ins.ctypes.data, pts.shape[0], int(bins), tp.ctypes.data, C.byref(out))
     return bool(ok), float(out.value)
+
+
+def calibrate_nelder_mead(cam: Camera, bags, init_T, max_outer_iterations=10, max_inner_iterations=256, delta_trans_thresh=0.1, delta_rot_thresh=0.5 * np.pi / 180.0,
+                          disable_z_buffer_culling=False, nid_bins=16, nelder_mead_init_step=1e-3, nelder_mead_convergence_criteria=1e-8, callback_capacity=8192):
+    """VisualCameraCalibration(proj, dataset, params).calibrate(init_T), NID_NELDER_MEAD branch.
+    bags: list of (image_u8[H, W], points_xyzw[N, 4], intensities[N]), all images of one size.  Returns the final pose and the
+    poses handed to params.callback (every new best cost, visual_camera_calibration.cpp:112-116)."""
+    keep = []
+    for image, pts, ins in bags:
+        keep.append((np.ascontiguousarray(image, dtype=np.uint8), _f64(pts).reshape(-1, 4), _f64(ins).reshape(-1)))
+    n = len(keep)
+    H, W = keep[0][0].shape
+    images = (C.c_void_p * n)(*[k[0].ctypes.data for k in keep])
+    strides = (C.c_int * n)(*[k[0].strides[0] for k in keep])
+    points = (C.c_void_p * n)(*[k[1].ctypes.data for k in keep])
+    intens = (C.c_void_p * n)(*[k[2].ctypes.data for k in keep])
+    counts = (C.c_int64 * n)(*[k[1].shape[0] for k in keep])
+    calib = _f64([max_outer_iterations, max_inner_iterations, delta_trans_thresh, delta_rot_thresh, 1.0 if disable_z_buffer_culling else 0.0, nid_bins, nelder_mead_init_step,
+                  nelder_mead_convergence_criteria])
+    t0 = _colmajor(init_T)
+    out = np.empty(16)
+    cb = np.zeros((callback_capacity, 16))
+    count = C.c_int(0)
+    lib().ref_calibrate_nelder_mead(cam.handle, n, images, W, H, strides, points, intens, counts, calib.ctypes.data, t0.ctypes.data, out.ctypes.data, cb.ctypes.data, callback_capacity,
+                                    C.byref(count))
+    k = min(count.value, callback_capacity)
+    return {"T": out.reshape(4, 4).T.copy(), "callback_T": cb[:k].reshape(k, 4, 4).transpose(0, 2, 1).copy(), "num_callbacks": count.value}

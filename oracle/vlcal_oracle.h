@@ -8,14 +8,14 @@
  * (direct_visual_lidar_calibration_b200/csrc) never includes or links it.
  *
  * PARITY STATUS: pinned against the reference's OWN sources of the path (camera models,
- * dfo::NelderMead, estimate_camera_fov, CostCalculatorNID::calculate, ViewCulling::cull, NIDCost<double>), compiled
+ * dfo::NelderMead, estimate_camera_fov, CostCalculatorNID::calculate, ViewCulling::cull, NIDCost<double>,
+ * VisualCameraCalibration::calibrate / estimate_pose_nelder_mead), compiled
  * from /root/reference against stand-in third-party headers -- oracle/ref_shim.cpp,
  * oracle/ref_standin/, tests/test_reference_pin.py: bit-exact on every comparison.  The reference
  * cannot be built as it ships (no Eigen/OpenCV/Ceres/GTSAM/Boost/Iridescence/PCL in this image) and
  * has no tests or golden vectors, so what stays "parity unpinned" is the
  * third-party arithmetic itself, restated from published semantics here and in the stand-ins alike:
- *   - GTSAM 4.2a9 Pose3::Expmap / SO3::Expmap (docs/installation.md:27); visual_camera_calibration.cpp
- *     (the caller of Expmap) is not among the compiled reference sources
+ *   - GTSAM 4.2a9 Pose3::Expmap / SO3::Expmap (docs/installation.md:27)
  *   - Eigen 3.4 Isometry3d*Vector4d, normalized(), reduction orders, cast<int>(), AngleAxisd(Matrix3d)
  *   - libstdc++ std::sort insertion-sort branch for n <= 16 (pinned: the reference build uses the real std::sort)
  *   - Sophus SO3/SE3 point action (thirdparty/Sophus/sophus/so3.hpp:408-417, se3.hpp:319-322)

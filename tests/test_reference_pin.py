@@ -197,3 +197,58 @@ def test_bspline_failure_flag(ref):
     ok_r, _ = ref.nid_cost_bspline(rc, pr["image"], far, np.full(10, 0.5), 16, tp)
     ok_o, _, _ = O.nid_cost_bspline(oc, pr["image"], far, np.full(10, 0.5), 16, tp)
     assert ok_r is False and ok_o is False  # no inliers -> NaN -> the functor returns false (nid_cost.hpp:98-102)
+
+
+def _best_cost_poses(init_T, trace):
+    """Poses the reference hands to params.callback: evaluations that improve on the best cost so far (:112-116)."""
+    best, out = np.finfo(np.float64).max, []
+    for row in trace:
+        if row[6] < best:
+            best = row[6]
+            out.append(O.isometry_mul(init_T, O.se3_expmap(row[:6])))
+    return out
+
+
+@pytest.mark.parametrize("model,n_bags", [("plumb_bob", 1), ("plumb_bob", 2), ("fisheye", 1), ("equirectangular", 2)])
+def test_estimate_pose_nelder_mead_identical(ref, model, n_bags):
+    """VisualCameraCalibration::estimate_pose_nelder_mead (visual_camera_calibration.cpp:70-139) through calibrate() with
+    one outer iteration: culling at the start pose, one cost object per bag, objective sum in bag order, best-cost
+    callbacks, result init_T * Expmap(x).  (GTSAM's Expmap and Eigen's Isometry product are stand-ins on the reference
+    side -- restated like the oracle's; everything else is the reference's code.)"""
+    oc, rc, W, H = cameras(model)
+    bags = []
+    for b in range(n_bags):
+        pr = U.random_problem(model, n=6000 + 500 * b, seed=90 + b)
+        bags.append((pr["image"], pr["points"], pr["intensities"]))
+    T0 = U.random_poses(pr["T"], 1, seed=12, rot_deg=0.5, trans=0.02)[0]
+    p = O.default_calib_params()
+    p.max_inner_iterations = 40
+    p.max_outer_iterations = 1
+    a = O.estimate_pose_nelder_mead(oc, bags, T0, p)
+    b = ref.calibrate_nelder_mead(rc, bags, T0, max_outer_iterations=1, max_inner_iterations=40)
+    assert np.array_equal(a["T"], b["T"])
+    want = _best_cost_poses(T0, a["trace"])
+    assert b["num_callbacks"] == len(want)
+    for Tw, Tg in zip(want, b["callback_T"]):
+        assert np.array_equal(Tw, Tg)
+
+
+def test_calibrate_outer_loop_identical(ref):
+    """VisualCameraCalibration::calibrate (visual_camera_calibration.cpp:35-68): re-culling at every outer iteration and
+    the delta_t / delta_r termination test."""
+    oc, rc, W, H = cameras("plumb_bob")
+    pr = U.random_problem("plumb_bob", n=8000, seed=95)
+    bags = [(pr["image"], pr["points"], pr["intensities"])]
+    T0 = U.random_poses(pr["T"], 1, seed=13, rot_deg=0.5, trans=0.02)[0]
+    for kw in (dict(max_outer_iterations=3, max_inner_iterations=25, delta_trans_thresh=1e-9, delta_rot_thresh=1e-9),  # never converges: 3 outer iterations
+               dict(max_outer_iterations=5, max_inner_iterations=25),  # default thresholds: stops after the first
+               dict(max_outer_iterations=2, max_inner_iterations=30, disable_z_buffer_culling=True, nelder_mead_init_step=5e-3)):
+        p = O.default_calib_params()
+        p.max_outer_iterations, p.max_inner_iterations = kw["max_outer_iterations"], kw["max_inner_iterations"]
+        p.delta_trans_thresh = kw.get("delta_trans_thresh", p.delta_trans_thresh)
+        p.delta_rot_thresh = kw.get("delta_rot_thresh", p.delta_rot_thresh)
+        p.disable_z_buffer_culling = int(kw.get("disable_z_buffer_culling", False))
+        p.nelder_mead_init_step = kw.get("nelder_mead_init_step", p.nelder_mead_init_step)
+        a = O.calibrate(oc, bags, T0, p)
+        b = ref.calibrate_nelder_mead(rc, bags, T0, **kw)
+        assert np.array_equal(a["T"], b["T"]), kw
