@@ -3,6 +3,9 @@
 The reference ships no golden vectors, so these pins are ours: they freeze the oracle's answers on
 seeded inputs so that (a) a later edit of the oracle that changes behaviour is caught by the CPU suite and (b) the
 GPU suite can compare against committed numbers, not only against a checker built in the same run.
+Where oracle/_ref (the reference's own sources compiled here, oracle/ref_shim.cpp) is available, every stored max_fov /
+nid / cull_indices is checked against the reference's code before it is written; tests/test_reference_pin.py repeats
+that check on the committed files.
     python tests/golden/make_golden.py
 """
 import json
@@ -16,6 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle import oracle as O  # noqa: E402
+from oracle import reference as R  # noqa: E402
 import util  # noqa: E402
 
 
@@ -53,6 +57,12 @@ def main():
             nids.append(nid)
             hists.append(h)
         idx = O.view_cull(cam, pr["W"], pr["H"], fov, True, pr["points"], Ts[0])
+        if R.build() is not None:
+            rcam = R.Camera(model, intr, pr["distortion"])
+            pts32 = pr["points"].astype(np.float32).astype(np.float64)
+            assert np.array_equal(pts32, pr["points"]) and R.estimate_camera_fov(rcam, pr["W"], pr["H"]) == fov
+            assert np.array_equal(R.nid_calculate(rcam, pr["image"], pr["points"], pr["intensities"].astype(np.float32).astype(np.float64), 16, Ts), np.array(nids))
+            assert np.array_equal(R.view_cull(rcam, pr["W"], pr["H"], True, pr["points"], Ts[0]), idx)
         np.savez_compressed(
             os.path.join(HERE, f"mode_a_{model}.npz"),
             intrinsics=np.array(intr), distortion=np.array(pr["distortion"], dtype=np.float64), image=pr["image"],
