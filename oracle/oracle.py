@@ -18,11 +18,8 @@ CAMERA_MODELS = ["plumb_bob", "fisheye", "atan", "omnidir", "equirectangular", "
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "vlcal_oracle.c")
-    hdr = os.path.join(_HERE, "vlcal_oracle.h")
-    stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, hdr)
-    )
+    srcs = [os.path.join(_HERE, f) for f in ("vlcal_oracle.c", "vlcal_oracle_grad.c", "vlcal_oracle.h")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _LIB_PATH
@@ -122,6 +119,8 @@ def lib():
         L.orc_view_cull.restype = C.c_int64
         L.orc_nid_cost_bspline.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, dp, dp, C.c_void_p]
         L.orc_nid_cost_bspline.restype = C.c_int
+        L.orc_nid_cost_bspline_grad.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, dp, dp, C.c_void_p, C.c_void_p]
+        L.orc_nid_cost_bspline_grad.restype = C.c_int
         L.orc_calib_default_params.argtypes = [C.POINTER(CalibParams)]
         L.orc_estimate_pose_nelder_mead.argtypes = [C.POINTER(Camera), C.POINTER(Bag), C.c_int, C.POINTER(CalibParams), dp, dp, C.POINTER(NMResult), C.POINTER(Trace)]
         L.orc_calibrate.argtypes = [C.POINTER(Camera), C.POINTER(Bag), C.c_int, C.POINTER(CalibParams), dp, dp, C.POINTER(CalibStats), C.POINTER(Trace)]
@@ -260,6 +259,22 @@ def nid_cost_bspline(cam, image_u8, points_xyzw, intensities, bins, T_params7):
     hist = np.zeros(bins * bins)
     ok = lib().orc_nid_cost_bspline(C.byref(cam), img64.ctypes.data, W, H, pts.ctypes.data, ins.ctypes.data, pts.shape[0], int(bins), _dp(tp), C.byref(out), hist.ctypes.data)
     return bool(ok), float(out.value), hist.reshape(bins, bins).T.copy()
+
+
+def nid_cost_bspline_grad(cam, image_u8, points_xyzw, intensities, bins, T_params7, return_hist=False):
+    """NIDCost::operator()<Jet<double, 7>> -> (ok, nid, grad[7] w.r.t. qx qy qz qw tx ty tz[, hist[bins(image), bins(lidar), 8]])."""
+    image, pts, ins = _check_inputs(image_u8, points_xyzw, intensities)
+    img64 = np.ascontiguousarray(image.astype(np.float64) * (1.0 / 255.0))
+    H, W = image.shape
+    tp = _f64(T_params7).reshape(7)
+    out = C.c_double(float("nan"))
+    grad = np.full(7, np.nan)
+    hist = np.zeros(bins * bins * 8)
+    ok = lib().orc_nid_cost_bspline_grad(C.byref(cam), img64.ctypes.data, W, H, pts.ctypes.data, ins.ctypes.data, C.c_int64(pts.shape[0]), int(bins), _dp(tp), C.byref(out), grad.ctypes.data,
+                                         hist.ctypes.data if return_hist else None)
+    if return_hist:
+        return bool(ok), float(out.value), grad, hist.reshape(bins, bins, 8).transpose(1, 0, 2).copy()
+    return bool(ok), float(out.value), grad
 
 
 def default_calib_params() -> CalibParams:

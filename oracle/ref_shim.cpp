@@ -172,6 +172,25 @@ int ref_nid_cost_bspline(
   return ok ? 1 : 0;
 }
 
+// NIDCost::operator()<ceres::Jet<double, 7>>: what ceres::AutoDiffFirstOrderFunction evaluates in the BFGS branch
+// (visual_camera_calibration.cpp:211): the residual and its partials w.r.t. the 7 ambient parameters (qx qy qz qw tx ty tz).
+int ref_nid_cost_bspline_jet(
+  const void* cam, const double* image64, int width, int height, const double* points_xyzw, const double* intensities, int64_t n, int bins, const double* T_params7,
+  double* nid_out, double* grad_out7) {
+  using Jet7 = ceres::Jet<double, 7>;
+  const cv::Mat image(height, width, CV_64FC1, const_cast<double*>(image64), sizeof(double) * static_cast<size_t>(width));
+  const vlcal::NIDCost cost(static_cast<const RefCamera*>(cam)->proj, image, frame_over(points_xyzw, intensities, n), bins);
+  Jet7 params[7], residual;
+  for (int k = 0; k < 7; k++) {
+    params[k] = Jet7(T_params7[k]);
+    params[k].v[k] = 1.0;
+  }
+  const bool ok = cost(params, &residual);
+  *nid_out = residual.a;
+  for (int k = 0; k < 7; k++) grad_out7[k] = residual.v[k];
+  return ok ? 1 : 0;
+}
+
 // VisualCameraCalibration(proj, dataset, params).calibrate(init_T) with registration_type = NID_NELDER_MEAD.
 // max_outer_iterations = 1 is exactly one estimate_pose_nelder_mead (visual_camera_calibration.cpp:35-68).
 // calib = {max_outer_iterations, max_inner_iterations, delta_trans_thresh, delta_rot_thresh, disable_z_buffer_culling,

@@ -1,7 +1,10 @@
-// ceres/jet.h STAND-IN (test infrastructure): a forward-mode dual number with the operations the reference's camera
-// templates apply to their scalar type.  camera::GenericCamera<Projection> has a virtual operator() on
-// Jet<double, 7> points (include/camera/generic_camera.hpp:29), so the type must be complete for create_camera.cpp to
-// compile; the NID path (mode A) never calls it and no test relies on the derivative parts.
+// ceres/jet.h STAND-IN (test infrastructure): a forward-mode dual number (value a, N partials v) with the operations
+// the reference's camera templates and NIDCost apply to their scalar type.  camera::GenericCamera<Projection> has a
+// virtual operator() on Jet<double, 7> points (include/camera/generic_camera.hpp:29), so the type must be complete for
+// create_camera.cpp to compile.  Mode A never evaluates it; the gradient pin (NIDCost::operator()<Jet<double, 7>>,
+// tests/test_reference_pin.py) does, so the rules below are ordinary first-order differentiation written in the form
+// ceres documents for its Jet (f/g = (f.a/g.a, (f.v - f.a/g.a g.v)/g.a), ...): the reference's code decides WHAT is
+// differentiated, this header only supplies the chain rule.
 #pragma once
 
 #include <cmath>
@@ -34,6 +37,11 @@ STANDIN_JET_LINEAR(+)
 STANDIN_JET_LINEAR(-)
 #undef STANDIN_JET_LINEAR
 
+template <class T, int N>
+Jet<T, N>& operator+=(Jet<T, N>& f, const Jet<T, N>& g) {
+  f = f + g;
+  return f;
+}
 template <class T, int N>
 Jet<T, N> operator-(const Jet<T, N>& f) {
   Jet<T, N> h;
@@ -136,6 +144,10 @@ Jet<T, N> atan2(const Jet<T, N>& y, const Jet<T, N>& x) {
   h.a = std::atan2(y.a, x.a);
   for (int i = 0; i < N; i++) h.v[i] = (x.a * y.v[i] - y.a * x.v[i]) / d;
   return h;
+}
+template <class T, int N>
+Jet<T, N> log(const Jet<T, N>& f) {
+  return chain(std::log(f.a), T(1) / f.a, f);
 }
 template <class T, int N>
 Jet<T, N> pow(const Jet<T, N>& f, double e) {

@@ -29,6 +29,16 @@ public:
     return Matrix<T, 3, 1>((v[0] + qw * uv[0] + c[0]) + p[4], (v[1] + qw * uv[1] + c[1]) + p[5], (v[2] + qw * uv[2] + c[2]) + p[6]);
   }
 
+  // SE3<Jet> * Vector3d (nid_cost.hpp:47): the point enters with zero partials
+  template <class U, std::enable_if_t<!std::is_same<U, T>::value && std::is_arithmetic<U>::value, int> = 0>
+  Matrix<T, 3, 1> operator*(const Matrix<U, 3, 1>& v) const {
+    return (*this) * Matrix<T, 3, 1>(T(v[0]), T(v[1]), T(v[2]));
+  }
+  template <class U, int N, std::enable_if_t<N == 3, int> = 0>
+  Matrix<T, 3, 1> operator*(const VecBlock<U, N>& v) const {
+    return (*this) * Matrix<T, 3, 1>(T(v[0]), T(v[1]), T(v[2]));
+  }
+
 private:
   const T* p;
 };

@@ -52,6 +52,8 @@ def lib():
         L.ref_nid_cost_bspline.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_calibrate_nelder_mead.restype = C.c_int
         L.ref_calibrate_nelder_mead.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.ref_nid_cost_bspline_jet.restype = C.c_int
+        L.ref_nid_cost_bspline_jet.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
         _lib = L
     return _lib
 
@@ -165,3 +167,16 @@ def calibrate_nelder_mead(cam: Camera, bags, init_T, max_outer_iterations=10, ma
                                     C.byref(count))
     k = min(count.value, callback_capacity)
     return {"T": out.reshape(4, 4).T.copy(), "callback_T": cb[:k].reshape(k, 4, 4).transpose(0, 2, 1).copy(), "num_callbacks": count.value}
+
+
+def nid_cost_bspline_jet(cam: Camera, image_u8, points_xyzw, intensities, bins, T_params7):
+    """NIDCost::operator()<ceres::Jet<double, 7>> -> (ok, residual, d residual / d(qx qy qz qw tx ty tz))."""
+    image = np.ascontiguousarray(image_u8, dtype=np.uint8)
+    img64 = np.ascontiguousarray(image.astype(np.float64) * (1.0 / 255.0))
+    pts, ins = _f64(points_xyzw).reshape(-1, 4), _f64(intensities).reshape(-1)
+    tp = _f64(T_params7).reshape(7)
+    out = C.c_double(float("nan"))
+    grad = np.full(7, np.nan)
+    H, W = image.shape
+    ok = lib().ref_nid_cost_bspline_jet(cam.handle, img64.ctypes.data, W, H, pts.ctypes.data, ins.ctypes.data, pts.shape[0], int(bins), tp.ctypes.data, C.byref(out), grad.ctypes.data)
+    return bool(ok), float(out.value), grad

@@ -214,6 +214,21 @@ void orc_calibrate(
   orc_calib_stats* stats,
   orc_trace* trace);
 
+/* NIDCost::operator()<ceres::Jet<double, 7>> (nid_cost.hpp:36-107): value + d/d(qx qy qz qw tx ty tz); vlcal_oracle_grad.c */
+int orc_nid_cost_bspline_grad(
+  const orc_camera* cam,
+  const double* image64,
+  int width,
+  int height,
+  const double* points_xyzw,
+  const double* intensities,
+  int64_t n,
+  int bins,
+  const double T_params[7],
+  double* nid_out,
+  double* grad_out,
+  double* hist_out);
+
 #ifdef __cplusplus
 }
 #endif

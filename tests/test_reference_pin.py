@@ -252,3 +252,34 @@ def test_calibrate_outer_loop_identical(ref):
         a = O.calibrate(oc, bags, T0, p)
         b = ref.calibrate_nelder_mead(rc, bags, T0, **kw)
         assert np.array_equal(a["T"], b["T"]), kw
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+def test_bspline_nid_gradient_bit_exact(ref, model):
+    """NIDCost::operator()<ceres::Jet<double, 7>> (what AutoDiffFirstOrderFunction evaluates in the BFGS branch,
+    visual_camera_calibration.cpp:211): residual and its 7 partials, reference functor + stand-in Jet vs the oracle."""
+    oc, rc, W, H = cameras(model)
+    pr = U.random_problem(model, n=6000, seed=75)
+    for bins, T in zip((16, 8), U.random_poses(pr["T"], 2, seed=6)):
+        tp = _sophus_params(T)
+        ok_r, nid_r, g_r = ref.nid_cost_bspline_jet(rc, pr["image"], pr["points"], pr["intensities"], bins, tp)
+        ok_o, nid_o, g_o = O.nid_cost_bspline_grad(oc, pr["image"], pr["points"], pr["intensities"], bins, tp)
+        assert ok_r and ok_o and nid_r == nid_o and np.array_equal(g_r, g_o), (nid_r, nid_o, g_r, g_o)
+        assert np.abs(g_o).max() > 1e-4
+
+
+def test_bspline_gradient_is_the_derivative_of_the_value(ref):
+    """Independent of any Jet arithmetic: central differences of the double functor on a smooth image."""
+    oc, rc, W, H = cameras("fisheye")
+    pr = U.random_problem("fisheye", n=6000, seed=76)
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = (127 + 100 * np.sin(xx / 37.0) * np.cos(yy / 23.0)).astype(np.uint8)
+    tp = _sophus_params(pr["T"])
+    _, _, g = O.nid_cost_bspline_grad(oc, img, pr["points"], pr["intensities"], 16, tp)
+    fd = np.zeros(7)
+    for k in range(7):
+        a, b = tp.copy(), tp.copy()
+        a[k] += 1e-6
+        b[k] -= 1e-6
+        fd[k] = (ref.nid_cost_bspline(rc, img, pr["points"], pr["intensities"], 16, a)[1] - ref.nid_cost_bspline(rc, img, pr["points"], pr["intensities"], 16, b)[1]) / 2e-6
+    assert np.abs(g - fd).max() < 1e-5 * max(1.0, np.abs(g).max()), (g, fd)
