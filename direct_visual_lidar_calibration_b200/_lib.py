@@ -112,6 +112,7 @@ def load_library():
     L.vlcal_nid_evaluate_async.argtypes = [vp, dp, C.c_int]
     L.vlcal_nid_wait.argtypes = [vp, dp, vp]
     L.vlcal_nid_evaluate_bspline.argtypes = [vp, dp, C.c_int, dp, vp, vp]
+    L.vlcal_nid_evaluate_bspline_grad.argtypes = [vp, dp, C.c_int, dp, dp, vp]
     L.vlcal_nid_num_points.argtypes = [vp]
     L.vlcal_nid_num_points.restype = C.c_int64
     L.vlcal_nid_bins.argtypes = [vp]

@@ -185,6 +185,16 @@ class NIDCost:
             return ok.astype(bool), nid, np.swapaxes(hist.reshape(P, self.bins, self.bins), 1, 2).copy()
         return ok.astype(bool), nid
 
+    def evaluate_with_gradient(self, T_params):
+        """NIDCost::operator()<ceres::Jet<double, 7>>: (ok[P], nid[P], grad[P, 7]) with grad = d NID / d [qx qy qz qw tx ty tz]."""
+        tp = np.ascontiguousarray(np.asarray(T_params, dtype=np.float64)).reshape(-1, 7)
+        P = tp.shape[0]
+        nid = np.empty(P)
+        grad = np.empty((P, 7))
+        ok = np.empty(P, dtype=np.int32)
+        _lib.check(self._L.vlcal_nid_evaluate_bspline_grad(self._ctx, _dp(tp), P, _dp(nid), _dp(grad), ok.ctypes.data))
+        return ok.astype(bool), nid, grad
+
     def __call__(self, T_params7):
         ok, nid = self.evaluate(np.asarray(T_params7).reshape(1, 7))
         return bool(ok[0]), float(nid[0])

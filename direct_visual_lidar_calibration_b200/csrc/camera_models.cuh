@@ -47,7 +47,8 @@ VL_HD bool camera_num_params(int model, int* n_intr, int* n_dist) {
 }
 
 // Eigen squaredNorm of a 3-vector ((x*x + y*y) + z*z) and normalized() (v / sqrt(|v|^2) when |v|^2 > 0)
-VL_HD xd sqnorm3(xd x, xd y, xd z) {
+template <class S>
+VL_HD S sqnorm3(S x, S y, S z) {
   return (x * x + y * y) + z * z;
 }
 
@@ -55,52 +56,54 @@ VL_HD xd sqnorm3(xd x, xd y, xd z) {
 // exact (double) projections
 // ---------------------------------------------------------------------------------------------
 
-template <int MODEL>
-VL_HD void project_exact(const CameraParams& c, xd px, xd py, xd pz, xd& u, xd& v) {
+// S = xd: the exact value path.  S = xj3 (dual_math.cuh): the same operations carrying d/d(px, py, pz); the camera
+// parameters stay plain xd, as T = double next to T2 = Jet in the reference's templates.
+template <int MODEL, class S>
+VL_HD void project_generic(const CameraParams& c, S px, S py, S pz, S& u, S& v) {
   const double* in = c.intr;
   const double* d = c.dist;
   if constexpr (MODEL == CAM_PLUMB_BOB) {
     // pinhole.hpp:41 pt_2d = head<2>() / z ; :13-38 distort ; :49-51
-    const xd x = px / pz;
-    const xd y = py / pz;
+    const S x = px / pz;
+    const S y = py / pz;
     const xd k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
-    const xd x2 = x * x;
-    const xd y2 = y * y;
-    const xd r2 = x2 + y2;
-    const xd r4 = r2 * r2;
-    const xd r6 = r2 * r4;
-    const xd r_coeff = xd(1.0) + k1 * r2 + k2 * r4 + k3 * r6;
-    const xd t_coeff1 = xd(2.0) * x * y;
-    const xd t_coeff2 = r2 + xd(2.0) * x2;
-    const xd t_coeff3 = r2 + xd(2.0) * y2;
-    const xd xdst = r_coeff * x + p1 * t_coeff1 + p2 * t_coeff2;
-    const xd ydst = r_coeff * y + p1 * t_coeff3 + p2 * t_coeff1;
+    const S x2 = x * x;
+    const S y2 = y * y;
+    const S r2 = x2 + y2;
+    const S r4 = r2 * r2;
+    const S r6 = r2 * r4;
+    const S r_coeff = xd(1.0) + k1 * r2 + k2 * r4 + k3 * r6;
+    const S t_coeff1 = xd(2.0) * x * y;
+    const S t_coeff2 = r2 + xd(2.0) * x2;
+    const S t_coeff3 = r2 + xd(2.0) * y2;
+    const S xdst = r_coeff * x + p1 * t_coeff1 + p2 * t_coeff2;
+    const S ydst = r_coeff * y + p1 * t_coeff3 + p2 * t_coeff1;
     u = xd(in[0]) * xdst + xd(in[2]);
     v = xd(in[1]) * ydst + xd(in[3]);
   } else if constexpr (MODEL == CAM_FISHEYE) {
     // fisheye.hpp:15-35 ; note abs(z) at :16, r == 0 -> NaN (kept)
-    const xd r = xsqrt(px * px + py * py);
-    const xd theta = xatan2(r, xabs(pz));
-    const xd theta2 = xpow(theta, 2);
-    const xd theta4 = xpow(theta, 4);
-    const xd theta6 = xpow(theta, 6);
-    const xd theta8 = xpow(theta, 8);
+    const S r = xsqrt(px * px + py * py);
+    const S theta = xatan2(r, xabs(pz));
+    const S theta2 = xpow(theta, 2);
+    const S theta4 = xpow(theta, 4);
+    const S theta6 = xpow(theta, 6);
+    const S theta8 = xpow(theta, 8);
     const xd k1 = d[0], k2 = d[1], k3 = d[2], k4 = d[3];
-    const xd theta_d = theta * (xd(1.0) + k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8);
-    const xd s = theta_d / r;
+    const S theta_d = theta * (xd(1.0) + k1 * theta2 + k2 * theta4 + k3 * theta6 + k4 * theta8);
+    const S s = theta_d / r;
     u = xd(in[0]) * (s * px) + xd(in[2]);
     v = xd(in[1]) * (s * py) + xd(in[3]);
   } else if constexpr (MODEL == CAM_ATAN) {
     // atan.hpp:30-38 ; distort :14-27
-    const xd x = px / pz;
-    const xd y = py / pz;
-    xd xdst = x, ydst = y;
+    const S x = px / pz;
+    const S y = py / pz;
+    S xdst = x, ydst = y;
     const xd d0 = d[0];
-    const xd r = xsqrt(x * x + y * y);
+    const S r = xsqrt(x * x + y * y);
     if (!(r < xd(1e-3) || d0 < xd(1e-7))) {
       const xd d1 = xd(1.0) / d0;
       const xd d2 = xd(2.0) * xtan(d0 / xd(2.0));
-      const xd factor = d1 * xatan(r * d2) / r;
+      const S factor = d1 * xatan(r * d2) / r;
       xdst = factor * x;
       ydst = factor * y;
     }
@@ -110,59 +113,64 @@ VL_HD void project_exact(const CameraParams& c, xd px, xd py, xd pz, xd& u, xd& 
     // omnidir.hpp:14-40
     const xd fx = in[0], fy = in[1], cx = in[2], cy = in[3], xi = in[4];
     const xd k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3];
-    xd sx = px, sy = py, sz = pz;
-    const xd n2 = sqnorm3(px, py, pz);
+    S sx = px, sy = py, sz = pz;
+    const S n2 = sqnorm3(px, py, pz);
     if (n2 > xd(0.0)) {
-      const xd n = xsqrt(n2);
+      const S n = xsqrt(n2);
       sx = px / n, sy = py / n, sz = pz / n;
     }
-    const xd ux = sx / (sz + xi);
-    const xd uy = sy / (sz + xi);
-    const xd r2 = ux * ux + uy * uy;
-    const xd r4 = r2 * r2;
-    const xd dr = (xd(1.0) + k1 * r2 + k2 * r4);
-    const xd x2 = ux * ux;
-    const xd y2 = uy * uy;
-    const xd xy = ux * uy;
-    const xd nx = ux * dr + xd(2.0) * p1 * xy + p2 * (r2 + xd(2.0) * x2);
-    const xd ny = uy * dr + p1 * (r2 + xd(2.0) * y2) + xd(2.0) * p2 * xy;
+    const S ux = sx / (sz + xi);
+    const S uy = sy / (sz + xi);
+    const S r2 = ux * ux + uy * uy;
+    const S r4 = r2 * r2;
+    const S dr = (xd(1.0) + k1 * r2 + k2 * r4);
+    const S x2 = ux * ux;
+    const S y2 = uy * uy;
+    const S xy = ux * uy;
+    const S nx = ux * dr + xd(2.0) * p1 * xy + p2 * (r2 + xd(2.0) * x2);
+    const S ny = uy * dr + p1 * (r2 + xd(2.0) * y2) + xd(2.0) * p2 * xy;
     u = fx * nx + cx;
     v = fy * ny + cy;
   } else if constexpr (MODEL == CAM_EQUIRECTANGULAR) {
     // equirectangular.hpp:14-28
-    const xd n2 = sqnorm3(px, py, pz);
+    const S n2 = sqnorm3(px, py, pz);
     if (n2 < xd(1e-3)) {
-      u = xd(in[0]) / xd(2.0);
-      v = xd(in[1]) / xd(2.0);
+      u = S(xd(in[0]) / xd(2.0));
+      v = S(xd(in[1]) / xd(2.0));
       return;
     }
-    const xd n = xsqrt(n2);  // n2 >= 1e-3 > 0 -> normalized() divides
-    const xd bx = px / n, by = py / n, bz = pz / n;
-    const xd lat = -xasin(by);
-    const xd lon = xatan2(bx, bz);
+    const S n = xsqrt(n2);  // n2 >= 1e-3 > 0 -> normalized() divides
+    const S bx = px / n, by = py / n, bz = pz / n;
+    const S lat = -xasin(by);
+    const S lon = xatan2(bx, bz);
     u = xd(in[0]) * (xd(0.5) + lon / xd(2.0 * M_PI));
     v = xd(in[1]) * (xd(0.5) - lat / xd(M_PI));
   } else {  // CAM_RATIONAL_POLYNOMIAL
     // rational_polynomial.hpp:47-58 ; distort :11-44
-    const xd x = px / pz;
-    const xd y = py / pz;
+    const S x = px / pz;
+    const S y = py / pz;
     const xd k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4], k4 = d[5], k5 = d[6], k6 = d[7];
-    const xd x2 = x * x;
-    const xd y2 = y * y;
-    const xd r2 = x2 + y2;
-    const xd r4 = r2 * r2;
-    const xd r6 = r2 * r4;
-    const xd numerator = xd(1.0) + k1 * r2 + k2 * r4 + k3 * r6;
-    const xd denominator = xd(1.0) + k4 * r2 + k5 * r4 + k6 * r6;
-    const xd r_coeff = denominator > xd(1e-8) ? numerator / denominator : numerator;  // :33
-    const xd t_coeff1 = xd(2.0) * x * y;
-    const xd t_coeff2 = r2 + xd(2.0) * x2;
-    const xd t_coeff3 = r2 + xd(2.0) * y2;
-    const xd xdst = r_coeff * x + p1 * t_coeff1 + p2 * t_coeff2;
-    const xd ydst = r_coeff * y + p1 * t_coeff3 + p2 * t_coeff1;
+    const S x2 = x * x;
+    const S y2 = y * y;
+    const S r2 = x2 + y2;
+    const S r4 = r2 * r2;
+    const S r6 = r2 * r4;
+    const S numerator = xd(1.0) + k1 * r2 + k2 * r4 + k3 * r6;
+    const S denominator = xd(1.0) + k4 * r2 + k5 * r4 + k6 * r6;
+    const S r_coeff = denominator > xd(1e-8) ? numerator / denominator : numerator;  // :33
+    const S t_coeff1 = xd(2.0) * x * y;
+    const S t_coeff2 = r2 + xd(2.0) * x2;
+    const S t_coeff3 = r2 + xd(2.0) * y2;
+    const S xdst = r_coeff * x + p1 * t_coeff1 + p2 * t_coeff2;
+    const S ydst = r_coeff * y + p1 * t_coeff3 + p2 * t_coeff1;
     u = xd(in[0]) * xdst + xd(in[2]);
     v = xd(in[1]) * ydst + xd(in[3]);
   }
+}
+
+template <int MODEL>
+VL_HD void project_exact(const CameraParams& c, xd px, xd py, xd pz, xd& u, xd& v) {
+  project_generic<MODEL, xd>(c, px, py, pz, u, v);
 }
 
 // ---------------------------------------------------------------------------------------------

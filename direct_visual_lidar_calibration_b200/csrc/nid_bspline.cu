@@ -28,6 +28,25 @@ static NidBKernel pick_b_kernel(int model, bool f32) {
   }
 }
 
+using NidGKernel = void (*)(const NidGArgs);
+
+template <int MODEL>
+static NidGKernel pick_g_layout(bool f32) {
+  return f32 ? nid_bspline_grad_kernel<MODEL, true> : nid_bspline_grad_kernel<MODEL, false>;
+}
+
+static NidGKernel pick_g_kernel(int model, bool f32) {
+  switch (model) {
+    case CAM_PLUMB_BOB: return pick_g_layout<CAM_PLUMB_BOB>(f32);
+    case CAM_FISHEYE: return pick_g_layout<CAM_FISHEYE>(f32);
+    case CAM_ATAN: return pick_g_layout<CAM_ATAN>(f32);
+    case CAM_OMNIDIR: return pick_g_layout<CAM_OMNIDIR>(f32);
+    case CAM_EQUIRECTANGULAR: return pick_g_layout<CAM_EQUIRECTANGULAR>(f32);
+    case CAM_RATIONAL_POLYNOMIAL: return pick_g_layout<CAM_RATIONAL_POLYNOMIAL>(f32);
+    default: return nullptr;
+  }
+}
+
 struct PoolBuf {
   void* p = nullptr;
   int device = 0;
@@ -112,5 +131,75 @@ extern "C" int vlcal_nid_evaluate_bspline(vlcal_nid_ctx* ctx, const double* T_pa
   VL_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ok_out)
     for (int p = 0; p < n_poses; p++) ok_out[p] = ok_host[p];
+  return VLCAL_OK;
+}
+
+// value + gradient of the mode-B cost (NIDCost::operator()<ceres::Jet<double, 7>>), one launch per pose
+extern "C" int vlcal_nid_evaluate_bspline_grad(vlcal_nid_ctx* ctx, const double* T_params, int n_poses, double* nid_out, double* grad_out, int32_t* ok_out) {
+  if (!ctx || !T_params || n_poses <= 0 || !nid_out || !grad_out) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  if (ctx->mode != VLCAL_NID_MODE_BSPLINE) {
+    set_last_error("context was created in histogram mode; create it with VLCAL_NID_MODE_BSPLINE");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  VL_CUDA(cudaSetDevice(ctx->device));
+  const int bins = ctx->bins, nb = bins * bins;
+  const size_t smem = static_cast<size_t>(nb) * 8 * 8 + static_cast<size_t>(bins) * 4 + 16;
+  if (smem > 200 * 1024) {
+    set_last_error("bins too large for the gradient kernel's shared-memory histogram (bins <= 56)");
+    return VLCAL_ERR_UNSUPPORTED;
+  }
+  PoolBuf gjoint, gpart, gpoints, counter, d_out;
+  VL_CUDA(gjoint.alloc(ctx->device, sizeof(unsigned long long) * nb));
+  VL_CUDA(gpart.alloc(ctx->device, sizeof(double) * nb * 7));
+  VL_CUDA(gpoints.alloc(ctx->device, sizeof(int) * bins));
+  VL_CUDA(counter.alloc(ctx->device, sizeof(unsigned int)));
+  VL_CUDA(d_out.alloc(ctx->device, sizeof(double) * 9 * n_poses));
+  VL_CUDA(cudaMemsetAsync(gjoint.p, 0, sizeof(unsigned long long) * nb, ctx->stream));
+  VL_CUDA(cudaMemsetAsync(gpart.p, 0, sizeof(double) * nb * 7, ctx->stream));
+  VL_CUDA(cudaMemsetAsync(gpoints.p, 0, sizeof(int) * bins, ctx->stream));
+  VL_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned int), ctx->stream));
+
+  NidGKernel kernel = pick_g_kernel(ctx->cam.model, ctx->cloud->f32);
+  VL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int blocks_per_sm = 1;
+  VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, NIDG_THREADS, smem));
+  const long long want = (ctx->cloud->n + NIDG_THREADS - 1) / NIDG_THREADS;
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(ctx->num_sms) * std::max(1, blocks_per_sm))));
+  static const double C6[4][4] = {{1.0, -3.0, 3.0, -1.0}, {4.0, 0.0, -6.0, 3.0}, {1.0, 3.0, 3.0, -3.0}, {0.0, 0.0, 0.0, 1.0}};  // nid_cost.hpp:29-32
+  for (int p = 0; p < n_poses; p++) {
+    NidGArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.points = ctx->cloud->d_points;
+    a.bin_image = ctx->d_bin_image;
+    a.n = ctx->cloud->n;
+    a.width = ctx->image->width;
+    a.height = ctx->image->height;
+    a.bins = bins;
+    a.nb = nb;
+    a.cam = ctx->cam;
+    std::memcpy(a.pose, T_params + 7 * static_cast<size_t>(p), 7 * sizeof(double));
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) a.C[i][j] = C6[i][j] / 6.0;
+    a.gjoint = static_cast<unsigned long long*>(gjoint.p);
+    a.gpart = static_cast<double*>(gpart.p);
+    a.gpoints = static_cast<int*>(gpoints.p);
+    a.counter = static_cast<unsigned int*>(counter.p);
+    a.out = static_cast<double*>(d_out.p) + 9 * static_cast<size_t>(p);
+    kernel<<<grid, NIDG_THREADS, smem, ctx->stream>>>(a);
+    VL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    ctx->poses_total += 1;
+  }
+  std::vector<double> host(static_cast<size_t>(9) * n_poses);
+  VL_CUDA(cudaMemcpyAsync(host.data(), d_out.p, sizeof(double) * 9 * n_poses, cudaMemcpyDeviceToHost, ctx->stream));
+  VL_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int p = 0; p < n_poses; p++) {
+    nid_out[p] = host[9 * static_cast<size_t>(p)];
+    for (int k = 0; k < 7; k++) grad_out[7 * static_cast<size_t>(p) + k] = host[9 * static_cast<size_t>(p) + 1 + k];
+    if (ok_out) ok_out[p] = host[9 * static_cast<size_t>(p) + 8] != 0.0 ? 1 : 0;
+  }
   return VLCAL_OK;
 }

@@ -463,7 +463,12 @@ static void fill_common_args(vlcal_nid_ctx* ctx, NidArgs& a) {
 static NidKernel select_kernel(vlcal_nid_ctx* ctx, bool devloop = false) {
   // the fp32 filter needs the float4 layout, a camera/FoV it has bounds for, and 32-bit point indices
   const bool use_filter = ctx->variant != 1 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
-  return pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? (ctx->variant == 2 ? 3 : 0) : 1, devloop);
+  // points per lane and tile: 4 for the polynomial pinhole models; 2 for the models whose projection carries
+  // transcendental calls and more live state per point (measured: fisheye / equirectangular 8-17 % faster with 2 at
+  // 5 M points, plumb_bob up to 8 % faster with 4 at 0.26 M; profiles/r01_final_configs.jsonl, r01_final_kernel_scaling.jsonl)
+  const bool light = ctx->cam.model == CAM_PLUMB_BOB || ctx->cam.model == CAM_RATIONAL_POLYNOMIAL;
+  const int filter_kind = ctx->variant == 2 ? 3 : (ctx->variant == 3 ? 0 : (light ? 0 : 3));
+  return pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? filter_kind : 1, devloop);
 }
 
 constexpr int PROFILE_STRIDE = 4;
@@ -869,7 +874,7 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
 }
 
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 2) return VLCAL_ERR_INVALID_ARGUMENT;
+  if (!ctx || variant < 0 || variant > 3) return VLCAL_ERR_INVALID_ARGUMENT;
   ctx->variant = variant;
   return VLCAL_OK;
 }

@@ -125,6 +125,13 @@ int vlcal_nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out);
  * false (non-finite NID, :98-102).  hist_out: optional P x bins x bins doubles (un-normalised). */
 int vlcal_nid_evaluate_bspline(vlcal_nid_ctx* ctx, const double* T_params, int n_poses, double* nid_out, int32_t* ok_out, double* hist_out);
 
+/* mode B value AND gradient: what ceres::AutoDiffFirstOrderFunction<MultiNIDCost, 7> evaluates per bag in the
+ * reference's BFGS branch (NIDCost::operator()<ceres::Jet<double, 7>>, nid_cost.hpp:36-107 called from
+ * visual_camera_calibration.cpp:141-173,211).  grad_out = P x 7 doubles, d NID / d [qx qy qz qw tx ty tz] (ambient
+ * parameters; the reference's Sophus::Manifold<SE3> projects them onto the 6-D tangent space afterwards).
+ * ok_out as above.  One kernel launch per pose. */
+int vlcal_nid_evaluate_bspline_grad(vlcal_nid_ctx* ctx, const double* T_params, int n_poses, double* nid_out, double* grad_out, int32_t* ok_out);
+
 /* introspection */
 int64_t vlcal_nid_num_points(const vlcal_nid_ctx* ctx);
 int vlcal_nid_bins(const vlcal_nid_ctx* ctx);
@@ -140,8 +147,9 @@ int vlcal_nid_max_poses_per_launch(void);
 int vlcal_nid_set_profiling(vlcal_nid_ctx* ctx, int enable);
 int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* kernel_ms_total, int64_t* poses_total);
 int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
-/* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck, 4 points/thread),
- * 1 = exact fp64 only, 2 = fp32 filter with 2 points/thread */
+/* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck; 4 points per lane and tile for
+ * plumb_bob / rational_polynomial, 2 for the other camera models), 1 = exact fp64 only, 2 = filter forced to 2 points,
+ * 3 = filter forced to 4 points */
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
 
 /* measurement hook: one launch (n_poses <= 8) with %globaltimer stamps; out_us = {main loop done, merged, ticket, finalize done,

@@ -572,3 +572,54 @@ def test_filter_bound_fuzz_over_random_cameras(gpu, model):
         assert np.array_equal(h_f, h_e)
         checked += 1
     assert checked >= 6
+
+
+@pytest.mark.parametrize("model", util.MODELS)
+def test_bspline_gradient_matches_oracle(gpu, oracle, model):
+    """K3: NIDCost::operator()<ceres::Jet<double, 7>> -- value and d NID / d (qx qy qz qw tx ty tz) against the oracle
+    (which tests/test_reference_pin.py pins bit-exact to the reference functor)."""
+    pr = util.random_problem(model, n=20000, seed=81)
+    Ts = util.random_poses(pr["T"], 3, seed=4)
+    tps = np.stack([_sophus_params(T) for T in Ts])
+    cam = gpu.create_camera(model, pr["intrinsics"], pr["distortion"])
+    cost = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], pr["points"], pr["intensities"]), 16)
+    ok, nid, grad = cost.evaluate_with_gradient(tps)
+    ocam = oracle.create_camera(model, pr["intrinsics"], pr["distortion"])
+    for p in range(len(Ts)):
+        rok, rnid, rgrad = oracle.nid_cost_bspline_grad(ocam, pr["image"], pr["points"], pr["intensities"], 16, tps[p])
+        assert bool(ok[p]) == rok
+        assert abs(nid[p] - rnid) < 1e-9, abs(nid[p] - rnid)
+        scale = max(1.0, np.abs(rgrad).max())
+        assert np.abs(grad[p] - rgrad).max() < 1e-8 * scale, (grad[p], rgrad)
+        assert np.abs(rgrad).max() > 1e-4
+    # the value half agrees with the value-only kernel (different rounding of the divisions: Jet vs double functor)
+    ok2, nid2 = cost.evaluate(tps)
+    assert np.abs(nid - nid2).max() < 1e-9
+    # run-to-run: the weights are fixed point (bit-stable), the partial sums are double atomics (last bits may move)
+    ok3, nid3, grad3 = cost.evaluate_with_gradient(tps)
+    assert np.array_equal(nid, nid3) and np.abs(grad - grad3).max() < 1e-10 * max(1.0, np.abs(grad).max())
+
+
+def test_bspline_gradient_other_bins_and_failure_flag(gpu, oracle):
+    pr = util.random_problem("plumb_bob", n=10000, seed=82)
+    tp = _sophus_params(pr["T"])
+    cam = gpu.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
+    ocam = oracle.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
+    for bins in (8, 32):
+        ok, nid, grad = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], pr["points"], pr["intensities"]), bins).evaluate_with_gradient(tp[None])
+        rok, rnid, rgrad = oracle.nid_cost_bspline_grad(ocam, pr["image"], pr["points"], pr["intensities"], bins, tp)
+        assert ok[0] == rok and abs(nid[0] - rnid) < 1e-9 and np.abs(grad[0] - rgrad).max() < 1e-8 * max(1.0, np.abs(rgrad).max())
+    far = np.array([[1.0, 5e3, 0.0, 1.0]] * 10)  # every projection lands outside the image -> NaN -> false (nid_cost.hpp:98-102)
+    ok, _, _ = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], far, np.full(10, 0.5)), 16).evaluate_with_gradient(tp[None])
+    rok, _, _ = oracle.nid_cost_bspline_grad(ocam, pr["image"], far, np.full(10, 0.5), 16, tp)
+    assert not ok[0] and not rok
+
+
+def test_bspline_gradient_double_layout(gpu, oracle):
+    pr = util.random_problem("fisheye", n=8000, seed=83, f32=False)
+    tp = _sophus_params(pr["T"])
+    cam = gpu.create_camera("fisheye", pr["intrinsics"], pr["distortion"])
+    ocam = oracle.create_camera("fisheye", pr["intrinsics"], pr["distortion"])
+    ok, nid, grad = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], pr["points"], pr["intensities"]), 16).evaluate_with_gradient(tp[None])
+    rok, rnid, rgrad = oracle.nid_cost_bspline_grad(ocam, pr["image"], pr["points"], pr["intensities"], 16, tp)
+    assert ok[0] == rok and abs(nid[0] - rnid) < 1e-9 and np.abs(grad[0] - rgrad).max() < 1e-8 * max(1.0, np.abs(rgrad).max())

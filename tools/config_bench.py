@@ -20,7 +20,7 @@ except Exception:
     pass
 
 
-def measure(name, bag, poses, launches=30, cpu_evals=3, variants=((0, "filter"), (2, "filter_kpt2"), (1, "exact_fp64")), tile_order=True):
+def measure(name, bag, poses, launches=30, cpu_evals=3, variants=((0, "filter"), (2, "filter_kpt2"), (3, "filter_kpt4"), (1, "exact_fp64")), tile_order=True):
     cam = V.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
     ocam = O.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
     data = V.VisualLiDARData(bag["image"], bag["points"], bag["intensities"])

@@ -18,7 +18,7 @@ rng = np.random.default_rng(0)
 poses = np.stack([S.perturb(bag["T_gt"], rng.uniform(-0.05, 0.05, 3), rng.uniform(-0.002, 0.002, 3)) for _ in range(8)])
 for n in (1024, 65536, 262144, len(pts)):
     cost = V.CostCalculatorNID(cam, V.VisualLiDARData(bag["image"], pts[:n], inten[:n]))
-    for variant, name in ((0, "filter_kpt4"), (2, "filter_kpt2"), (1, "exact_fp64")):
+    for variant, name in ((3, "filter_kpt4"), (2, "filter_kpt2"), (1, "exact_fp64")):
         cost.set_kernel_variant(variant)
         for P in (1, 4, 8):
             for _ in range(5):
