@@ -19,6 +19,7 @@ from .camera import GenericCamera, create_camera
 from .cost import CostCalculatorNID, NIDCost, NIDCostParams, VisualLiDARData
 from .culling import ViewCulling, ViewCullingParams
 from .nelder_mead import NelderMead, NelderMeadParams
+from . import bfgs
 from .calibration import RegistrationType, VisualCameraCalibration, VisualCameraCalibrationParams, estimate_camera_fov, se3_expmap
 
 __all__ = [

@@ -80,6 +80,22 @@ class CalibStats(C.Structure):
     ]
 
 
+class BfgsParams(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int), ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+        ("sufficient_decrease", C.c_double), ("sufficient_curvature_decrease", C.c_double), ("max_step_expansion", C.c_double), ("max_line_search_steps", C.c_int),
+        ("max_translation_from_init", C.c_double), ("max_rotation_from_init", C.c_double),
+    ]
+
+
+class BfgsResult(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int), ("evaluations", C.c_int), ("termination", C.c_int), ("line_search_restarts", C.c_int),
+        ("initial_cost", C.c_double), ("final_cost", C.c_double), ("gradient_max_norm", C.c_double),
+    ]
+
+
+SE3_OBJECTIVE = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 NM_BATCH_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p)
 NM_OBSERVE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_void_p)
 POSE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_double, C.c_void_p)
@@ -145,6 +161,10 @@ def load_library():
     common = [C.c_int, C.c_int, dp, C.c_int, dp, C.c_int, C.POINTER(Bag), C.c_int, C.POINTER(CalibParams), dp, POSE_CALLBACK, ALLREDUCE_FN, vp, C.c_int, dp]
     L.vlcal_estimate_pose_nelder_mead.argtypes = common + [C.POINTER(NMResult), C.POINTER(CalibStats)]
     L.vlcal_calibrate_nelder_mead.argtypes = common + [C.POINTER(CalibStats)]
+    L.vlcal_bfgs_default_params.argtypes = [C.POINTER(BfgsParams)]
+    L.vlcal_bfgs_default_params.restype = None
+    L.vlcal_bfgs_minimize_se3.argtypes = [SE3_OBJECTIVE, vp, C.POINTER(BfgsParams), dp, POSE_CALLBACK, vp, dp, C.POINTER(BfgsResult)]
+    L.vlcal_estimate_pose_bfgs_ctx.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(BfgsParams), dp, POSE_CALLBACK, vp, dp, C.POINTER(BfgsResult)]
     _lib = L
     return L
 

@@ -1,5 +1,6 @@
-"""vlcal::VisualCameraCalibration mirror, NID_NELDER_MEAD branch
-(reference: include/vlcal/calib/visual_camera_calibration.hpp, src/vlcal/calib/visual_camera_calibration.cpp:35-139)."""
+"""vlcal::VisualCameraCalibration mirror (reference: include/vlcal/calib/visual_camera_calibration.hpp,
+src/vlcal/calib/visual_camera_calibration.cpp): the NID_NELDER_MEAD branch (:70-139, trajectory-exact, the hot path) and
+the NID_BFGS branch (:187-238: mode-B value + gradient on the GPU, Ceres-free BFGS -- see bfgs.py)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -41,8 +42,10 @@ class VisualCameraCalibrationParams:
         self.delta_rot_thresh = 0.5 * math.pi / 180.0
         self.disable_z_buffer_culling = False
         self.nid_bins = 16
-        # the CLI default is NID_BFGS (src/calibrate.cpp:176); only the Nelder-Mead branch is in scope here
+        # the reference's default is NID_BFGS (visual_camera_calibration.hpp:22, src/calibrate.cpp:176); the hot path of this
+        # repository is the Nelder-Mead branch, which stays the default here
         self.registration_type = RegistrationType.NID_NELDER_MEAD
+        self.bfgs_params = None  # _lib.BfgsParams; None = Ceres' documented defaults (bfgs.default_bfgs_params())
         self.nelder_mead_init_step = 1e-3
         self.nelder_mead_convergence_criteria = 1e-8
         self.callback = None  # callable(T_camera_lidar[4,4]) on every best-cost improvement
@@ -110,10 +113,55 @@ class VisualCameraCalibration:
 
     def _check_type(self):
         if self.params.registration_type != RegistrationType.NID_NELDER_MEAD:
-            raise _lib.VlcalError(_lib.ERR_UNSUPPORTED, "only RegistrationType.NID_NELDER_MEAD is built (the BFGS / NIDCost autodiff branch is out of scope)")
+            raise _lib.VlcalError(_lib.ERR_UNSUPPORTED, "this entry point is the Nelder-Mead branch; use calibrate() / estimate_pose_bfgs() for RegistrationType.NID_BFGS")
+
+    def estimate_pose_bfgs(self, init_T_camera_lidar):
+        """One inner BFGS solve (visual_camera_calibration.cpp:187-238): cull every bag at the start pose (:196), build one
+        NIDCost per bag on the image / 255 (:198-206), minimise their sum (:208-228).  Returns (T, result dict)."""
+        from . import bfgs
+        from .cost import NIDCost
+        from .culling import ViewCulling, ViewCullingParams
+
+        if self.allreduce is not None:
+            raise _lib.VlcalError(_lib.ERR_UNSUPPORTED, "the BFGS branch is single-process (the bag all-reduce exists for the Nelder-Mead path)")
+        first = self.dataset[0]
+        culling = ViewCulling(self.proj, (first.image.shape[1], first.image.shape[0]), ViewCullingParams(not self.params.disable_z_buffer_culling), device=self.device)
+        costs = []
+        for d in self.dataset:
+            pts, ins = culling.cull(d.points, d.intensities, init_T_camera_lidar)
+            costs.append(NIDCost(self.proj, VisualLiDARData(d.image, pts, ins), self.params.nid_bins, device=self.device))
+
+        def _cb(T, cost):
+            self.trace.append((T, cost))
+            if self.params.callback:
+                self.params.callback(T)
+
+        try:
+            T, r = bfgs.estimate_pose_bfgs_on_costs(costs, init_T_camera_lidar, self.params.bfgs_params, _cb)
+        finally:
+            for c in costs:
+                c.close()
+        return T, r
+
+    def _calibrate_bfgs(self, init_T_camera_lidar) -> np.ndarray:
+        """Outer loop of visual_camera_calibration.cpp:35-68 around estimate_pose_bfgs."""
+        T = np.array(init_T_camera_lidar, dtype=np.float64).reshape(4, 4)
+        inner = []
+        for _ in range(self.params.max_outer_iterations):
+            new_T, r = self.estimate_pose_bfgs(T)
+            inner.append(r)
+            delta = np.linalg.inv(new_T) @ T
+            T = new_T
+            delta_t = float(np.linalg.norm(delta[:3, 3]))
+            delta_r = float(np.arccos(np.clip(0.5 * (np.trace(delta[:3, :3]) - 1.0), -1.0, 1.0)))
+            if delta_t < self.params.delta_trans_thresh and delta_r < self.params.delta_rot_thresh:
+                break
+        self.stats = {"outer_iterations": len(inner), "inner": inner, "total_evaluations": sum(r["evaluations"] for r in inner)}
+        return T
 
     def calibrate(self, init_T_camera_lidar) -> np.ndarray:
-        self._check_type()
+        if self.params.registration_type == RegistrationType.NID_BFGS:
+            return self._calibrate_bfgs(init_T_camera_lidar)
         L = _lib.load_library()
         bags = _make_bags(self.dataset)
         cb, ar = self._callbacks()

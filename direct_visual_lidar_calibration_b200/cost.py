@@ -185,6 +185,10 @@ class NIDCost:
             return ok.astype(bool), nid, np.swapaxes(hist.reshape(P, self.bins, self.bins), 1, 2).copy()
         return ok.astype(bool), nid
 
+    @property
+    def handle(self):
+        return self._ctx
+
     def evaluate_with_gradient(self, T_params):
         """NIDCost::operator()<ceres::Jet<double, 7>>: (ok[P], nid[P], grad[P, 7]) with grad = d NID / d [qx qy qz qw tx ty tz]."""
         tp = np.ascontiguousarray(np.asarray(T_params, dtype=np.float64)).reshape(-1, 7)

@@ -353,6 +353,68 @@ int vlcal_calibrate_nelder_mead(
   double T_out[16],
   vlcal_calib_stats* stats);
 
+/* ---- NID_BFGS branch (VisualCameraCalibration::estimate_pose_bfgs, visual_camera_calibration.cpp:187-238) -------------
+ * The reference solves min_T sum_bags NIDCost(T) with ceres::GradientProblemSolver (line-search BFGS) on the
+ * Sophus::Manifold<SE3>.  Ceres is not available to this build, so this is a Ceres-free BFGS with the same problem
+ * structure and Ceres' documented defaults (csrc/bfgs.cu); its iterates are not claimed to coincide with Ceres'. */
+typedef struct vlcal_bfgs_params {
+  int max_num_iterations;               /* 50   */
+  double function_tolerance;            /* 1e-6  |d cost| <= tol * cost */
+  double gradient_tolerance;            /* 1e-10 max norm of the tangent-space gradient */
+  double parameter_tolerance;           /* 1e-8  */
+  double sufficient_decrease;           /* 1e-4  (Armijo) */
+  double sufficient_curvature_decrease; /* 0.9   (strong Wolfe) */
+  double max_step_expansion;            /* 10    */
+  int max_line_search_steps;            /* 20    */
+  double max_translation_from_init;     /* 0.2 m   MultiNIDCost returns false beyond it (:154) */
+  double max_rotation_from_init;        /* 2 deg in rad (:154) */
+} vlcal_bfgs_params;
+
+enum {
+  VLCAL_BFGS_NO_CONVERGENCE = 0, /* max_num_iterations reached */
+  VLCAL_BFGS_CONVERGED_GRADIENT = 1,
+  VLCAL_BFGS_CONVERGED_FUNCTION = 2,
+  VLCAL_BFGS_CONVERGED_PARAMETER = 3,
+  VLCAL_BFGS_LINE_SEARCH_FAILED = 4,
+  VLCAL_BFGS_FAILURE = 5 /* objective invalid at the initial pose */
+};
+
+typedef struct vlcal_bfgs_result {
+  int iterations;
+  int evaluations; /* value + gradient evaluations requested (each = one pose over all bags) */
+  int termination;
+  int line_search_restarts;
+  double initial_cost, final_cost;
+  double gradient_max_norm;
+} vlcal_bfgs_result;
+
+void vlcal_bfgs_default_params(vlcal_bfgs_params* p);
+
+/* value and AMBIENT gradient (d/d[qx qy qz qw tx ty tz]) of an objective on SE(3); return 0 for "invalid here" */
+typedef int (*vlcal_se3_objective)(const double x[7], double* cost, double grad7[7], void* user);
+
+/* the solver on a caller-supplied objective (host only; used by the CPU tests and for custom costs) */
+int vlcal_bfgs_minimize_se3(
+  vlcal_se3_objective objective,
+  void* user,
+  const vlcal_bfgs_params* params,
+  const double init_T[16],
+  vlcal_pose_callback callback, /* once per accepted iteration (IterationCallback, :222-226) */
+  void* callback_user,
+  double T_out[16],
+  vlcal_bfgs_result* result);
+
+/* the inner BFGS solve over mode-B contexts (one per bag, already culled at init_T like :196-206) */
+int vlcal_estimate_pose_bfgs_ctx(
+  vlcal_nid_ctx* const* ctxs,
+  int n_ctx,
+  const vlcal_bfgs_params* params,
+  const double init_T_camera_lidar[16],
+  vlcal_pose_callback callback,
+  void* user,
+  double T_out[16],
+  vlcal_bfgs_result* result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -623,3 +623,36 @@ def test_bspline_gradient_double_layout(gpu, oracle):
     ok, nid, grad = gpu.NIDCost(cam, gpu.VisualLiDARData(pr["image"], pr["points"], pr["intensities"]), 16).evaluate_with_gradient(tp[None])
     rok, rnid, rgrad = oracle.nid_cost_bspline_grad(ocam, pr["image"], pr["points"], pr["intensities"], 16, tp)
     assert ok[0] == rok and abs(nid[0] - rnid) < 1e-9 and np.abs(grad[0] - rgrad).max() < 1e-8 * max(1.0, np.abs(rgrad).max())
+
+
+def test_bfgs_branch_runs_on_the_gpu_cost(gpu, oracle):
+    """NID_BFGS branch (visual_camera_calibration.cpp:187-238) on K3: the solver is ours (Ceres-free), so the checks are
+    (i) every cost it reports is the oracle's mode-B NID of the same culled cloud at that pose, (ii) it descends,
+    (iii) it stays inside the reference's 0.2 m / 2 deg trust region."""
+    from direct_visual_lidar_calibration_b200 import synthetic as S
+
+    bag = S.make_bag("pinhole_640x480", "frustum", 40000, config_index=11, scale=0.5)
+    cam = gpu.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    T0 = S.perturb(bag["T_gt"], (0.3, -0.2, 0.25), (0.01, -0.008, 0.006))
+    params = gpu.VisualCameraCalibrationParams()
+    params.registration_type = gpu.RegistrationType.NID_BFGS
+    seen = []
+    params.callback = lambda T: seen.append(T.copy())
+    calib = gpu.VisualCameraCalibration(cam, [gpu.VisualLiDARData(bag["image"], bag["points"], bag["intensities"])], params)
+    T, r = calib.estimate_pose_bfgs(T0)
+    assert r["iterations"] >= 1 and len(seen) == r["iterations"] and r["final_cost"] < r["initial_cost"], r
+    d = np.linalg.inv(T0) @ T
+    assert np.linalg.norm(d[:3, 3]) <= 0.2 and np.arccos(np.clip(0.5 * (np.trace(d[:3, :3]) - 1), -1, 1)) <= np.deg2rad(2.0)
+    # the costs are the reference functor's values on the cloud culled at T0 (view_culling.cpp + nid_cost.hpp)
+    ocam = oracle.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    fov = oracle.estimate_camera_fov(ocam, bag["width"], bag["height"])
+    idx = oracle.view_cull(ocam, bag["width"], bag["height"], fov, True, bag["points"], T0)
+    pts, ins = bag["points"][idx], bag["intensities"][idx]
+    ok0, c0, _ = oracle.nid_cost_bspline_grad(ocam, bag["image"], pts, ins, 16, _sophus_params(T0))
+    ok1, c1, g1 = oracle.nid_cost_bspline_grad(ocam, bag["image"], pts, ins, 16, _sophus_params(T))
+    assert ok0 and ok1 and abs(c0 - r["initial_cost"]) < 1e-9 and abs(c1 - r["final_cost"]) < 1e-9
+    assert [c for _, c in calib.trace] == sorted([c for _, c in calib.trace], reverse=True)  # monotone descent
+    # the outer loop (visual_camera_calibration.cpp:35-68) around it
+    params.max_outer_iterations = 2
+    T2 = calib.calibrate(T0)
+    assert calib.stats["outer_iterations"] >= 1 and np.isfinite(T2).all()
