@@ -219,6 +219,9 @@ CAMERAS = {
     "pinhole_1920x1080": ("plumb_bob", [1000.0, 1000.0, 960.0, 540.0], [-0.04, 0.08, 1e-4, -3e-4, -0.04], 1920, 1080),
     "equirect_3840x1920": ("equirectangular", [3840.0, 1920.0], [], 3840, 1920),
     "fisheye_1920x1080": ("fisheye", [600.0, 600.0, 960.0, 540.0], [0.01, -0.02, 0.003, -0.001], 1920, 1080),
+    "atan_1920x1080": ("atan", [1000.0, 1000.0, 960.0, 540.0], [0.9], 1920, 1080),
+    "omnidir_1920x1080": ("omnidir", [700.0, 700.0, 960.0, 540.0, 1.1], [-0.1, 0.02, 1e-3, -2e-3], 1920, 1080),
+    "rational_1920x1080": ("rational_polynomial", [1000.0, 1000.0, 960.0, 540.0], [-0.04, 0.08, 1e-4, -3e-4, -0.04, 0.01, 0.02, -0.005], 1920, 1080),
 }
 
 SEED0 = 20260922

@@ -75,7 +75,7 @@ def measure(name, bag, poses, launches=30, cpu_evals=3, variants=((0, "filter"),
 
 
 def main():
-    which = sys.argv[1:] or ["C1", "C3", "C3f", "C5"]
+    which = sys.argv[1:] or ["C1", "C3", "C3f", "TILE", "C5"]
     rng = np.random.default_rng(5)
     if "C1" in which:
         bag = S.config_c1()
@@ -89,6 +89,12 @@ def main():
         bag = S.config_c3(5_000_000, "fisheye_1920x1080")
         poses = np.stack([S.perturb(bag["T_gt"], rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.01, 0.01, 3)) for _ in range(8)])
         measure("C3-fisheye", bag, poses)
+    if "TILE" in which:  # A/B of the per-model tile-size default on the models C3 does not cover
+        for key in ("atan_1920x1080", "omnidir_1920x1080", "rational_1920x1080"):
+            bag = S.config_c3(2_000_000, "pinhole_1920x1080")  # the scene renderer has no inverse for these models: timing + parity only
+            bag["camera_model"], bag["intrinsics"], bag["distortion"] = S.CAMERAS[key][0], S.CAMERAS[key][1], S.CAMERAS[key][2]
+            poses = np.stack([S.perturb(bag["T_gt"], rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.01, 0.01, 3)) for _ in range(8)])
+            measure(f"TILE-{key}", bag, poses, launches=20, cpu_evals=1, variants=((2, "filter_kpt2"), (3, "filter_kpt4")))
     if "C5" in which:
         bag = S.config_c3(5_000_000, "pinhole_1920x1080")
         grid = S.pose_grid(bag["T_gt"])  # 16384 poses
