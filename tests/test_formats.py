@@ -72,12 +72,33 @@ def test_dataset_files_load_like_the_reference(tmp_path):
     assert open(os.path.join(tmp_path, "calib.json")).read().endswith("}\n")
 
 
-def test_cli_rejects_what_is_not_built(tmp_path, capsys):
+def test_cli_rejects_unknown_registration_type(tmp_path, capsys):
     from direct_visual_lidar_calibration_b200 import calibrate as cli
 
     _write_dataset(tmp_path, 1000)
-    assert cli.main([str(tmp_path)]) == 1  # default registration_type is nid_bfgs (calibrate.cpp:176): not built
-    assert "nid_nelder_mead" in capsys.readouterr().err
+    assert cli.main([str(tmp_path), "--registration_type", "nid_newton"]) == 1  # calibrate.cpp:105-108
+    assert "unknown registration type" in capsys.readouterr().err
+
+
+@pytest.mark.gpu
+def test_cli_default_is_the_bfgs_branch(gpu, oracle, tmp_path):
+    """The reference's default registration_type is nid_bfgs (calibrate.cpp:176): runs on K3 + the Ceres-free BFGS."""
+    from direct_visual_lidar_calibration_b200 import calibrate as cli
+
+    bag, T_init = _write_dataset(tmp_path)
+    assert cli.main([str(tmp_path)]) == 0
+    cfg = json.load(open(os.path.join(tmp_path, "calib.json")))
+    T = vio.invert_isometry(vio.tum_to_T(cfg["results"]["T_lidar_camera"]))
+    init_T = vio.invert_isometry(vio.tum_to_T(cfg["results"]["init_T_lidar_camera_auto"]))
+    ocam = oracle.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    from scipy.spatial.transform import Rotation
+
+    def tp(M):
+        return np.concatenate([Rotation.from_matrix(M[:3, :3]).as_quat(), M[:3, 3]])
+
+    c0 = oracle.nid_cost_bspline(ocam, bag["image"], bag["points"], bag["intensities"], 16, tp(init_T))[1]
+    c1 = oracle.nid_cost_bspline(ocam, bag["image"], bag["points"], bag["intensities"], 16, tp(T))[1]
+    assert c1 <= c0 + 1e-6  # mode-B NID over the whole cloud did not get worse
 
 
 @pytest.mark.gpu
