@@ -463,11 +463,15 @@ static void fill_common_args(vlcal_nid_ctx* ctx, NidArgs& a) {
 static NidKernel select_kernel(vlcal_nid_ctx* ctx, bool devloop = false) {
   // the fp32 filter needs the float4 layout, a camera/FoV it has bounds for, and 32-bit point indices
   const bool use_filter = ctx->variant != 1 && ctx->cloud->f32 && ctx->fast.enabled && ctx->cloud->n < 0x7fffffffLL;
-  // points per lane and tile: 4 for the polynomial pinhole models; 2 for the models whose projection carries
-  // transcendental calls and more live state per point (measured: fisheye / equirectangular 8-17 % faster with 2 at
-  // 5 M points, plumb_bob up to 8 % faster with 4 at 0.26 M; profiles/r01_final_configs.jsonl, r01_final_kernel_scaling.jsonl)
-  const bool light = ctx->cam.model == CAM_PLUMB_BOB || ctx->cam.model == CAM_RATIONAL_POLYNOMIAL;
-  const int filter_kind = ctx->variant == 2 ? 3 : (ctx->variant == 3 ? 0 : (light ? 0 : 3));
+  // points per lane and tile (profiles/r01_final_configs.jsonl, r01_final_kernel_scaling.jsonl):
+  //  * fisheye / equirectangular / atan carry transcendental calls and more live state per point: 2 is 2-17 % faster
+  //  * plumb_bob / rational_polynomial / omnidir: 4 wins (6-9 %) while a warp's share of the cloud is a few 128-point
+  //    tiles; below one tile the 4-point path degenerates to single rows, and on long ranges (5 M points) the lighter
+  //    register footprint of 2 wins again (2-5 %)
+  const bool heavy = ctx->cam.model == CAM_FISHEYE || ctx->cam.model == CAM_EQUIRECTANGULAR || ctx->cam.model == CAM_ATAN;
+  const long long points_per_warp = ctx->cloud->n / (static_cast<long long>(ctx->num_sms) * 2 * (NID_THREADS / 32));
+  const bool four = !heavy && points_per_warp >= 96 && points_per_warp <= 1100;
+  const int filter_kind = ctx->variant == 2 ? 3 : (ctx->variant == 3 ? 0 : (four ? 0 : 3));
   return pick_kernel(ctx->cam.model, ctx->cloud->f32, use_filter ? filter_kind : 1, devloop);
 }
 

@@ -147,8 +147,8 @@ int vlcal_nid_max_poses_per_launch(void);
 int vlcal_nid_set_profiling(vlcal_nid_ctx* ctx, int enable);
 int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* kernel_ms_total, int64_t* poses_total);
 int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
-/* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck; 4 points per lane and tile for
- * plumb_bob / rational_polynomial, 2 for the other camera models), 1 = exact fp64 only, 2 = filter forced to 2 points,
+/* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck; 2 or 4 points per lane and
+ * tile, chosen from the camera model and the cloud size), 1 = exact fp64 only, 2 = filter forced to 2 points,
  * 3 = filter forced to 4 points */
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
 

@@ -377,6 +377,9 @@ def test_filter_kernel_is_bit_identical_to_exact_kernel(gpu, oracle, model):
     cost.set_kernel_variant(2)  # filter kernel, 2 points per thread
     nid_2, hist_2 = cost.calculate_batch(Ts, return_hist=True)
     assert np.array_equal(hist_f, hist_2) and np.array_equal(nid_f, nid_2, equal_nan=True)
+    cost.set_kernel_variant(3)  # filter kernel, 4 points per thread
+    nid_4, hist_4 = cost.calculate_batch(Ts, return_hist=True)
+    assert np.array_equal(hist_f, hist_4) and np.array_equal(nid_f, nid_4, equal_nan=True)
     cost.set_kernel_variant(1)  # exact fp64 kernel
     nid_e, hist_e = cost.calculate_batch(Ts, return_hist=True)
     assert int(np.abs(hist_f - hist_e).sum()) == 0 and hist_f.sum() > 100000
