@@ -24,6 +24,8 @@ public:
 class FirstOrderFunction {
 public:
   virtual ~FirstOrderFunction() {}
+  virtual bool Evaluate(const double* const parameters, double* cost, double* gradient) const = 0;
+  virtual int NumParameters() const = 0;
 };
 
 class Manifold {
@@ -36,6 +38,8 @@ class AutoDiffFirstOrderFunction : public FirstOrderFunction {
 public:
   explicit AutoDiffFirstOrderFunction(Functor* f) : functor(f) {}
   ~AutoDiffFirstOrderFunction() override { delete functor; }
+  bool Evaluate(const double* const, double*, double*) const override { return false; }  // no autodiff behind the stand-in
+  int NumParameters() const override { return N; }
 
 private:
   Functor* functor;

@@ -55,3 +55,22 @@ def test_shim_matches_python_surface_and_oracle(gpu, oracle, tmp_path):
     ocam = oracle.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
     onid = oracle.nid_calculate(ocam, pr["image"], pr["points"], pr["intensities"], 16, oracle.estimate_camera_fov(ocam, pr["W"], pr["H"]), pr["T"])[0]
     assert abs(vals[0] - onid) < 1e-12
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "include")), reason="needs the reference tree's headers (this container only)")
+def test_bindings_compile_inside_the_reference_tree(vlcal, tmp_path):
+    """Both reference-side bindings against the reference's OWN headers (third-party ones from oracle/ref_standin):
+    cost_calculator_nid_cuda.hpp (Nelder-Mead branch) and nid_cost_cuda.hpp (BFGS branch, a ceres::FirstOrderFunction)."""
+    exe = str(tmp_path / "cpp_bfgs")
+    libdir = os.path.dirname(vlcal.library_path())
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-w", "-I", os.path.join(ROOT, "oracle", "ref_standin"), "-I", os.path.join(REFERENCE, "include"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(HERE, "cpp_bfgs_main.cpp"), "-o", exe, "-L", libdir, "-lvlcal_nid", f"-Wl,-rpath,{libdir}"]
+    subprocess.run(cmd, check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    if vlcal.device_count() > 0:
+        assert out.returncode == 0 and out.stdout.startswith("EVAL ok="), out.stdout + out.stderr
+    else:  # no CPU fallback: the constructor throws with the library's message
+        assert out.returncode == 3 and "EXCEPTION" in out.stdout, out.stdout + out.stderr
