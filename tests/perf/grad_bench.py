@@ -6,7 +6,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import direct_visual_lidar_calibration_b200 as V
 from direct_visual_lidar_calibration_b200 import synthetic as S
 from oracle import oracle as O
