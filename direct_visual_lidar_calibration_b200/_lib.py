@@ -164,7 +164,7 @@ def load_library():
     L.vlcal_bfgs_default_params.argtypes = [C.POINTER(BfgsParams)]
     L.vlcal_bfgs_default_params.restype = None
     L.vlcal_bfgs_minimize_se3.argtypes = [SE3_OBJECTIVE, vp, C.POINTER(BfgsParams), dp, POSE_CALLBACK, vp, dp, C.POINTER(BfgsResult)]
-    L.vlcal_estimate_pose_bfgs_ctx.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(BfgsParams), dp, POSE_CALLBACK, vp, dp, C.POINTER(BfgsResult)]
+    L.vlcal_estimate_pose_bfgs_ctx.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(BfgsParams), dp, POSE_CALLBACK, ALLREDUCE_FN, vp, dp, C.POINTER(BfgsResult)]
     _lib = L
     return L
 

@@ -56,12 +56,18 @@ def minimize_se3(objective, init_T, params: _lib.BfgsParams | None = None, callb
     return colmajor_to_T(out)[0], _result_dict(res)
 
 
-def estimate_pose_bfgs_on_costs(costs, init_T_camera_lidar, params: _lib.BfgsParams | None = None, callback=None):
-    """BFGS over already-built mode-B cost objects (NIDCost, one per bag; the `nid_costs` vector of :198-206)."""
+def estimate_pose_bfgs_on_costs(costs, init_T_camera_lidar, params: _lib.BfgsParams | None = None, callback=None, allreduce=None):
+    """BFGS over already-built mode-B cost objects (NIDCost, one per bag; the `nid_costs` vector of :198-206).
+    allreduce: optional callable(np.ndarray[9]) summing in place over all ranks (bags sharded, one process per GPU)."""
     L = _lib.load_library()
+
+    def _allreduce(vals, count, _user):
+        allreduce(np.ctypeslib.as_array(vals, shape=(count,)))
+
+    ar = _lib.ALLREDUCE_FN(_allreduce) if allreduce else _lib.ALLREDUCE_FN()
     handles = (C.c_void_p * len(costs))(*[c.handle for c in costs])
     p = params or default_bfgs_params()
     out = np.empty(16)
     res = _lib.BfgsResult()
-    _lib.check(L.vlcal_estimate_pose_bfgs_ctx(handles, len(costs), C.byref(p), _dp(T_to_colmajor(init_T_camera_lidar)), _pose_callback(callback), None, _dp(out), C.byref(res)))
+    _lib.check(L.vlcal_estimate_pose_bfgs_ctx(handles, len(costs), C.byref(p), _dp(T_to_colmajor(init_T_camera_lidar)), _pose_callback(callback), ar, None, _dp(out), C.byref(res)))
     return colmajor_to_T(out)[0], _result_dict(res)

@@ -122,8 +122,6 @@ class VisualCameraCalibration:
         from .cost import NIDCost
         from .culling import ViewCulling, ViewCullingParams
 
-        if self.allreduce is not None:
-            raise _lib.VlcalError(_lib.ERR_UNSUPPORTED, "the BFGS branch is single-process (the bag all-reduce exists for the Nelder-Mead path)")
         first = self.dataset[0]
         culling = ViewCulling(self.proj, (first.image.shape[1], first.image.shape[0]), ViewCullingParams(not self.params.disable_z_buffer_culling), device=self.device)
         costs = []
@@ -137,7 +135,7 @@ class VisualCameraCalibration:
                 self.params.callback(T)
 
         try:
-            T, r = bfgs.estimate_pose_bfgs_on_costs(costs, init_T_camera_lidar, self.params.bfgs_params, _cb)
+            T, r = bfgs.estimate_pose_bfgs_on_costs(costs, init_T_camera_lidar, self.params.bfgs_params, _cb, self.allreduce)
         finally:
             for c in costs:
                 c.close()

@@ -410,6 +410,8 @@ struct CtxObjective {
   vlcal_nid_ctx* const* ctxs;
   int n;
   int status;
+  vlcal_allreduce_fn allreduce;  // optional: bags sharded over ranks (one process per GPU)
+  void* allreduce_user;
 };
 
 int ctx_objective(const double x[7], double* cost, double grad7[7], void* user) {
@@ -428,6 +430,13 @@ int ctx_objective(const double x[7], double* cost, double grad7[7], void* user) 
     total += nid;
     for (int k = 0; k < 7; k++) g[k] += gb[k];
   }
+  if (o->allreduce) {  // sum_bags over all ranks: cost, 7 partials and the number of bags whose functor returned false
+    double vals[9] = {total, g[0], g[1], g[2], g[3], g[4], g[5], g[6], all_ok ? 0.0 : 1.0};
+    o->allreduce(vals, 9, o->allreduce_user);
+    total = vals[0];
+    for (int k = 0; k < 7; k++) g[k] = vals[1 + k];
+    all_ok = vals[8] == 0.0;
+  }
   *cost = total;
   for (int k = 0; k < 7; k++) grad7[k] = g[k];
   return all_ok ? 1 : 0;
@@ -435,8 +444,8 @@ int ctx_objective(const double x[7], double* cost, double grad7[7], void* user) 
 }  // namespace
 
 extern "C" int vlcal_estimate_pose_bfgs_ctx(
-  vlcal_nid_ctx* const* ctxs, int n_ctx, const vlcal_bfgs_params* params, const double init_T_camera_lidar[16], vlcal_pose_callback callback, void* user,
-  double T_out[16], vlcal_bfgs_result* result) {
+  vlcal_nid_ctx* const* ctxs, int n_ctx, const vlcal_bfgs_params* params, const double init_T_camera_lidar[16], vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce, void* user, double T_out[16], vlcal_bfgs_result* result) {
   if (!ctxs || n_ctx <= 0 || !init_T_camera_lidar || !T_out) {
     set_last_error("invalid arguments");
     return VLCAL_ERR_INVALID_ARGUMENT;
@@ -447,7 +456,7 @@ extern "C" int vlcal_estimate_pose_bfgs_ctx(
       return VLCAL_ERR_INVALID_ARGUMENT;
     }
   }
-  CtxObjective o{ctxs, n_ctx, VLCAL_OK};
+  CtxObjective o{ctxs, n_ctx, VLCAL_OK, allreduce, user};
   const int rc = vlcal_bfgs_minimize_se3(ctx_objective, &o, params, init_T_camera_lidar, callback, user, T_out, result);
   return o.status != VLCAL_OK ? o.status : rc;
 }

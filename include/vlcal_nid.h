@@ -404,13 +404,16 @@ int vlcal_bfgs_minimize_se3(
   double T_out[16],
   vlcal_bfgs_result* result);
 
-/* the inner BFGS solve over mode-B contexts (one per bag, already culled at init_T like :196-206) */
+/* the inner BFGS solve over mode-B contexts (one per bag, already culled at init_T like :196-206).
+ * allreduce (optional): bags sharded over ranks -- called once per evaluation with 9 doubles (cost, 7 partials, number of
+ * failed bags) to be summed in place over all ranks; every rank then takes identical steps. */
 int vlcal_estimate_pose_bfgs_ctx(
   vlcal_nid_ctx* const* ctxs,
   int n_ctx,
   const vlcal_bfgs_params* params,
   const double init_T_camera_lidar[16],
   vlcal_pose_callback callback,
+  vlcal_allreduce_fn allreduce,
   void* user,
   double T_out[16],
   vlcal_bfgs_result* result);

@@ -125,3 +125,59 @@ def test_registration_type_enum_and_params():
     d = bfgs.default_bfgs_params()
     assert d.max_num_iterations == 50 and d.function_tolerance == 1e-6 and d.gradient_tolerance == 1e-10 and d.parameter_tolerance == 1e-8
     assert d.max_translation_from_init == 0.2 and abs(d.max_rotation_from_init - np.deg2rad(2.0)) < 1e-15
+
+
+BFGS_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+from scipy.spatial.transform import Rotation
+sys.path.insert(0, sys.argv[1])
+import direct_visual_lidar_calibration_b200 as V
+from direct_visual_lidar_calibration_b200 import bfgs
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# bag-sharded BFGS: each rank owns one term of the objective; value, the 7 partials and the failure count are summed over
+# the ranks at every evaluation (the 9-double all-reduce of vlcal_estimate_pose_bfgs_ctx), so all ranks take the same steps.
+def make_T(rv, t):
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec(rv).as_matrix(); T[:3, 3] = t; return T
+T0 = make_T([0.2, -0.1, 0.3], [0.5, -0.2, 1.0])
+targets = [T0 @ make_T([0.01, 0.0, -0.01], [0.02, 0.01, 0.0]), T0 @ make_T([-0.005, 0.01, 0.0], [0.0, -0.02, 0.03])]
+def term(r, x):
+    qt = Rotation.from_matrix(targets[r][:3, :3]).as_quat(); tt = targets[r][:3, 3]
+    if np.dot(x[:4], qt) < 0: qt = -qt
+    e = np.concatenate([x[:4] - qt, (r + 1.0) * (x[4:] - tt)])
+    return 0.5 * float(e @ e), np.concatenate([x[:4] - qt, (r + 1.0) ** 2 * (x[4:] - tt)])
+def sharded(x):
+    c, g = term(rank, x)
+    t = torch.from_numpy(np.concatenate([[c], g, [0.0]]))
+    dist.all_reduce(t)
+    v = t.numpy()
+    return v[8] == 0.0, v[0], v[1:8]
+T, r = bfgs.minimize_se3(sharded, T0)
+out = torch.from_numpy(np.concatenate([T.reshape(-1), [r["final_cost"], r["iterations"], r["evaluations"]]]))
+gathered = [torch.zeros_like(out) for _ in range(world)]
+dist.all_gather(gathered, out)
+if rank == 0:
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "ranks diverged"
+    def joint(x):
+        cs = [term(k, x) for k in range(world)]
+        return True, sum(c for c, _ in cs), sum(g for _, g in cs)
+    T1, r1 = bfgs.minimize_se3(joint, T0)
+    assert np.allclose(T1, T, atol=1e-12) and r1["iterations"] == r["iterations"] and r["final_cost"] < r["initial_cost"]
+    print("GLOO_BFGS_OK", r["iterations"], r["final_cost"])
+dist.destroy_process_group()
+"""
+
+
+def test_bag_sharded_bfgs_over_gloo_world_size_2(tmp_path):
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "bfgs_worker.py"
+    script.write_text(BFGS_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29537", WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script), root], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GLOO_BFGS_OK" in outs[0]

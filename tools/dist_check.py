@@ -82,6 +82,36 @@ if rank == 0:
     full = IG.score_poses(rep, grid)
     print(f"POSE_SHARD_CHECK world={world} poses={len(grid)} identical={bool(np.array_equal(sharded, full, equal_nan=True))}")
     assert np.array_equal(sharded, full, equal_nan=True)
+# NID_BFGS branch, bags sharded over ranks: one 9-double all-reduce (cost, 7 partials, failed-bag count) per evaluation
+from direct_visual_lidar_calibration_b200 import bfgs as BF
+from direct_visual_lidar_calibration_b200.cost import NIDCost
+
+T0b = S.perturb(S.gt_T_camera_lidar(), (0.2, -0.2, 0.2), (0.008, -0.006, 0.005))
+culling = V.ViewCulling(cam, (bags[0]["width"], bags[0]["height"]), device=local)
+bbuf = torch.zeros(9, dtype=torch.float64, device="cuda")
+
+
+def allreduce9(vals):
+    bbuf.copy_(torch.from_numpy(vals))
+    dist.all_reduce(bbuf)
+    vals[:] = bbuf.cpu().numpy()
+
+
+def bspline_cost(b):
+    pts, ins = culling.cull(b["points"], b["intensities"], T0b)
+    return NIDCost(cam, V.VisualLiDARData(b["image"], pts, ins), 16, device=local)
+
+
+Tb, rb = BF.estimate_pose_bfgs_on_costs([bspline_cost(bags[rank])], T0b, allreduce=allreduce9)
+outb = torch.from_numpy(np.concatenate([Tb.reshape(-1), [rb["final_cost"], rb["iterations"], rb["evaluations"]]])).cuda()
+gb = [torch.zeros_like(outb) for _ in range(world)]
+dist.all_gather(gb, outb)
+if rank == 0:
+    assert all(torch.equal(g, gb[0]) for g in gb), "ranks diverged on the sharded BFGS"
+    T1b, r1b = BF.estimate_pose_bfgs_on_costs([bspline_cost(b) for b in bags], T0b)
+    close_b = bool(np.abs(T1b - Tb).max() < 1e-8 and abs(r1b["final_cost"] - rb["final_cost"]) < 1e-9)
+    print(f"BFGS_SHARD_CHECK world={world} ranks_identical=True close_to_single_gpu={close_b} iterations={rb['iterations']} evaluations={rb['evaluations']} cost {rb['initial_cost']:.9f} -> {rb['final_cost']:.9f}")
+    assert close_b and rb["final_cost"] < rb["initial_cost"]
 dist.barrier()
 px.close()
 dist.destroy_process_group()
