@@ -98,10 +98,6 @@ static dj dj_sqrt(dj f) {
   const double r = sqrt(f.a);
   return dj_chain(r, 0.5 / r, f);
 }
-static dj dj_tan_unused(dj f) {
-  const double t = tan(f.a);
-  return dj_chain(t, 1.0 + t * t, f);
-}
 static dj dj_atan(dj f) { return dj_chain(atan(f.a), 1.0 / (1.0 + f.a * f.a), f); }
 static dj dj_asin(dj f) { return dj_chain(asin(f.a), 1.0 / sqrt(1.0 - f.a * f.a), f); }
 static dj dj_log(dj f) { return dj_chain(log(f.a), 1.0 / f.a, f); }
@@ -356,7 +352,6 @@ int orc_nid_cost_bspline_grad(
   free(hist);
   free(hist_image);
   free(hist_points);
-  (void)dj_tan_unused;
   if (!isfinite(NID.a)) { /* :98-102 */
     return 0;
   }
