@@ -181,3 +181,37 @@ def test_bag_sharded_bfgs_over_gloo_world_size_2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GLOO_BFGS_OK" in outs[0]
+
+
+def test_bfgs_on_the_oracle_mode_b_objective():
+    """The whole NID_BFGS branch on the CPU: our solver driving the ORACLE's NIDCost<Jet> (value + 7 partials), on a small
+    synthetic bag.  Checks the interplay the GPU path relies on: ambient gradient -> tangent pull-back -> descent."""
+    import util as U
+    from direct_visual_lidar_calibration_b200 import synthetic as S
+    from oracle import oracle as O
+
+    bag = S.make_bag("pinhole_640x480", "frustum", 6000, config_index=12, scale=0.5)
+    cam = O.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+    T0 = S.perturb(bag["T_gt"], (0.25, -0.2, 0.2), (0.008, -0.006, 0.005))
+    fov = O.estimate_camera_fov(cam, bag["width"], bag["height"])
+    idx = O.view_cull(cam, bag["width"], bag["height"], fov, True, bag["points"], T0)  # :196 cull at the start pose
+    pts, ins = bag["points"][idx], bag["intensities"][idx]
+    evals = []
+
+    def f(x):
+        ok, nid, grad = O.nid_cost_bspline_grad(cam, bag["image"], pts, ins, 16, x)
+        evals.append(nid)
+        return ok, nid, grad
+
+    p = bfgs.default_bfgs_params()
+    p.max_num_iterations = 12
+    seen = []
+    T, r = bfgs.minimize_se3(f, T0, p, callback=lambda Tk, c: seen.append(c))
+    assert r["iterations"] >= 2 and r["final_cost"] < r["initial_cost"] - 1e-4, r
+    assert seen == sorted(seen, reverse=True) and abs(seen[-1] - r["final_cost"]) < 1e-15
+    # the reported costs are the functor's values at the reported poses
+    q = np.concatenate([Rotation.from_matrix(T[:3, :3]).as_quat(), T[:3, 3]])
+    ok, c1, _ = O.nid_cost_bspline_grad(cam, bag["image"], pts, ins, 16, q)
+    assert ok and (abs(c1 - r["final_cost"]) < 1e-9)
+    dt, dr = pose_error(T0, T)
+    assert dt <= 0.2 and dr <= np.deg2rad(2.0)
