@@ -283,3 +283,44 @@ def test_bspline_gradient_is_the_derivative_of_the_value(ref):
         b[k] -= 1e-6
         fd[k] = (ref.nid_cost_bspline(rc, img, pr["points"], pr["intensities"], 16, a)[1] - ref.nid_cost_bspline(rc, img, pr["points"], pr["intensities"], 16, b)[1]) / 2e-6
     assert np.abs(g - fd).max() < 1e-5 * max(1.0, np.abs(g).max()), (g, fd)
+
+
+def _random_camera(model, rng):
+    W, H = int(rng.integers(64, 400)), int(rng.integers(48, 300))
+    f = rng.uniform(0.4, 1.6) * W
+    intr = [f, f * rng.uniform(0.9, 1.1), W * rng.uniform(0.4, 0.6), H * rng.uniform(0.4, 0.6)]
+    if model == "plumb_bob":
+        dist = list(rng.normal(0, [0.05, 0.05, 1e-3, 1e-3, 0.02]))
+    elif model == "fisheye":
+        dist = list(rng.normal(0, [0.02, 0.01, 0.005, 0.002]))
+    elif model == "atan":
+        dist = [float(rng.choice([0.0, 1e-8, rng.uniform(0.2, 1.2)]))]  # includes the d0 < 1e-7 branch (atan.hpp:17)
+    elif model == "omnidir":
+        intr = intr + [rng.uniform(0.5, 1.5)]
+        dist = list(rng.normal(0, [0.05, 0.02, 1e-3, 1e-3]))
+    elif model == "equirectangular":
+        intr, dist = [float(W), float(H)], []
+    else:
+        dist = list(rng.normal(0, [0.05, 0.05, 1e-3, 1e-3, 0.02, 0.05, 0.03, 0.01]))
+    return intr, dist, W, H
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+def test_fuzz_random_cameras_projection_fov_nid_culling(ref, model):
+    """Random intrinsics / distortions / image sizes (the fixed presets above could hide a branch): projection, FoV, NID and
+    culling of the oracle against the reference's code, bit for bit."""
+    rng = np.random.default_rng(1000 + U.MODELS.index(model))
+    for trial in range(8):
+        intr, dist, W, H = _random_camera(model, rng)
+        oc, rc = O.create_camera(model, intr, dist), ref.Camera(model, intr, dist)
+        pts = rng.normal(size=(3000, 3)) * rng.uniform(0.05, 30.0, (3000, 1))
+        assert np.array_equal(np.array([O.project(oc, p) for p in pts]), ref.project(rc, pts), equal_nan=True), (model, trial)
+        fov = O.estimate_camera_fov(oc, W, H)
+        assert fov == ref.estimate_camera_fov(rc, W, H), (model, trial, intr, dist)
+        pr = U.random_problem(model, n=4000, seed=2000 + trial, size=(W, H))
+        Ts = U.random_poses(pr["T"], 2, seed=trial, rot_deg=4.0, trans=0.3)
+        bins = int(rng.choice([4, 16, 64]))
+        got = ref.nid_calculate(rc, pr["image"], pr["points"], pr["intensities"], bins, Ts)
+        want = np.array([O.nid_calculate(oc, pr["image"], pr["points"], pr["intensities"], bins, fov, T)[0] for T in Ts])
+        assert np.array_equal(got, want, equal_nan=True), (model, trial, got, want)
+        assert np.array_equal(O.view_cull(oc, W, H, fov, True, pr["points"], Ts[0]), ref.view_cull(rc, W, H, True, pr["points"], Ts[0]))
