@@ -154,12 +154,37 @@ def run_reference(args, rank, world):
             evals += r["num_evaluations"]
     total = sum(times)
     value = evals / total
+    # the same bounded sample through the reference's OWN visual_camera_calibration.cpp + cost_calculator_nid.cpp (oracle/_ref,
+    # compiled against stand-in third-party headers); the port above is the faster of the two and stays the headline
+    ref_build = None
+    try:
+        from oracle import reference as R
+
+        if R.available():
+            rcam = R.Camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
+            sys.stdout.flush()
+            saved = os.dup(1)
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(devnull, 1)  # the reference prints "cost:<best>" to stdout (visual_camera_calibration.cpp:115)
+            try:
+                t0 = time.perf_counter()
+                R.calibrate_nelder_mead(rcam, bags, bag["T_init"], max_outer_iterations=1, max_inner_iterations=args.ref_iterations)
+                dt = time.perf_counter() - t0
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
+                os.close(devnull)
+            per_step = evals / max(1, args.steps)  # same trajectory as the port (tests/test_reference_pin.py), hence the same count
+            ref_build = {"value": per_step / dt, "unit": UNIT, "cores": 1, "ms_per_step": 1e3 * dt,
+                         "note": "VisualCameraCalibration::calibrate (1 outer iteration) from the reference's own sources, stand-in Eigen/cv::Mat/GTSAM headers, -O2"}
+    except Exception as e:
+        ref_build = {"unavailable": repr(e)}
     sample = f"first {args.ref_iterations} Nelder-Mead iterations ({evals // max(1, args.steps)} evaluations) of the C2 inner solve per step, view culling included; serial over points like the reference"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "points": args.points, "image": "1920x1080", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "reference_build": ref_build},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
