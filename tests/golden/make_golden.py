@@ -69,6 +69,36 @@ def main():
             points=pr["points"].astype(np.float32), intensities=pr["intensities"].astype(np.float32), poses=Ts, max_fov=fov,
             nid=np.array(nids), hist=np.stack(hists).astype(np.int32), cull_indices=idx.astype(np.int32),
         )
+    # 3. mode-B fixtures (NIDCost value + gradient), FROM THE REFERENCE'S OWN FUNCTOR when oracle/_ref is available
+    #    (include/vlcal/costs/nid_cost.hpp instantiated with double and with Jets, oracle/ref_shim.cpp); the oracle must agree
+    #    bit for bit before anything is written
+    from scipy.spatial.transform import Rotation
+
+    for model in util.MODELS:
+        pr = util.random_problem(model, n=2500, seed=300 + util.MODELS.index(model), size=(160, 120) if model != "equirectangular" else (160, 80))
+        intr = [160.0, 80.0] if model == "equirectangular" else [v * 0.25 for v in pr["intrinsics"]]
+        cam = O.create_camera(model, intr, pr["distortion"])
+        Ts = util.random_poses(pr["T"], 2, seed=11)
+        tps = np.stack([np.concatenate([Rotation.from_matrix(T[:3, :3]).as_quat(), T[:3, 3]]) for T in Ts])
+        pts = pr["points"].astype(np.float32).astype(np.float64)
+        ins = pr["intensities"].astype(np.float32).astype(np.float64)
+        vals, grads = [], []
+        for tp in tps:
+            ok, nid, grad = O.nid_cost_bspline_grad(cam, pr["image"], pts, ins, 16, tp)
+            ok_v, nid_v, _ = O.nid_cost_bspline(cam, pr["image"], pts, ins, 16, tp)
+            assert ok and ok_v
+            if R.build() is not None:
+                rcam = R.Camera(model, intr, pr["distortion"])
+                ok_r, nid_r, grad_r = R.nid_cost_bspline_jet(rcam, pr["image"], pts, ins, 16, tp)
+                ok_d, nid_d = R.nid_cost_bspline(rcam, pr["image"], pts, ins, 16, tp)
+                assert ok_r and ok_d and nid_r == nid and np.array_equal(grad_r, grad) and nid_d == nid_v
+            vals.append((nid_v, nid))
+            grads.append(grad)
+        np.savez_compressed(
+            os.path.join(HERE, f"mode_b_{model}.npz"),
+            intrinsics=np.array(intr), distortion=np.array(pr["distortion"], dtype=np.float64), image=pr["image"], points=pts.astype(np.float32), intensities=ins.astype(np.float32),
+            T_params=tps, nid_double_functor=np.array([v[0] for v in vals]), nid_jet_functor=np.array([v[1] for v in vals]), grad=np.stack(grads),
+        )
     print("golden fixtures written to", HERE)
 
 

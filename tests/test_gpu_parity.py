@@ -659,3 +659,16 @@ def test_bfgs_branch_runs_on_the_gpu_cost(gpu, oracle):
     params.max_outer_iterations = 2
     T2 = calib.calibrate(T0)
     assert calib.stats["outer_iterations"] >= 1 and np.isfinite(T2).all()
+
+
+@pytest.mark.parametrize("model", util.MODELS)
+def test_mode_b_golden_fixtures(gpu, model):
+    """K2 / K3 against the committed vectors of the reference functor (tests/golden/mode_b_*.npz)."""
+    g = np.load(os.path.join(GOLDEN, f"mode_b_{model}.npz"))
+    cam = gpu.create_camera(model, g["intrinsics"], g["distortion"])
+    cost = gpu.NIDCost(cam, gpu.VisualLiDARData(g["image"], g["points"].astype(np.float64), g["intensities"].astype(np.float64)), 16)
+    ok, nid = cost.evaluate(g["T_params"])
+    assert ok.all() and np.abs(nid - g["nid_double_functor"]).max() < 1e-9
+    ok, nid, grad = cost.evaluate_with_gradient(g["T_params"])
+    assert ok.all() and np.abs(nid - g["nid_jet_functor"]).max() < 1e-9
+    assert np.abs(grad - g["grad"]).max() < 1e-8 * max(1.0, np.abs(g["grad"]).max())

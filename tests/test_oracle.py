@@ -306,3 +306,21 @@ def test_oracle_agrees_with_an_independent_numpy_restatement(oracle):
             Hr, Hs, Hrs = Hf(h_np.sum(1) / s), Hf(h_np.sum(0) / s), Hf(h_np / s)
             nid_np = (Hrs - (Hr + Hs - Hrs)) / Hrs
             assert abs(nid_np - oracle.nid_from_hist(h)[0]) < 1e-13
+
+
+def test_mode_b_golden_fixtures(oracle):
+    """Committed mode-B vectors (value of the double functor, value + 7 partials of the Jet functor; written from the
+    reference functor by tests/golden/make_golden.py).  Runs wherever the oracle builds -- no reference tree needed."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mode_b_*.npz")))
+    assert len(files) == 6
+    for path in files:
+        model = os.path.basename(path)[len("mode_b_"):-len(".npz")]
+        g = np.load(path)
+        cam = oracle.create_camera(model, g["intrinsics"], g["distortion"])
+        pts, ins = g["points"].astype(np.float64), g["intensities"].astype(np.float64)
+        for k, tp in enumerate(g["T_params"]):
+            ok, nid, grad = oracle.nid_cost_bspline_grad(cam, g["image"], pts, ins, 16, tp)
+            assert ok and nid == g["nid_jet_functor"][k] and np.array_equal(grad, g["grad"][k])
+            assert oracle.nid_cost_bspline(cam, g["image"], pts, ins, 16, tp)[1] == g["nid_double_functor"][k]

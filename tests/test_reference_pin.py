@@ -324,3 +324,21 @@ def test_fuzz_random_cameras_projection_fov_nid_culling(ref, model):
         want = np.array([O.nid_calculate(oc, pr["image"], pr["points"], pr["intensities"], bins, fov, T)[0] for T in Ts])
         assert np.array_equal(got, want, equal_nan=True), (model, trial, got, want)
         assert np.array_equal(O.view_cull(oc, W, H, fov, True, pr["points"], Ts[0]), ref.view_cull(rc, W, H, True, pr["points"], Ts[0]))
+
+
+def test_mode_b_golden_fixtures_match_reference_and_oracle(ref):
+    """tests/golden/mode_b_*.npz were written from the reference functor (make_golden.py); both the reference build and
+    the oracle must reproduce them exactly."""
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "mode_b_*.npz")))
+    assert len(files) == len(U.MODELS)
+    for path in files:
+        model = os.path.basename(path)[len("mode_b_"):-len(".npz")]
+        g = np.load(path)
+        rc, oc = ref.Camera(model, g["intrinsics"], g["distortion"]), O.create_camera(model, g["intrinsics"], g["distortion"])
+        pts, ins = g["points"].astype(np.float64), g["intensities"].astype(np.float64)
+        for k, tp in enumerate(g["T_params"]):
+            ok_r, nid_r, grad_r = ref.nid_cost_bspline_jet(rc, g["image"], pts, ins, 16, tp)
+            ok_o, nid_o, grad_o = O.nid_cost_bspline_grad(oc, g["image"], pts, ins, 16, tp)
+            assert ok_r and ok_o and nid_r == nid_o == g["nid_jet_functor"][k]
+            assert np.array_equal(grad_r, g["grad"][k]) and np.array_equal(grad_o, g["grad"][k])
+            assert ref.nid_cost_bspline(rc, g["image"], pts, ins, 16, tp)[1] == g["nid_double_functor"][k] == O.nid_cost_bspline(oc, g["image"], pts, ins, 16, tp)[1]
