@@ -421,10 +421,13 @@ int ctx_objective(const double x[7], double* cost, double grad7[7], void* user) 
   for (int b = 0; b < o->n; b++) {  // MultiNIDCost: residuals[0] += residuals[i] in bag order (:163-169)
     double nid = 0.0, gb[7];
     int32_t ok = 0;
-    const int rc = vlcal_nid_evaluate_bspline_grad(o->ctxs[b], x, 1, &nid, gb, &ok);
+    const int rc = o->status == VLCAL_OK ? vlcal_nid_evaluate_bspline_grad(o->ctxs[b], x, 1, &nid, gb, &ok) : o->status;
     if (rc != VLCAL_OK) {
+      // a local failure must still reach the collective below (the other ranks are already waiting in it): record it,
+      // report "invalid here" through the failed-bag count, and let every rank abort the solve consistently
       o->status = rc;
-      return 0;
+      all_ok = false;
+      break;
     }
     all_ok = all_ok && ok != 0;
     total += nid;
@@ -439,6 +442,7 @@ int ctx_objective(const double x[7], double* cost, double grad7[7], void* user) 
   }
   *cost = total;
   for (int k = 0; k < 7; k++) grad7[k] = g[k];
+  if (o->status != VLCAL_OK) return 0;
   return all_ok ? 1 : 0;
 }
 }  // namespace

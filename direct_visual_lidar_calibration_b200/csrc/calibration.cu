@@ -24,6 +24,11 @@ double now_ms() {
 vlcal_p2p* g_default_p2p = nullptr;  // vlcal_nid_p2p_set_default
 int g_solver_mode = 0;                // vlcal_nid_set_solver_mode: 0 auto, 1 host loop, 2 device-resident loop
 
+// the kernel sums over ranks only when a CONNECTED exchange spanning more than one rank is attached (fill_common_args)
+inline bool ctx_exchange_is_fused(const vlcal_nid_ctx* c) {
+  return c->p2p != nullptr && c->p2p->connected && c->p2p->world > 1;
+}
+
 struct PoseObjective {
   vlcal_nid_ctx* const* ctxs;
   int n_ctxs;
@@ -64,7 +69,7 @@ struct PoseObjective {
       }
     }
     // with a peer exchange attached (one bag per rank) the kernel already returned the sum over ranks
-    const bool fused = n_ctxs == 1 && ctxs[0]->p2p != nullptr;
+    const bool fused = n_ctxs == 1 && ctx_exchange_is_fused(ctxs[0]);
     if (allreduce && !fused) allreduce(partial.data(), count, user);
     for (int i = 0; i < count; i++) ys[i] = status == VLCAL_OK ? partial[i] : NAN;
   }
@@ -189,7 +194,7 @@ int run_inner_solve(
   double T_out[16], vlcal_nm_result* nm_result) {
   // one bag on this GPU, scores either local or summed in-kernel over the peer exchange: the whole solve can stay on
   // the device.  (Several local bags, or a host-side all-reduce callback, need the host between batches.)
-  const bool device_ok = n_ctxs == 1 && ctxs[0]->mode == VLCAL_NID_MODE_HISTOGRAM && ctxs[0]->max_poses >= NID_MAX_POSES && (allreduce == nullptr || ctxs[0]->p2p != nullptr) &&
+  const bool device_ok = n_ctxs == 1 && ctxs[0]->mode == VLCAL_NID_MODE_HISTOGRAM && ctxs[0]->max_poses >= NID_MAX_POSES && (allreduce == nullptr || ctx_exchange_is_fused(ctxs[0])) &&
                          params->max_inner_iterations >= 0;
   if (g_solver_mode == 2 && !device_ok) {
     set_last_error("device-resident solver loop requested but this solve needs the host between batches (several local bags / host all-reduce / bins too large)");

@@ -57,6 +57,15 @@ struct PoolBuf {
   ~PoolBuf() { MemPool::instance().device_free(device, p); }
 };
 
+// synchronises the stream when it goes out of scope (normal returns have already synchronised: this is free there)
+struct StreamGuard {
+  cudaStream_t stream;
+  ~StreamGuard() {
+    if (cudaStreamQuery(stream) == cudaErrorNotReady) cudaStreamSynchronize(stream);
+    cudaGetLastError();
+  }
+};
+
 }  // namespace vlcal
 
 using namespace vlcal;
@@ -72,7 +81,15 @@ extern "C" int vlcal_nid_evaluate_bspline(vlcal_nid_ctx* ctx, const double* T_pa
   }
   VL_CUDA(cudaSetDevice(ctx->device));
   const int bins = ctx->bins, nb = bins * bins;
+  {  // one pose's joint histogram (8 B per bin) + marginal must fit the shared memory K2 opts into
+    constexpr size_t SMEM_OPT_IN_CHECK = 100 * 1024;
+    if (static_cast<size_t>(nb) * 8 + static_cast<size_t>(bins) * 4 + 64 > SMEM_OPT_IN_CHECK) {
+      set_last_error("bins too large for the mode-B kernel's shared-memory histogram (bins <= 112)");
+      return VLCAL_ERR_UNSUPPORTED;
+    }
+  }
   PoolBuf gjoint, gpoints, counter, d_nid, d_ok, d_hist;
+  StreamGuard guard{ctx->stream};  // declared last = destroyed first: no scratch goes back to the pool while launches may still run
   VL_CUDA(gjoint.alloc(ctx->device, sizeof(unsigned long long) * NIDB_MAX_POSES * nb));
   VL_CUDA(gpoints.alloc(ctx->device, sizeof(int) * NIDB_MAX_POSES * bins));
   VL_CUDA(counter.alloc(ctx->device, sizeof(unsigned int)));
@@ -152,6 +169,7 @@ extern "C" int vlcal_nid_evaluate_bspline_grad(vlcal_nid_ctx* ctx, const double*
     return VLCAL_ERR_UNSUPPORTED;
   }
   PoolBuf gjoint, gpart, gpoints, counter, d_out;
+  StreamGuard guard{ctx->stream};
   VL_CUDA(gjoint.alloc(ctx->device, sizeof(unsigned long long) * nb));
   VL_CUDA(gpart.alloc(ctx->device, sizeof(double) * nb * 7));
   VL_CUDA(gpoints.alloc(ctx->device, sizeof(int) * bins));

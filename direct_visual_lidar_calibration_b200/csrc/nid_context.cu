@@ -15,6 +15,8 @@
 #include <cstring>
 #include <ctime>
 #include <map>
+#include <thread>
+#include <tuple>
 
 #include "fast_filter.hpp"
 #include "host_math.hpp"
@@ -126,11 +128,14 @@ DeviceImage::~DeviceImage() {
   MemPool::instance().device_free(device, d_raw);
 }
 
-// process-wide pinned staging buffer (cudaHostAlloc costs milliseconds; contexts are rebuilt every outer iteration)
+// pinned staging buffers (cudaHostAlloc costs milliseconds; contexts are rebuilt every outer iteration).  A small pool
+// rather than one buffer: the reference builds its cost objects from an OpenMP loop over bags
+// (visual_camera_calibration.cpp:107 runs calculate() that way; constructors may be called from several threads too),
+// and concurrent uploads -- to the same or to different devices -- must not serialise on one staging area.
 struct PinnedStage {
-  std::mutex mu;
   void* ptr = nullptr;
   size_t cap = 0;
+  bool busy = false;
   int reserve(size_t bytes) {
     if (bytes <= cap) return VLCAL_OK;
     MemPool::instance().pinned_free(ptr);
@@ -141,7 +146,50 @@ struct PinnedStage {
     return VLCAL_OK;
   }
 };
-static PinnedStage g_stage;
+
+class StagePool {
+public:
+  // a free stage (the one with the largest capacity, so that steady-state callers never reallocate); grows on demand
+  PinnedStage* acquire() {
+    std::lock_guard<std::mutex> lock(mu_);
+    PinnedStage* best = nullptr;
+    for (auto& s : stages_)
+      if (!s->busy && (!best || s->cap > best->cap)) best = s.get();
+    if (!best) {
+      stages_.emplace_back(new PinnedStage());
+      best = stages_.back().get();
+    }
+    best->busy = true;
+    return best;
+  }
+  void release(PinnedStage* s) {
+    std::lock_guard<std::mutex> lock(mu_);
+    s->busy = false;
+  }
+
+private:
+  std::mutex mu_;
+  std::vector<std::unique_ptr<PinnedStage>> stages_;
+};
+static StagePool g_stages;
+
+struct StageLease {
+  PinnedStage* s;
+  StageLease() : s(g_stages.acquire()) {}
+  ~StageLease() { g_stages.release(s); }
+};
+
+// threads of the copy-convert team.  NOT omp_get_max_threads(): launchers such as torch.distributed.run export
+// OMP_NUM_THREADS=1 for every rank, which silently made the upload serial (6 ms instead of 0.8 ms per 1 M points).
+// The loop is memory-bound: a dozen threads saturate it, waking every core of a 128-core host costs more than it saves.
+static int conversion_threads() {
+  static const int n = [] {
+    if (const char* e = std::getenv("VLCAL_UPLOAD_THREADS")) return std::max(1, std::min(64, std::atoi(e)));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return static_cast<int>(std::max(1u, std::min(16u, hw ? hw : 1u)));
+  }();
+  return n;
+}
 
 int upload_cloud(int device, const double* points_xyzw, const double* intensities, int64_t n, cudaStream_t stream, std::shared_ptr<DeviceCloud>* out) {
   auto cloud = std::make_shared<DeviceCloud>();
@@ -152,7 +200,8 @@ int upload_cloud(int device, const double* points_xyzw, const double* intensitie
     *out = cloud;
     return VLCAL_OK;
   }
-  std::lock_guard<std::mutex> lock(g_stage.mu);
+  StageLease lease;
+  PinnedStage& g_stage = *lease.s;
   {
     const int rc = g_stage.reserve(static_cast<size_t>(n) * 32);
     if (rc != VLCAL_OK) return rc;
@@ -161,8 +210,7 @@ int upload_cloud(int device, const double* points_xyzw, const double* intensitie
   // Convert in a few chunks so that the H2D copy of chunk c overlaps the conversion of chunk c+1.
   float4* stage = static_cast<float4*>(g_stage.ptr);
   int lossless = 1, w_is_one = 1;
-  // memory-bound copy-convert: a dozen threads saturate it; waking every core of a 128-core host costs more than it saves
-  const int conv_threads = std::max(1, std::min(16, omp_get_max_threads()));
+  const int conv_threads = conversion_threads();
   VL_CUDA(MemPool::instance().device_alloc(device, static_cast<size_t>(n) * 16, &cloud->d_points));
   constexpr int64_t CHUNK = 1 << 18;
   for (int64_t c0 = 0; c0 < n; c0 += CHUNK) {
@@ -265,7 +313,8 @@ struct LaunchGeom {
 };
 
 static std::mutex g_geom_mu;
-static std::map<std::pair<const void*, size_t>, int> g_occupancy_cache;
+// keyed by device too: function attributes (the dynamic shared memory opt-in) and occupancy are per device / context
+static std::map<std::tuple<int, const void*, size_t>, int> g_occupancy_cache;
 
 static int hist_copies_cap() {
   // warp-private copies buy nothing measurable over a couple of shared ones (profiles/r01_microbench.log: 1.32 vs 1.35 T
@@ -278,7 +327,7 @@ static int hist_copies_cap() {
   return cap;
 }
 
-static int launch_geometry(NidKernel kernel, int n_poses, int nb, int bins, LaunchGeom* g) {
+static int launch_geometry(int device, NidKernel kernel, int n_poses, int nb, int bins, LaunchGeom* g) {
   const size_t per_copy = static_cast<size_t>(n_poses) * nb * sizeof(int);
   int copies = static_cast<int>(NID_SMEM_TARGET / per_copy);
   copies = std::max(1, std::min(copies, hist_copies_cap()));
@@ -290,7 +339,7 @@ static int launch_geometry(NidKernel kernel, int n_poses, int nb, int bins, Laun
   g->finalize_split = nb <= 1024;
   if (g->finalize_split) g->smem = std::max(g->smem, split_need);
   std::lock_guard<std::mutex> lock(g_geom_mu);
-  const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), g->smem);
+  const auto key = std::make_tuple(device, reinterpret_cast<const void*>(kernel), g->smem);
   auto it = g_occupancy_cache.find(key);
   if (it == g_occupancy_cache.end()) {
     VL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(NID_SMEM_OPT_IN)));
@@ -480,7 +529,7 @@ constexpr int PROFILE_STRIDE = 4;
 static int launch_one(vlcal_nid_ctx* ctx, NidKernel kernel, NidArgs& a, int geometry_poses, int profile_poses) {
   LaunchGeom g{1, 0, 1, 0};
   {
-    const int rc = launch_geometry(kernel, geometry_poses, a.nb, a.bins, &g);
+    const int rc = launch_geometry(ctx->device, kernel, geometry_poses, a.nb, a.bins, &g);
     if (rc != VLCAL_OK) return rc;
   }
   a.copies = g.copies;
