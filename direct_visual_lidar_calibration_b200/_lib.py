@@ -127,6 +127,9 @@ def load_library():
     L.vlcal_nid_evaluate.argtypes = [vp, dp, C.c_int, dp, vp]
     L.vlcal_nid_evaluate_async.argtypes = [vp, dp, C.c_int]
     L.vlcal_nid_wait.argtypes = [vp, dp, vp]
+    L.vlcal_nid_score_poses.argtypes = [C.POINTER(vp), C.c_int, dp, C.c_int, dp]
+    L.vlcal_nid_get_profile_passes.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.vlcal_nid_debug_solve_stamps.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), ip]
     L.vlcal_nid_evaluate_bspline.argtypes = [vp, dp, C.c_int, dp, vp, vp]
     L.vlcal_nid_evaluate_bspline_grad.argtypes = [vp, dp, C.c_int, dp, dp, vp]
     L.vlcal_nid_num_points.argtypes = [vp]
@@ -176,7 +179,7 @@ def check(rc: int):
 
 
 def set_solver_mode(mode: int):
-    """0 auto, 1 host loop, 2 device-resident loop (see include/vlcal_nid.h)."""
+    """0 auto (persistent kernel where possible), 1 host loop, 2 device-resident loop, 3 persistent kernel (see include/vlcal_nid.h)."""
     check(load_library().vlcal_nid_set_solver_mode(int(mode)))
 
 

@@ -137,9 +137,22 @@ class CostCalculatorNID:
         _lib.check(self._L.vlcal_nid_reset_profile(self._ctx))
 
     def profile(self):
-        launches, poses, ms = C.c_int64(), C.c_int64(), C.c_double()
+        launches, poses, ms, passes = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
         _lib.check(self._L.vlcal_nid_get_profile(self._ctx, C.byref(launches), C.byref(ms), C.byref(poses)))
-        return {"kernel_launches": launches.value, "kernel_ms_total": ms.value, "poses_total": poses.value}
+        _lib.check(self._L.vlcal_nid_get_profile_passes(self._ctx, C.byref(passes)))
+        return {"kernel_launches": launches.value, "kernel_ms_total": ms.value, "poses_total": poses.value, "passes": passes.value}
+
+    def arm_solve_stamps(self, capacity: int = 64):
+        """The next persistent solve on this cost object records %globaltimer stamps for its first `capacity` batches."""
+        _lib.check(self._L.vlcal_nid_debug_solve_stamps(self._ctx, int(capacity), None, None))
+
+    def solve_stamps(self, capacity: int = 64):
+        """(n, 8) uint64 nanosecond stamps per batch: block 0 enters, main loop done, merged + arrived, finalizer saw all
+        blocks, score published, block 0 saw all scores, next poses ready, unused."""
+        buf = (C.c_uint64 * (8 * capacity))()
+        n = C.c_int()
+        _lib.check(self._L.vlcal_nid_debug_solve_stamps(self._ctx, int(capacity), buf, C.byref(n)))
+        return np.ctypeslib.as_array(buf).reshape(capacity, 8)[: n.value].copy()
 
     def close(self):
         if self._ctx:
@@ -151,6 +164,17 @@ class CostCalculatorNID:
             self.close()
         except Exception:
             pass
+
+
+def score_poses(costs, Ts) -> np.ndarray:
+    """sum over the cost objects (bags) of calculate(T) for every pose of a list of any length, in ONE persistent launch
+    (the objective of visual_camera_calibration.cpp:105-110 over a pose grid)."""
+    Tc = T_to_colmajor(Ts)
+    P = Tc.shape[0]
+    out = np.empty(P)
+    handles = (C.c_void_p * len(costs))(*[c.handle for c in costs])
+    _lib.check(_lib.load_library().vlcal_nid_score_poses(handles, len(costs), _dp(Tc), P, _dp(out)))
+    return out
 
 
 class NIDCost:

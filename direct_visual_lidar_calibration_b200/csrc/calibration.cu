@@ -192,8 +192,24 @@ int run_inner_solve_device(
 int run_inner_solve(
   vlcal_nid_ctx* const* ctxs, int n_ctxs, const vlcal_calib_params* params, const double init_T[16], vlcal_pose_callback callback, vlcal_allreduce_fn allreduce, void* user,
   double T_out[16], vlcal_nm_result* nm_result) {
-  // one bag on this GPU, scores either local or summed in-kernel over the peer exchange: the whole solve can stay on
-  // the device.  (Several local bags, or a host-side all-reduce callback, need the host between batches.)
+  // Persistent cooperative kernel (nid_persistent.cuh; default): the whole solve is ONE launch -- candidates scored,
+  // summed over bags and ranks, and the Nelder-Mead machine stepped inside the kernel.  Needs what pk_supported checks
+  // (float4 clouds, lean classifier, bins <= 32, one camera / image size / device) and no host-side all-reduce callback
+  // (a connected peer exchange is summed in-kernel instead).
+  bool same_px = true;
+  for (int i = 1; i < n_ctxs; i++) same_px = same_px && ctxs[i]->p2p == ctxs[0]->p2p;
+  const bool px_fused = n_ctxs >= 1 && ctx_exchange_is_fused(ctxs[0]);
+  const bool pk_ok = n_ctxs >= 1 && params->max_inner_iterations >= 0 && same_px && (allreduce == nullptr || px_fused) && pk_supported(ctxs, n_ctxs);
+  if (g_solver_mode == 3 && !pk_ok) {
+    set_last_error("persistent solve requested but these contexts need the host loop (double-layout cloud / bins > 32 / camera without the lean classifier / host all-reduce / mixed image sizes)");
+    return VLCAL_ERR_UNSUPPORTED;
+  }
+  if (pk_ok && (g_solver_mode == 0 || g_solver_mode == 3)) {
+    return pk_solve(ctxs, n_ctxs, params, init_T, callback, user, T_out, nm_result);
+  }
+  // one bag on this GPU, scores either local or summed in-kernel over the peer exchange: the round-1 device-resident loop
+  // (one launch per batch, machine stepped by the finalizing block).  (Several local bags, or a host-side all-reduce
+  // callback, need the host between batches.)
   const bool device_ok = n_ctxs == 1 && ctxs[0]->mode == VLCAL_NID_MODE_HISTOGRAM && ctxs[0]->max_poses >= NID_MAX_POSES && (allreduce == nullptr || ctx_exchange_is_fused(ctxs[0])) &&
                          params->max_inner_iterations >= 0;
   if (g_solver_mode == 2 && !device_ok) {
@@ -202,6 +218,11 @@ int run_inner_solve(
   }
   if (device_ok && g_solver_mode == 2) {
     return run_inner_solve_device(ctxs[0], params, init_T, callback, user, T_out, nm_result);
+  }
+  if (n_ctxs > 1 && px_fused) {
+    // the round-1 kernels exchange one bag per rank; with several local bags only the persistent kernel sums in-kernel
+    set_last_error("several local bags with an attached peer exchange need the persistent solve (solver mode 0 / 3)");
+    return VLCAL_ERR_UNSUPPORTED;
   }
   PoseObjective obj;
   obj.ctxs = ctxs, obj.n_ctxs = n_ctxs, obj.init_T = init_T, obj.callback = callback, obj.allreduce = allreduce, obj.user = user;
@@ -282,8 +303,13 @@ int inner_solve_resident(
     rc = nid_ctx_create(device, VLCAL_NID_MODE_HISTOGRAM, cam, bags[b].image, culled, params->nid_bins, bags[b].max_fov, &ctx);  // :82-84
     if (rc != VLCAL_OK) return rc;
     ctx->profiling = profiling != 0;
-    if (g_default_p2p && bags.size() == 1 && g_default_p2p->device == device) ctx->p2p = g_default_p2p;
     ctxs.v.push_back(ctx);
+  }
+  if (g_default_p2p && g_default_p2p->device == device) {
+    // one bag per rank: every path can sum in-kernel; several local bags: only the persistent solve does
+    const bool pk_path = (g_solver_mode == 0 || g_solver_mode == 3) && pk_supported(ctxs.v.data(), static_cast<int>(ctxs.v.size()));
+    if (bags.size() == 1 || pk_path)
+      for (auto* c : ctxs.v) c->p2p = g_default_p2p;
   }
   const double t_solve0 = now_ms();
   if (stats) stats->cull_ms += t_solve0 - t_cull0;
@@ -329,8 +355,8 @@ int check_common(const vlcal_calib_params* params, const double* init_T, double*
 extern "C" {
 
 int vlcal_nid_set_solver_mode(int mode) {
-  if (mode < 0 || mode > 2) {
-    set_last_error("solver mode must be 0 (auto), 1 (host loop) or 2 (device-resident loop)");
+  if (mode < 0 || mode > 3) {
+    set_last_error("solver mode must be 0 (auto), 1 (host loop), 2 (device-resident loop) or 3 (persistent kernel)");
     return VLCAL_ERR_INVALID_ARGUMENT;
   }
   g_solver_mode = mode;

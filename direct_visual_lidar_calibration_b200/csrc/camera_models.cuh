@@ -205,12 +205,34 @@ struct FastCam {
 
 constexpr float F32_U = 5.9604644775390625e-08f;  // 2^-24, unit roundoff of binary32
 
+// approximate reciprocal / reciprocal square root: MUFU.RCP / MUFU.RSQ on the device (<= 1 ulp, which the bounds assume);
+// the host build (tests/cpp_lean_check.cu runs the filter on the CPU) uses the correctly rounded operations
+#if defined(__CUDA_ARCH__)
+// bare MUFU.RCP / MUFU.RSQ (flush-to-zero forms: __fdividef(1, x) and rsqrtf(x) wrap the MUFU in 4-5 instructions of
+// denormal scaling; a denormal argument flushes to 0 -> inf, which every caller treats as "uncertain")
+__device__ __forceinline__ float vl_rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float vl_rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+#define VL_RCPF(x) vl_rcp_approx(x)
+#define VL_RSQRTF(x) vl_rsqrt_approx(x)
+#else
+#define VL_RCPF(x) (1.0f / (x))
+#define VL_RSQRTF(x) (1.0f / sqrtf(x))
+#endif
+
 // fp32 projection + per-point error bounds; returns false if this point must take the exact path regardless
 template <int MODEL>
-__device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float pcy, float pcz, float nrm, float delta, float& u, float& v, float& Eu, float& Ev) {
+VL_HD bool project_fast(const FastCam& c, float pcx, float pcy, float pcz, float nrm, float delta, float& u, float& v, float& Eu, float& Ev) {
   if constexpr (MODEL == CAM_PLUMB_BOB || MODEL == CAM_RATIONAL_POLYNOMIAL) {
     // enabled only when cos_fov >= 0.05: a certain FoV pass then implies pcz >= 0.05*|pc| > 0
-    const float inv = __fdividef(1.0f, pcz);  // MUFU.RCP, <= 1 ulp
+    const float inv = VL_RCPF(pcz);  // MUFU.RCP, <= 1 ulp
     const float x = pcx * inv, y = pcy * inv;
     const float x2 = x * x, y2 = y * y, xy = x * y;
     const float r2 = x2 + y2;
@@ -232,8 +254,8 @@ __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float 
       // lower bound of the true denominator on the segment between the fp32 and the exact normalised point
       const float den_lb = den - fmaf(qd_a, 2.0f * (r2b - r2), (8.0f * F32_U) * den_a);
       ok = den_lb > 0.1f;  // far from the reference's 1e-8 guard (rational_polynomial.hpp:33) and from a pole
-      const float dinv = __fdividef(1.0f, den_lb);
-      rc = num * __fdividef(1.0f, den);
+      const float dinv = VL_RCPF(den_lb);
+      rc = num * VL_RCPF(den);
       RC = num_a * dinv;
       Q = (qn_a + RC * qd_a) * dinv;
       m_extra = RC * den_a * dinv;
@@ -262,9 +284,9 @@ __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float 
   } else if constexpr (MODEL == CAM_EQUIRECTANGULAR) {
     // u = W (0.5 + atan2(x, z) / 2pi),  v = H (0.5 + asin(y/|p|) / pi)   (equirectangular.hpp:21-27)
     const float rxz2 = fmaf(pcx, pcx, pcz * pcz);
-    const float inv_rxz = rsqrtf(rxz2);
+    const float inv_rxz = VL_RSQRTF(rxz2);
     const float rxz = rxz2 * inv_rxz;
-    const float inv_n = __fdividef(1.0f, nrm);
+    const float inv_n = VL_RCPF(nrm);
     const float lon = atan2f(pcx, pcz);
     const float asn = asinf(pcy * inv_n);
     u = c.fx * fmaf(lon, 0.15915494309189535f, 0.5f);  // c.fx = W, c.fy = H
@@ -280,7 +302,7 @@ __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float 
   } else if constexpr (MODEL == CAM_FISHEYE) {
     // theta = atan2(r, |z|), theta_d = theta (1 + k1 th^2 + ... + k4 th^8), uv = f theta_d (x, y)/r + c  (fisheye.hpp:15-35)
     const float r2 = fmaf(pcx, pcx, pcy * pcy);
-    const float inv_r = rsqrtf(r2);
+    const float inv_r = VL_RSQRTF(r2);
     const float r = r2 * inv_r;
     const float theta = atan2f(r, fabsf(pcz));
     const float t2 = theta * theta;
@@ -292,16 +314,16 @@ __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float 
     const float pm = fmaf(t2b, fmaf(t2b, fmaf(t2b, fmaf(t2b, c.a4, c.a3), c.a2), c.a1), 1.0f);                             // >= |poly|
     const float pd = fmaf(t2b, fmaf(t2b, fmaf(t2b, fmaf(t2b, 9.0f * c.a4, 7.0f * c.a3), 5.0f * c.a2), 3.0f * c.a1), 1.0f);  // >= |d theta_d / d theta|
     // |d(theta_d x / r)| <= (2 pd + 8 pm) delta / |p| + (9 pd + 19 pm) u     (DESIGN.md / fast_filter.hpp)
-    const float e = fmaf(fmaf(2.0f, pd, 8.0f * pm), delta * __fdividef(1.0f, nrm), fmaf(9.0f, pd, 19.0f * pm) * F32_U);
+    const float e = fmaf(fmaf(2.0f, pd, 8.0f * pm), delta * VL_RCPF(nrm), fmaf(9.0f, pd, 19.0f * pm) * F32_U);
     Eu = fmaf(c.sfx, e, c.cu);
     Ev = fmaf(c.sfy, e, c.cv);
     return (r > 8.0f * delta) && (nrm > 40.0f * delta);  // r -> 0 is the reference's NaN corner (theta_d / r)
   } else if constexpr (MODEL == CAM_OMNIDIR) {
     // s = p/|p|, m = (sx, sy)/(sz + xi), plumb-bob style distortion with (k1, k2, p1, p2)   (omnidir.hpp:25-40)
-    const float inv_n = __fdividef(1.0f, nrm);
+    const float inv_n = VL_RCPF(nrm);
     const float sx = pcx * inv_n, sy = pcy * inv_n, sz = pcz * inv_n;
     const float D = sz + c.xi;
-    const float inv_d = __fdividef(1.0f, D);
+    const float inv_d = VL_RCPF(D);
     const float x = sx * inv_d, y = sy * inv_d;
     const float x2 = x * x, y2 = y * y, xy = x * y;
     const float r2 = x2 + y2;
@@ -323,10 +345,10 @@ __device__ __forceinline__ bool project_fast(const FastCam& c, float pcx, float 
     return (D > 0.1f) && (nrm > 40.0f * delta);
   } else {  // CAM_ATAN
     // pt = (x, y)/z; r < 1e-3 or d0 < 1e-7: identity, else pt * atan(r * 2 tan(d0/2)) / (d0 r)   (atan.hpp:14-38)
-    const float inv = __fdividef(1.0f, pcz);
+    const float inv = VL_RCPF(pcz);
     const float x = pcx * inv, y = pcy * inv;
     const float r2 = fmaf(x, x, y * y);
-    const float inv_r = rsqrtf(r2);
+    const float inv_r = VL_RSQRTF(r2);
     const float r = r2 * inv_r;
     const float mh = fmaf(0.5f, r2, 0.5f) * 1.001f;
     const float rho = delta * inv;

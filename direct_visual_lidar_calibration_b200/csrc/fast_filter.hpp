@@ -19,6 +19,7 @@
 #include <cmath>
 
 #include "camera_models.cuh"
+#include "lean_filter.cuh"
 
 namespace vlcal {
 
@@ -115,6 +116,57 @@ inline FastCam make_fast_cam(const CameraParams& cam, int width, int height, dou
     f.enabled = 1;
   }
   return f;
+}
+
+// constants of the lean classifier (lean_filter.cuh) from the validated round-1 constants `f` = make_fast_cam(...).
+// Every quantity is an upper bound of the round-1 one on the set of points that can be accepted, rounded outward.
+inline LeanCam make_lean_cam(const CameraParams& cam, const FastCam& f, int width, int height, double max_fov) {
+  constexpr double U = 5.9604644775390625e-08;
+  LeanCam c{};
+  c.enabled = 0;
+  if (!f.enabled) return c;
+  // magic-constant rounding needs |u'| < 2^22 wherever a verdict is accepted, and 32-bit pixel indices
+  if (width < 1 || height < 1 || width >= (1 << 21) || height >= (1 << 21) || static_cast<long long>(width) * height >= (1LL << 31)) return c;
+  auto up = [](double v) { return std::nextafter(static_cast<float>(v), INFINITY); };
+  auto dn = [](double v) { return std::nextafter(static_cast<float>(v), -INFINITY); };
+  c.t_lo = LEAN_MAGIC - 1.0f;
+  c.t_hi = LEAN_MAGIC + static_cast<float>(width - 1);
+  c.s_lo = LEAN_MAGIC - 1.0f;
+  c.s_hi = LEAN_MAGIC + static_cast<float>(height - 1);
+  c.idx_bias = static_cast<int>(static_cast<unsigned int>(LEAN_MAGIC_BITS) * static_cast<unsigned int>(width + 1));  // modulo 2^32, like the kernel's IMAD
+  c.hx0 = dn(0.5 - static_cast<double>(f.cu));
+  c.hy0 = dn(0.5 - static_cast<double>(f.cv));
+  c.nsfx = -f.sfx;
+  c.nsfy = -f.sfy;
+  if (cam.model == CAM_PLUMB_BOB) {
+    const double cs = std::cos(max_fov);
+    if (!(cs >= 0.05)) return c;  // make_fast_cam already requires it
+    const double T2 = 1.0 / (cs * cs) - 1.0;  // tan^2(max_fov)
+    const double sT = std::sqrt(T2);
+    // a point that certainly passes the FoV test has r2 < T2, hence r2b = fma(r2, 1.001, 1e-6) <= R2B
+    const double R2B = (1.001 * T2 + 1e-6) * (1.0 + 1e-6);
+    const double l0 = f.l0, l1 = f.l1, l2 = f.l2, l3 = f.l3;
+    const double L_at = l0 + R2B * (l1 + R2B * (l2 + R2B * l3));
+    const double S = R2B > 0.0 ? (L_at - l0) / R2B : 0.0;  // chord slope of the convex L over [0, R2B]
+    c.l0c = up((l0 + 1e-6 * S) * (1.0 + 8 * U));
+    c.lsc = up(1.001 * S * (1.0 + 8 * U));
+    const double M16_at = f.m0 + R2B * (f.m1 + R2B * (f.m2 + R2B * (f.m3 + R2B * f.m4)));
+    c.m16c = up(M16_at * (1.0 + 8 * U));
+    const double MH = 0.5 * R2B + 0.5;  // mh = (1 + r2b) / 2 <= MH
+    c.C1 = up(1.0 + MH);
+    c.C2 = up(4.0 * U * MH);
+    c.C1x3 = up(3.0 * (1.0 + MH));
+    c.C2x3 = up(12.0 * U * MH);
+    c.T2lo = dn(T2 * (1.0 - 1e-6));
+    c.T2hi = up(T2 * (1.0 + 2e-6));
+    c.K3 = up(3.0 * (1.0 + sT) * (1.0 + sT));
+    c.cxh = static_cast<float>(cam.intr[2] - 0.5);
+    c.cyh = static_cast<float>(cam.intr[3] - 0.5);
+    // the chord / maxima must be finite and the certain zone non-empty somewhere
+    if (!std::isfinite(c.l0c) || !std::isfinite(c.lsc) || !std::isfinite(c.m16c) || !std::isfinite(c.K3) || !(c.hx0 > 0.0f) || !(c.hy0 > 0.0f)) return c;
+  }
+  c.enabled = 1;
+  return c;
 }
 
 }  // namespace vlcal

@@ -22,6 +22,7 @@
 #include "host_math.hpp"
 #include "mem_pool.hpp"
 #include "nid_kernels.cuh"
+#include "nid_persistent.cuh"
 
 namespace vlcal {
 
@@ -399,6 +400,7 @@ int nid_ctx_create(
   ctx->max_fov = max_fov;
   ctx->cos_fov = std::cos(max_fov);  // cost_calculator_nid.cpp:32
   ctx->fast = make_fast_cam(cam, image->width, image->height, max_fov);
+  ctx->lean = make_lean_cam(cam, ctx->fast, image->width, image->height, max_fov);
   VL_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
   VL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 
@@ -592,6 +594,7 @@ int nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_colmajor, int n_poses
     const int rc = launch_one(ctx, kernel, a, pc, pc);
     if (rc != VLCAL_OK) return rc;
     ctx->launches++;
+    ctx->passes++;
     ctx->poses_total += pc;
   }
   ctx->seq += 1;
@@ -653,6 +656,7 @@ int nid_account_device_steps(vlcal_nid_ctx* ctx, int enqueued, int worked, int p
     ctx->events_used = first;
   }
   ctx->launches += worked;
+  ctx->passes += worked;
   ctx->poses_total += poses;
   return VLCAL_OK;
 }
@@ -873,9 +877,42 @@ int vlcal_nid_evaluate(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_p
     set_last_error("invalid arguments");
     return VLCAL_ERR_INVALID_ARGUMENT;
   }
+  // default: the persistent kernel in pose-list mode (one launch for any number of poses); contexts it does not cover
+  // (double layout, bins > 32, cameras without the lean classifier, an attached peer exchange) take the round-1 kernels
+  if (!ctx->p2p && ctx->variant != 4 && pk_supported(&ctx, 1)) {
+    if (!nid_out) {
+      set_last_error("nid_out is NULL");
+      return VLCAL_ERR_INVALID_ARGUMENT;
+    }
+    return pk_score_poses(&ctx, 1, T_camera_lidar, n_poses, nid_out, hist_out);
+  }
   const int rc = nid_evaluate_async(ctx, T_camera_lidar, n_poses, hist_out != nullptr);
   if (rc != VLCAL_OK) return rc;
   return nid_wait(ctx, nid_out, hist_out);
+}
+
+int vlcal_nid_score_poses(vlcal_nid_ctx* const* ctxs, int n_ctxs, const double* T_camera_lidar, int n_poses, double* nid_out) {
+  if (!ctxs || n_ctxs <= 0 || !T_camera_lidar || n_poses <= 0 || !nid_out) {
+    set_last_error("invalid arguments");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  for (int i = 0; i < n_ctxs; i++) {
+    if (!ctxs[i]) {
+      set_last_error("NULL context");
+      return VLCAL_ERR_INVALID_ARGUMENT;
+    }
+  }
+  if (pk_supported(ctxs, n_ctxs)) return pk_score_poses(ctxs, n_ctxs, T_camera_lidar, n_poses, nid_out, nullptr);
+  // contexts the persistent kernel does not cover: one batched evaluation per context, summed in context order
+  std::vector<double> part(n_poses);
+  for (int p = 0; p < n_poses; p++) nid_out[p] = 0.0;
+  for (int i = 0; i < n_ctxs; i++) {
+    int rc = nid_evaluate_async(ctxs[i], T_camera_lidar, n_poses, false);
+    if (rc == VLCAL_OK) rc = nid_wait(ctxs[i], part.data(), nullptr);
+    if (rc != VLCAL_OK) return rc;
+    for (int p = 0; p < n_poses; p++) nid_out[p] += part[p];
+  }
+  return VLCAL_OK;
 }
 
 int64_t vlcal_nid_num_points(const vlcal_nid_ctx* ctx) {
@@ -913,6 +950,26 @@ int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* 
   return VLCAL_OK;
 }
 
+int vlcal_nid_get_profile_passes(vlcal_nid_ctx* ctx, int64_t* passes) {
+  if (!ctx || !passes) return VLCAL_ERR_INVALID_ARGUMENT;
+  *passes = ctx->passes;
+  return VLCAL_OK;
+}
+
+int vlcal_nid_debug_solve_stamps(vlcal_nid_ctx* ctx, int capacity, uint64_t* stamps_out, int* n_out) {
+  if (!ctx || capacity < 0) return VLCAL_ERR_INVALID_ARGUMENT;
+  if (!stamps_out) {  // arm: the next persistent solve on this context records `capacity` batches
+    ctx->pk_stamps_cap = capacity;
+    ctx->pk_stamps.clear();
+    return VLCAL_OK;
+  }
+  const int have = static_cast<int>(ctx->pk_stamps.size() / PK_STAMP_SLOTS);
+  const int n = std::min(capacity, have);
+  for (int i = 0; i < n * PK_STAMP_SLOTS; i++) stamps_out[i] = ctx->pk_stamps[i];
+  if (n_out) *n_out = n;
+  return VLCAL_OK;
+}
+
 int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
   if (!ctx) return VLCAL_ERR_INVALID_ARGUMENT;
   VL_CUDA(cudaSetDevice(ctx->device));
@@ -922,12 +979,13 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
   ctx->timed_launches = 0;
   ctx->launch_counter = 0;
   ctx->poses_total = 0;
+  ctx->passes = 0;
   ctx->kernel_ms_accum = 0.0;
   return VLCAL_OK;
 }
 
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 3) return VLCAL_ERR_INVALID_ARGUMENT;
+  if (!ctx || variant < 0 || variant > 4) return VLCAL_ERR_INVALID_ARGUMENT;
   ctx->variant = variant;
   return VLCAL_OK;
 }
@@ -968,6 +1026,9 @@ int vlcal_nid_debug_timeline(vlcal_nid_ctx* ctx, const double* T_camera_lidar, i
   return rc;
 }
 
+// layout of the cudaIpc-shared allocation of a rank: [P2PMailbox (round-1 kernels) | pad | PkMailbox (persistent kernel)]
+static constexpr size_t P2P_PK_OFFSET = (sizeof(P2PMailbox) + 255) & ~static_cast<size_t>(255);
+
 int vlcal_nid_p2p_create(int device, int rank, int world, vlcal_p2p** out, void* ipc_handle_out) {
   if (!out || !ipc_handle_out || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) {
     set_last_error("invalid arguments (1 <= world <= 8)");
@@ -981,8 +1042,8 @@ int vlcal_nid_p2p_create(int device, int rank, int world, vlcal_p2p** out, void*
   VL_CUDA(cudaSetDevice(device));
   std::unique_ptr<vlcal_p2p> p(new vlcal_p2p());
   p->device = device, p->rank = rank, p->world = world;
-  VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->local), sizeof(P2PMailbox)));  // own allocation: cudaIpc shares whole allocations
-  VL_CUDA(cudaMemset(p->local, 0, sizeof(P2PMailbox)));
+  VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->local), P2P_PK_OFFSET + sizeof(PkMailbox)));  // own allocation: cudaIpc shares whole allocations
+  VL_CUDA(cudaMemset(p->local, 0, P2P_PK_OFFSET + sizeof(PkMailbox)));
   VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_counter), sizeof(unsigned long long)));
   VL_CUDA(cudaMemset(p->d_counter, 0, sizeof(unsigned long long)));
   VL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p->h_error), sizeof(int), cudaHostAllocDefault));
@@ -992,6 +1053,7 @@ int vlcal_nid_p2p_create(int device, int rank, int world, vlcal_p2p** out, void*
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   std::memcpy(ipc_handle_out, &h, sizeof(h));
   p->peers[rank] = p->local;
+  p->pk_peers[rank] = reinterpret_cast<PkMailbox*>(reinterpret_cast<char*>(p->local) + P2P_PK_OFFSET);
   *out = p.release();
   return VLCAL_OK;
 }
@@ -1009,6 +1071,7 @@ int vlcal_nid_p2p_connect(vlcal_p2p* p, const void* all_handles) {
     void* ptr = nullptr;
     VL_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     p->peers[r] = static_cast<P2PMailbox*>(ptr);
+    p->pk_peers[r] = reinterpret_cast<PkMailbox*>(static_cast<char*>(ptr) + P2P_PK_OFFSET);
   }
   p->connected = true;
   return VLCAL_OK;
@@ -1086,6 +1149,8 @@ int vlcal_nid_debug_filter_check(vlcal_nid_ctx* ctx, const double* T_camera_lida
   VL_CUDA(MemPool::instance().device_alloc(ctx->device, 4 * sizeof(unsigned long long), reinterpret_cast<void**>(&d_dbg)));
   VL_CUDA(cudaMemsetAsync(d_dbg, 0, 4 * sizeof(unsigned long long), ctx->stream));
   NidKernel kernel = pick_kernel(ctx->cam.model, true, 2);
+  // contexts that run the lean classifier (persistent kernel) are checked with it; variant 4 checks the round-1 filter
+  const bool lean = ctx->lean.enabled && ctx->variant != 4;
   for (int p0 = 0; p0 < n_poses; p0 += NID_MAX_POSES) {
     const int pc = std::min(NID_MAX_POSES, n_poses - p0);
     NidArgs a;
@@ -1110,7 +1175,18 @@ int vlcal_nid_debug_filter_check(vlcal_nid_ctx* ctx, const double* T_camera_lida
     a.dbg = d_dbg;
     const long long want_blocks = (a.n + NID_THREADS - 1) / NID_THREADS;
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(want_blocks, static_cast<long long>(ctx->num_sms) * 4)));
-    kernel<<<grid, NID_THREADS, 0, ctx->stream>>>(a);
+    if (lean) {
+      switch (ctx->cam.model) {
+        case CAM_PLUMB_BOB: nid_lean_verify_kernel<CAM_PLUMB_BOB><<<grid, NID_THREADS, 0, ctx->stream>>>(a, ctx->lean); break;
+        case CAM_FISHEYE: nid_lean_verify_kernel<CAM_FISHEYE><<<grid, NID_THREADS, 0, ctx->stream>>>(a, ctx->lean); break;
+        case CAM_ATAN: nid_lean_verify_kernel<CAM_ATAN><<<grid, NID_THREADS, 0, ctx->stream>>>(a, ctx->lean); break;
+        case CAM_OMNIDIR: nid_lean_verify_kernel<CAM_OMNIDIR><<<grid, NID_THREADS, 0, ctx->stream>>>(a, ctx->lean); break;
+        case CAM_EQUIRECTANGULAR: nid_lean_verify_kernel<CAM_EQUIRECTANGULAR><<<grid, NID_THREADS, 0, ctx->stream>>>(a, ctx->lean); break;
+        default: nid_lean_verify_kernel<CAM_RATIONAL_POLYNOMIAL><<<grid, NID_THREADS, 0, ctx->stream>>>(a, ctx->lean); break;
+      }
+    } else {
+      kernel<<<grid, NID_THREADS, 0, ctx->stream>>>(a);
+    }
     VL_CUDA(cudaGetLastError());
   }
   unsigned long long h[4];

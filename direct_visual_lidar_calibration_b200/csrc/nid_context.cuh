@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "camera_models.cuh"
+#include "lean_filter.cuh"
 #include "vlcal_nid.h"
 
 namespace vlcal {
@@ -63,6 +64,7 @@ struct ProfileEvents {
 
 namespace vlcal {
 struct P2PMailbox;
+struct PkMailbox;
 }
 
 // one per process: this rank's mailbox + the mapped mailboxes of the peers (vlcal_nid_p2p_*)
@@ -70,6 +72,8 @@ struct vlcal_p2p {
   int device = 0, rank = 0, world = 1;
   vlcal::P2PMailbox* local = nullptr;
   vlcal::P2PMailbox* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // the persistent kernel's mailbox (nid_persistent.cuh) lives in the same cudaIpc-shared allocation, behind the first one
+  vlcal::PkMailbox* pk_peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool connected = false;
   unsigned long long* d_counter = nullptr;  // device word: exchanges done (advanced by the kernels)
   int* h_error = nullptr;  // pinned + mapped
@@ -84,6 +88,7 @@ struct vlcal_nid_ctx {
   double cos_fov = 0.0;
   vlcal::CameraParams cam{};
   vlcal::FastCam fast{};
+  vlcal::LeanCam lean{};  // lean classifier constants (lean_filter.cuh); lean.enabled == 0: round-1 kernels only
   std::shared_ptr<vlcal::DeviceCloud> cloud;
   std::shared_ptr<vlcal::DeviceImage> image;
   uint8_t* d_bin_image = nullptr;
@@ -116,7 +121,11 @@ struct vlcal_nid_ctx {
   int64_t timed_launches = 0;  // launches bracketed by events (profiling samples 1 launch in PROFILE_STRIDE)
   int64_t launch_counter = 0;
   int64_t poses_total = 0;
+  int64_t passes = 0;  // passes over the cloud (a persistent launch carries one per Nelder-Mead batch / pose chunk)
   double kernel_ms_accum = 0.0;
+  // debug: globaltimer stamps of the persistent kernel's batches (vlcal_nid_debug_solve_stamps)
+  int pk_stamps_cap = 0;
+  std::vector<unsigned long long> pk_stamps;
 
   ~vlcal_nid_ctx();
 };
@@ -131,4 +140,14 @@ struct NmDevice;
 int nid_enqueue_device_steps(vlcal_nid_ctx* ctx, NmDevice* d_nm, int count);
 // after the stream was synchronised: account the first `worked` launches of the last enqueue in the profile
 int nid_account_device_steps(vlcal_nid_ctx* ctx, int enqueued, int worked, int poses);
+
+// persistent cooperative kernel (nid_persistent.cu): can these contexts (bags of one camera on one device) run on it?
+bool pk_supported(vlcal_nid_ctx* const* ctxs, int n_ctxs);
+// a whole Nelder-Mead inner solve (visual_camera_calibration.cpp:103-129) in one launch; sums over the peer exchange
+// attached to ctxs[0] when it spans several ranks
+int pk_solve(
+  vlcal_nid_ctx* const* ctxs, int n_ctxs, const vlcal_calib_params* params, const double init_T[16], vlcal_pose_callback callback, void* user, double T_out[16],
+  vlcal_nm_result* nm_result);
+// sum over the contexts of calculate(T_p) for a pose list of any length, one launch (hist_out: bag 0's joint histograms)
+int pk_score_poses(vlcal_nid_ctx* const* ctxs, int n_ctxs, const double* T_colmajor, int n_poses, double* nid_out, int32_t* hist_out);
 }  // namespace vlcal

@@ -1,0 +1,897 @@
+// nid_persistent.cuh -- K1p: the NID hot path as ONE persistent cooperative kernel per inner solve (sm_100a).
+//
+// Replaces, for a whole dfo::NelderMead<6> inner solve (reference: include/dfo/nelder_mead.hpp:32-101 driving
+// CostCalculatorNID::calculate, src/vlcal/calib/cost_calculator_nid.cpp:21-67, through the objective of
+// src/vlcal/calib/visual_camera_calibration.cpp:103-119), the round-1 scheme "one launch per Nelder-Mead batch + host
+// round trip" (36 us kernel of which ~16 us were launch ramp / serial tail, + ~5 us host gap, x 115 batches at C2).
+//
+// One launch, grid = every co-resident block of the GPU (cooperative launch, so the waits below cannot deadlock), each
+// warp owning a fixed contiguous slice of the cloud for the whole solve.  Per Nelder-Mead batch:
+//   (A) every block scores the batch's P <= 8 candidate poses on its slice -- lean fp32 filter (lean_filter.cuh) with the
+//       exact fp64 recheck for the ~3 % of point-poses near a decision edge (exact_classify.cuh), privatised shared-memory
+//       histograms, predicated red.shared -- and merges its non-zero bins into the global accumulators (red.global);
+//   (B) one block per (bag, pose) waits for the bag's blocks (arrival counter), reduces the accumulator to the NID score
+//       (:54-64; same canonical summation order as nid_finalize, so scores are a function of the histogram alone) and
+//       stores it, as two tagged 8-byte words, into the mailbox of EVERY rank (NVLink peer stores when world > 1);
+//   (C) every block of every rank waits for the world x bags x P words, adds them in (rank, bag) order -- the joint
+//       objective sum_bags NID (:105-110), bit-identical everywhere -- and then steps the Nelder-Mead state machine
+//       REDUNDANTLY in its own shared memory (warp-parallel over the simplex coordinates, nm_warp_step below; same
+//       operations in the same order as NmMachine::step) and computes the next candidates' poses T = init_T * Expmap(x)
+//       (:104), one lane per candidate.  No broadcast of poses, no host, no launch.
+// The same kernel in pose-list mode (no step (C): the next 8 poses come from a device array) serves batched evaluation
+// (vlcal_nid_evaluate) and the pose-grid search (vlcal_nid_score_poses): one launch for any number of poses.
+//
+// Several bags per GPU: the grid is partitioned over the bags in proportion to their sizes (one tail for all bags).
+#pragma once
+
+#include <cstdint>
+
+#include "exact_classify.cuh"
+#include "lean_filter.cuh"
+#include "nid_kernels.cuh"
+
+namespace vlcal {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_WARPS = PK_THREADS / 32;
+constexpr int PK_MAX_POSES = 8;
+constexpr int PK_MAX_BAGS = 8;
+constexpr int PK_MAX_WORDS = 256;  // world x bags x 8 score words per batch, one polling thread each
+constexpr int PK_QUEUE = 64;
+constexpr int PK_MAX_BINS = 32;    // nb <= 1024: the finalizing block keeps its share of the joint histogram in registers
+constexpr int PK_STAMP_SLOTS = 8;
+#ifndef PK_MIN_BLOCKS
+#define PK_MIN_BLOCKS 3  // blocks per SM the register allocation must allow (<= 85 registers per thread)
+#endif
+
+// score exchange: every double travels as two 8-byte words {32 data bits | 32-bit sequence tag} (an aligned 8-byte store
+// is never torn, so the data is its own arrival flag).  w[slot][(rank * n_bags + bag) * 8 + pose][lo, hi]
+struct PkMailbox {
+  unsigned long long w[2][PK_MAX_WORDS][2];
+};
+
+struct PkBag {
+  const float4* points;
+  const uint8_t* bin_image;
+  unsigned int n;
+  int block_begin, block_count;  // blocks [block_begin, block_begin + block_count) of the grid work on this bag
+};
+
+// Nelder-Mead solve: initial state in device memory (every block copies it into its shared memory once) ...
+struct PkSolve {
+  NmMachine nm;  // after NmMachine::begin on the host: first batch pending
+  double init_T[16];
+};
+// ... and the outcome in MAPPED PINNED HOST memory, written by block 0 (no device-to-host copy, the host polls done_host)
+struct PkResult {
+  NmMachine nm;                   // final state (result_x, result_y, converged, counters)
+  unsigned long long batches;     // Nelder-Mead batches executed
+  unsigned long long poses;       // poses scored (speculative ones included)
+  int trace_count;                // reference-order evaluations written to the trace (may exceed the capacity: truncated)
+  int pad_;
+};
+
+struct PkArgs {
+  // camera + image geometry (shared by all bags of the launch: one camera, equal image sizes)
+  int width, height, bins, nb;
+  double cos_fov;
+  CameraParams cam;
+  FastCam fast;
+  LeanCam lean;
+  int n_bags;
+  PkBag bag[PK_MAX_BAGS];
+  int copies;  // shared-memory histogram copies per block
+  // work source
+  const PkSolve* solve;      // Nelder-Mead mode when non-null
+  PkResult* result_host;     // Nelder-Mead mode: outcome (mapped pinned host memory)
+  double* trace_host;        // [trace_cap][NM_MAX_N + 1] evaluations (x, y) in the reference's order, for the callback replay
+  int trace_cap;
+  const double* poses_in;    // pose-list mode: [n_total][12] row-major 3x4 [R|t]
+  int n_total;
+  double* scores_out;        // pose-list mode: [n_total] (sum over bags of this launch)
+  int* hist_out;             // optional [n_total][nb] (bag 0 only)
+  // synchronisation scratch (zero on entry)
+  int* ghist;                // [2][n_bags][8][nb]
+  unsigned int* arrive;      // [2][PK_MAX_BAGS]
+  unsigned int* fin_done;    // [2]
+  unsigned int* abort_flag;  // set by any block that timed out: everybody leaves
+  PkMailbox* box[P2P_MAX_RANKS];  // box[r]: rank r's mailbox as mapped here (self included; world == 1: local scratch)
+  int world, rank;
+  unsigned long long* seq_counter;  // persistent exchange counter (device word of the peer exchange; local scratch otherwise)
+  unsigned long long timeout_ns;
+  int* error_host;                  // mapped host word: 1 = wait timed out
+  unsigned long long* done_host;    // mapped host word: receives done_seq when the results are visible
+  unsigned long long done_seq;
+  unsigned long long* stamps;       // optional [cap][PK_STAMP_SLOTS] globaltimer stamps per batch
+  int stamps_cap;
+};
+
+struct PkShared {
+  NmMachine nm;
+  double init_T[16];
+  double pose64[PK_MAX_POSES][12];
+  float4 pose32[PK_MAX_POSES][4];  // rows: [R00 R01 R02 t0] [R10 R11 R12 t1] [R20 R21 R22 t2] [max|t| 0 0 0]
+  double ys[PK_MAX_POSES];
+  double parts[PK_MAX_WORDS];
+  float tmax;
+  int n_poses;
+  int wait_failed;
+  int trace_count;
+  unsigned long long poses_scored;
+  unsigned long long seq_base;
+  int s_cnt[PK_WARPS];
+  unsigned int q_idx[PK_WARPS][PK_QUEUE];
+  unsigned char q_pose[PK_WARPS][PK_QUEUE];
+};
+
+// ---- small PTX helpers ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// histogram increment, two forms (A/B measured on B200, profiles/):
+//   ATOM == 0: `if (counted) atomicAdd(p, 1)` -- ptxas emits BSSY / BRA / ATOMS.POPC.INC / BSYNC (lanes of a warp that hit
+//              the same bin are merged by the hardware; predication is not available for this form, hence the branch);
+//   ATOM == 1: unconditional red.shared.add of a 0 / 1 register -- one ATOMS.ADD, no branch, same-bin lanes serialise.
+__device__ __forceinline__ void red_shared_add(unsigned int smem_addr, int inc) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr), "r"(inc) : "memory");
+}
+__device__ __forceinline__ void red_shared_inc(unsigned int smem_addr) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_addr) : "memory");
+}
+
+// 1-byte read-only gather under a predicate; -1 when off (the sign doubles as the "counted" flag one pose later)
+__device__ __forceinline__ int ldg_u8_or_neg(bool pred, const uint8_t* p) {
+  int v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tmov.u32 %0, -1;\n\t@q ld.global.nc.u8 %0, [%2];\n\t}" : "=r"(v) : "r"(static_cast<int>(pred)), "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ int ldg_u8_or_zero(bool pred, const uint8_t* p) {
+  int v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tmov.u32 %0, 0;\n\t@q ld.global.nc.u8 %0, [%2];\n\t}" : "=r"(v) : "r"(static_cast<int>(pred)), "l"(p));
+  return v;
+}
+
+// ---- warp-parallel Nelder-Mead step --------------------------------------------------------------------------------
+// NmMachine::step / loop_top (nm_machine.cuh) executed by one warp on a machine that lives in shared memory: lane d owns
+// column d of the simplex (d = 0 the values, d = 1..n the coordinates).  Every element sees the same operations in the
+// same order as in the serial code (the serial loops run over independent columns), so the state is bit-identical; only
+// the sort permutation and the scalar decisions are computed redundantly by every lane.
+
+__device__ __forceinline__ void nm_warp_observe(NmMachine& s, int lane, const double* vertex, double y) {
+  const int k = s.n_obs;
+  if (lane >= 1 && lane <= s.n) s.obs_x[k][lane - 1] = vertex[lane];
+  __syncwarp();
+  if (lane == 0) {
+    s.obs_y[k] = y;
+    s.n_obs = k + 1;
+    s.num_evaluations++;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void nm_warp_finish(NmMachine& s, int lane) {
+  if (lane >= 1 && lane <= s.n) s.result_x[lane - 1] = s.x[0][lane];  // :99
+  if (lane == 0) {
+    s.result_y = s.x[0][0];  // :100
+    s.n_cand = 0;
+    s.phase = 3;
+  }
+  __syncwarp();
+}
+
+static __device__ void nm_warp_loop_top(NmMachine& s, int lane) {
+  constexpr int M = NM_MAX_N + 1;
+  const int n = s.n, m = n + 1;
+  if (s.it >= s.params.max_iterations) {
+    nm_warp_finish(s, lane);
+    return;
+  }
+  __syncwarp();
+  if (lane == 0) s.num_iterations = s.it;  // :50
+  // :51 std::sort = libstdc++ insertion sort on the values; the permutation is computed by every lane in registers
+  double val[M];
+  int ord[M];
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+    val[i] = i < m ? s.x[i][0] : 0.0;
+    ord[i] = i;
+  }
+#pragma unroll
+  for (int i = 1; i < M; i++) {
+    if (i < m) {
+      const double v = val[i];
+      const int o = ord[i];
+      // unguarded linear insert: walk left while v < element; the first branch (v < *first) moves to the front
+      bool cont = true;
+      int cnt = 0;
+#pragma unroll
+      for (int k = M - 1; k >= 0; k--) {
+        if (k < i) {
+          cont = cont && (v < val[k]);
+          cnt += cont ? 1 : 0;
+        }
+      }
+      const int pos = (v < val[0]) ? 0 : i - cnt;
+#pragma unroll
+      for (int k = M - 1; k >= 1; k--) {
+        if (k <= i && k > pos) {
+          val[k] = val[k - 1];
+          ord[k] = ord[k - 1];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < M; k++) {
+        if (k <= i && k == pos) {
+          val[k] = v;
+          ord[k] = o;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  const bool mine = lane < m;
+  {
+    double tmp[M];
+#pragma unroll
+    for (int k = 0; k < M; k++) tmp[k] = (mine && k < m) ? s.x[ord[k]][lane] : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < M; k++)
+      if (mine && k < m) s.x[k][lane] = tmp[k];
+  }
+  __syncwarp();
+  // :52-55, :105-113 convergence: sum over the coordinates of sum_k (x_k - mean)^2
+  double var = 0.0;
+  if (mine) {
+    xd sum(0.0);
+    for (int k = 0; k < m; k++) sum = sum + xd(s.x[k][lane]);
+    const xd mean = sum / xd(static_cast<double>(m));
+    xd acc(0.0);
+    for (int k = 0; k < m; k++) {
+      const xd e = xd(s.x[k][lane]) - mean;
+      acc = acc + e * e;
+    }
+    var = acc.v;
+  }
+  xd total(0.0);
+  for (int d = 1; d < m; d++) total = total + xd(__shfl_sync(0xffffffffu, var, d));
+  if (total.v < s.params.convergence_var_thresh) {
+    if (lane == 0) s.converged = 1;
+    __syncwarp();
+    nm_warp_finish(s, lane);
+    return;
+  }
+  // :57, :60, :66, :75  xo, xr, xe, xc
+  if (mine) {
+    xd sum(0.0);
+    for (int k = 0; k < n; k++) sum = sum + xd(s.x[k][lane]);
+    const xd xo = sum / xd(static_cast<double>(n));
+    const xd diff = xo - xd(s.x[n][lane]);
+    s.cand[0][lane] = xo.v;
+    s.cand[1][lane] = (xo + xd(s.params.alpha) * diff).v;
+    s.cand[2][lane] = (xo + xd(s.params.gamma) * diff).v;
+    s.cand[3][lane] = (xo + xd(s.params.rho) * diff).v;
+  }
+  if (lane == 0) {
+    s.n_cand = 4;
+    s.phase = 1;
+  }
+  __syncwarp();
+}
+
+// consume the scores ys[0..n_cand) of the pending batch (one warp, all 32 lanes call)
+static __device__ __noinline__ void nm_warp_step(NmMachine& s, const double* ys, int lane) {
+  const int n = s.n, m = n + 1;
+  const int phase = s.phase;
+  const bool mine = lane < m;
+  __syncwarp();
+  if (lane == 0) {
+    s.n_obs = 0;
+    s.num_batches++;
+    s.num_evaluations_computed += s.n_cand;
+  }
+  __syncwarp();
+  if (phase == 0) {
+    for (int k = 0; k < m; k++) {
+      if (mine) s.x[k][lane] = lane == 0 ? ys[k] : s.cand[k][lane];
+      __syncwarp();
+      nm_warp_observe(s, lane, s.x[k], ys[k]);
+    }
+    nm_warp_loop_top(s, lane);
+  } else if (phase == 1) {
+    const double f0 = s.x[0][0], fn1 = s.x[n - 1][0], fn = s.x[n][0];
+    const double y0 = ys[0], y1 = ys[1], y2 = ys[2], y3 = ys[3];
+    __syncwarp();
+    if (lane == 0) {
+      s.cand[0][0] = y0;
+      s.cand[1][0] = y1;
+    }
+    __syncwarp();
+    nm_warp_observe(s, lane, s.cand[0], y0);  // :58 evaluated, never used in a decision
+    nm_warp_observe(s, lane, s.cand[1], y1);  // :61
+    bool shrink = false;
+    if (f0 <= y1 && y1 < fn1) {  // :63-64
+      if (mine) s.x[n][lane] = s.cand[1][lane];
+    } else if (y1 < f0) {  // :65-73 expansion
+      if (lane == 0) s.cand[2][0] = y2;
+      __syncwarp();
+      nm_warp_observe(s, lane, s.cand[2], y2);
+      const int pick = (y2 < y1) ? 2 : 1;
+      if (mine) s.x[n][lane] = s.cand[pick][lane];
+    } else {  // :74-86
+      if (lane == 0) s.cand[3][0] = y3;
+      __syncwarp();
+      nm_warp_observe(s, lane, s.cand[3], y3);
+      if (y3 < fn) {
+        if (mine) s.x[n][lane] = s.cand[3][lane];
+      } else {
+        shrink = true;
+        if (mine) {
+          const xd x0(s.x[0][lane]);
+          for (int j = 1; j < m; j++) {
+            const double v = (x0 + xd(s.params.rho) * (xd(s.x[j][lane]) - x0)).v;  // :82 (rho, not sigma)
+            s.x[j][lane] = v;
+            s.cand[j - 1][lane] = v;
+          }
+        }
+        if (lane == 0) {
+          s.n_cand = n;
+          s.phase = 2;
+        }
+      }
+    }
+    __syncwarp();
+    if (!shrink) {
+      if (lane == 0) s.it++;
+      __syncwarp();
+      nm_warp_loop_top(s, lane);
+    }
+  } else if (phase == 2) {
+    for (int j = 1; j < m; j++) {
+      if (lane == 0) s.x[j][0] = ys[j - 1];
+      __syncwarp();
+      nm_warp_observe(s, lane, s.x[j], ys[j - 1]);
+    }
+    if (lane == 0) s.it++;
+    __syncwarp();
+    nm_warp_loop_top(s, lane);
+  }
+  __syncwarp();
+}
+
+// T = init_T * Expmap(x) of candidate k (visual_camera_calibration.cpp:104) -> shared pose slots
+static __device__ __noinline__ void pk_pose_of_candidate(PkShared& sh, int k) {
+  double E[16], T[16];
+  se3_expmap_gtsam_hd(&sh.nm.cand[k][1], E);
+  isometry_mul_hd(sh.init_T, E, T);
+  double tmax = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) sh.pose64[k][4 * r + c] = T[r + 4 * c];
+    sh.pose32[k][r] = make_float4(static_cast<float>(T[r]), static_cast<float>(T[r + 4]), static_cast<float>(T[r + 8]), static_cast<float>(T[r + 12]));
+    tmax = fmax(tmax, fabs(T[r + 12]));
+  }
+  sh.pose32[k][3] = make_float4(nextafterf(static_cast<float>(tmax), INFINITY), 0.f, 0.f, 0.f);  // max|t| rounded up
+}
+
+// pose-list mode: pose k of the chunk from its row-major 3x4 doubles
+__device__ __forceinline__ void pk_pose_from_list(PkShared& sh, int k, const double* __restrict__ T) {
+  double tmax = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) sh.pose64[k][4 * r + c] = T[4 * r + c];
+    sh.pose32[k][r] = make_float4(static_cast<float>(T[4 * r]), static_cast<float>(T[4 * r + 1]), static_cast<float>(T[4 * r + 2]), static_cast<float>(T[4 * r + 3]));
+    tmax = fmax(tmax, fabs(T[4 * r + 3]));
+  }
+  sh.pose32[k][3] = make_float4(nextafterf(static_cast<float>(tmax), INFINITY), 0.f, 0.f, 0.f);
+}
+
+// ---- block-uniform waits with a timeout ------------------------------------------------------------------------------
+
+// thread 0 spins until *counter >= expected; returns false (for every thread) if the launch is being aborted
+__device__ __forceinline__ bool pk_wait_counter(const PkArgs& a, PkShared& sh, const unsigned int* counter, unsigned int expected) {
+  if (threadIdx.x == 0) {
+    int failed = 0;
+    const unsigned long long t0 = global_ns();
+    unsigned int spins = 0;
+    while (ld_acquire_u32(counter) < expected) {
+      if ((++spins & 255u) == 0) {
+        if (ld_acquire_u32(a.abort_flag) != 0u) {
+          failed = 1;
+          break;
+        }
+        if (global_ns() - t0 > a.timeout_ns) {
+          atomicExch(a.abort_flag, 1u);
+          if (a.error_host) *reinterpret_cast<volatile int*>(a.error_host) = 1;
+          failed = 1;
+          break;
+        }
+      }
+    }
+    sh.wait_failed = failed;
+  }
+  __syncthreads();
+  const bool ok = sh.wait_failed == 0;
+  __syncthreads();
+  return ok;
+}
+
+// ---- the NID of one accumulated joint histogram, by a whole block (cost_calculator_nid.cpp:54-64) -----------------------
+// Same arithmetic and the same canonical summation order as nid_finalize (nid_kernels.cuh): staged p*log(p + 1e-6) terms,
+// lane l of warp 0 adds terms l, l+32, ... in ascending order, then a fixed xor tree -- a function of the histogram alone.
+// g: this (bag, pose)'s accumulator [nb]; zeroed again on the way.  scratch: >= nb + 2*bins doubles + 2*bins ints.
+constexpr int PK_FIN_CH = (PK_MAX_BINS * PK_MAX_BINS + PK_THREADS - 1) / PK_THREADS;  // joint bins per thread
+
+static __device__ __noinline__ double pk_block_nid(PkShared& sh, int* __restrict__ g, int nb, int bins, int* __restrict__ hist_out, int* scratch) {
+  double* s_term = reinterpret_cast<double*>(scratch);  // [nb]
+  double* s_mterm = s_term + nb;                        // [2*bins]
+  int* s_marg = reinterpret_cast<int*>(s_mterm + 2 * bins);  // [2*bins]: image marginal, then lidar marginal
+  __shared__ double s_nid;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < 2 * bins; i += PK_THREADS) s_marg[i] = 0;
+  __syncthreads();
+  int c[PK_FIN_CH];
+  int part = 0;
+#pragma unroll
+  for (int m = 0; m < PK_FIN_CH; m++) {
+    const int k = m * PK_THREADS + t;
+    c[m] = k < nb ? __ldcg(g + k) : 0;
+  }
+#pragma unroll
+  for (int m = 0; m < PK_FIN_CH; m++) {
+    const int k = m * PK_THREADS + t;
+    if (c[m]) {
+      atomicAdd(&s_marg[k % bins], c[m]);         // hist_image[image_bin]   (:50)
+      atomicAdd(&s_marg[bins + k / bins], c[m]);  // hist_points[lidar_bin]  (:51)
+      part += c[m];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) sh.s_cnt[warp] = part;
+  __syncthreads();
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < PK_WARPS; w++) total += sh.s_cnt[w];
+  const double sum = static_cast<double>(total);  // :54 sum = hist_image.sum()
+#pragma unroll
+  for (int m = 0; m < PK_FIN_CH; m++) {
+    const int k = m * PK_THREADS + t;
+    if (k < nb) {
+      const double pr = static_cast<double>(c[m]) / sum;
+      s_term[k] = pr * log_pos_normal(pr + 1e-6);  // :59-61
+      if (hist_out) hist_out[k] = c[m];
+      if (c[m]) g[k] = 0;
+    }
+  }
+  for (int f = t; f < 2 * bins; f += PK_THREADS) {
+    const double pm = static_cast<double>(s_marg[f]) / sum;
+    s_mterm[f] = pm * log_pos_normal(pm + 1e-6);
+  }
+  __threadfence();  // the zeroed accumulator must be visible before anybody can see the score
+  __syncthreads();
+  if (warp == 0) {
+    double t_rs = 0.0, t_r = 0.0, t_s = 0.0;
+    for (int k = lane; k < nb; k += 32) t_rs += s_term[k];
+    for (int k = lane; k < bins; k += 32) {
+      t_r += s_mterm[k];
+      t_s += s_mterm[bins + k];
+    }
+    const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);
+    if (lane == 0) {
+      const double MI = Hr + Hs - Hrs;  // :63
+      s_nid = (Hrs - MI) / Hrs;         // :64 (NaN when there are no inliers, as in the reference)
+    }
+  }
+  __syncthreads();
+  return s_nid;
+}
+
+// ---- hot loop -----------------------------------------------------------------------------------------------------------
+
+struct PkWarp {
+  unsigned int hist_addr;  // shared-memory byte address of this warp's histogram copy [P][nb]
+  unsigned int* q_idx;
+  unsigned char* q_pose;
+  int qn;
+  int lane;
+  unsigned int lt_mask;
+};
+
+// the per-bag pointers in registers (PkArgs::bag[] is indexed by a runtime bag number: every use would be an indexed LDC)
+struct PkBagRegs {
+  const float4* points;
+  const uint8_t* bin_image;
+};
+
+template <int MODEL>
+__device__ __noinline__ void pk_drain32(const PkArgs& a, const PkShared& sh, const PkBagRegs& B, PkWarp& w, int first, int count) {
+  if (w.lane < count) {  // one deferred (point, pose) per lane, exact path
+    const unsigned int i = w.q_idx[first + w.lane];
+    const int p = w.q_pose[first + w.lane];
+    const float4 q = __ldg(B.points + i);
+    const int pix = exact_pixel_hd<MODEL>(a.cam, a.cos_fov, a.width, a.height, sh.pose64[p], q.x, q.y, q.z);
+    if (pix >= 0) {
+      const int ib = __ldg(B.bin_image + pix);  // :43,:46 via the pre-binned image
+      const unsigned int addr = w.hist_addr + 4u * static_cast<unsigned int>(p * a.nb + ib + lidar_bin_of(q.w, a.bins) * a.bins);
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");  // :49 hist(image_bin, lidar_bin)++
+    }
+  }
+}
+
+// one tile = 32*K consecutive points starting at `tile`, swept over the P poses of the batch; the image-bin gathers of
+// pose p stay in flight while pose p+1 is classified and are consumed by the histogram increments one iteration later.
+// PARTIAL: the tile may reach past `end` (only the single-row tiles at the end of a warp's slice).
+template <int MODEL, int K, bool PARTIAL, int ATOM>
+__device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, const PkBagRegs& B, int n_poses, PkWarp& w, unsigned int tile, unsigned int end, const float4 (&q)[K]) {
+  float px[K], py[K], pz[K], dl[K];
+  unsigned int lb[K];
+  const float tmax = sh.tmax;
+  const bool valid0 = !PARTIAL || (tile + w.lane < end);  // PARTIAL tiles have K == 1
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    px[j] = q[j].x, py[j] = q[j].y, pz[j] = q[j].z;
+    dl[j] = (5.25f * F32_U) * (fabsf(q[j].x) + fabsf(q[j].y) + fabsf(q[j].z) + tmax);
+    lb[j] = w.hist_addr + 4u * static_cast<unsigned int>(lidar_bin_of(q[j].w, a.bins) * a.bins);
+  }
+  int pend_bin[K];  // image bin of the previous pose's verdict, -1 = not counted
+  int pend_inc[K];  // ATOM == 1: 0 / 1
+#pragma unroll
+  for (int j = 0; j < K; j++) pend_bin[j] = -1, pend_inc[j] = 0;
+  unsigned int pend_off = 0;
+  for (int p = 0; p <= n_poses; p++) {
+    bool acc[K], unc[K];
+    int pix[K];
+    bool any_unc = false;
+    if (p < n_poses) {
+      const float4 r0 = sh.pose32[p][0], r1 = sh.pose32[p][1], r2 = sh.pose32[p][2];
+      const float Pm[12] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, r1.w, r2.w};
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const LeanVerdict v = classify_lean<MODEL>(a.fast, a.lean, a.width, Pm, px[j], py[j], pz[j], dl[j]);
+        acc[j] = PARTIAL ? (v.accept & valid0) : v.accept;
+        unc[j] = PARTIAL ? (v.uncertain & valid0) : v.uncertain;
+        pix[j] = v.idx;
+        any_unc = any_unc | unc[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; j++) {  // :49 hist(image_bin, lidar_bin)++ for the previous pose
+      if constexpr (ATOM == 0) {
+        if (pend_bin[j] >= 0) red_shared_inc(lb[j] + pend_off + 4u * static_cast<unsigned int>(pend_bin[j]));
+      } else {
+        red_shared_add(lb[j] + pend_off + 4u * static_cast<unsigned int>(pend_bin[j]), pend_inc[j]);
+      }
+    }
+    if (p < n_poses) {
+      pend_off = 4u * static_cast<unsigned int>(p * a.nb);
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        if constexpr (ATOM == 0) {
+          pend_bin[j] = ldg_u8_or_neg(acc[j], B.bin_image + pix[j]);
+        } else {
+          pend_bin[j] = ldg_u8_or_zero(acc[j], B.bin_image + pix[j]);
+          pend_inc[j] = acc[j] ? 1 : 0;
+        }
+      }
+      if (__any_sync(0xffffffffu, any_unc)) {  // some lane deferred a point: queue it for the exact path
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          const unsigned int m = __ballot_sync(0xffffffffu, unc[j]);
+          if (m) {
+            if (unc[j]) {
+              const int pos = w.qn + __popc(m & w.lt_mask);
+              w.q_idx[pos] = tile + j * 32 + w.lane;
+              w.q_pose[pos] = static_cast<unsigned char>(p);
+            }
+            w.qn += __popc(m);
+            __syncwarp();
+            if (w.qn >= 32) {
+              pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
+              w.qn -= 32;
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void pk_load_tile(const float4* __restrict__ pts, unsigned int tile, unsigned int end, int lane, float4 (&q)[K]) {
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const unsigned int i = tile + j * 32 + lane;
+    q[j] = make_float4(0.f, 0.f, -1.f, 0.f);
+    if (i < end) q[j] = __ldg(pts + i);
+  }
+}
+
+__device__ __forceinline__ void pk_stamp(const PkArgs& a, unsigned long long batch, int slot) {
+  if (a.stamps && batch < static_cast<unsigned long long>(a.stamps_cap)) a.stamps[batch * PK_STAMP_SLOTS + slot] = global_ns();
+}
+
+// stamps per batch: 0 block 0 enters the batch, 1 block 0 main loop done, 2 block 0 merged + arrived,
+//                   3 finalizer of item 0: all blocks arrived, 4 finalizer of item 0: score published,
+//                   5 block 0: all scores seen, 6 block 0: next poses ready
+template <int MODEL, int K, int ATOM>
+__global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kernel(const __grid_constant__ PkArgs a) {
+  extern __shared__ int smem_hist[];
+  __shared__ PkShared sh;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool solve_mode = a.solve != nullptr;
+
+  // block -> bag, warp -> fixed slice of the bag's cloud
+  int bag = 0;
+  while (bag + 1 < a.n_bags && static_cast<int>(blockIdx.x) >= a.bag[bag + 1].block_begin) bag++;
+  const PkBag& Bc = a.bag[bag];
+  PkBagRegs B;
+  B.points = Bc.points;
+  B.bin_image = Bc.bin_image;
+  const unsigned int bag_n = Bc.n, bag_block_begin = static_cast<unsigned int>(Bc.block_begin), bag_block_count = static_cast<unsigned int>(Bc.block_count);
+  const unsigned int warps_total = bag_block_count * PK_WARPS;
+  const unsigned int warp_global = (blockIdx.x - bag_block_begin) * PK_WARPS + warp;
+  const unsigned int chunk = ((bag_n + warps_total - 1) / warps_total + 31u) & ~31u;
+  const unsigned long long lo = static_cast<unsigned long long>(warp_global) * chunk;
+  const bool has_work = lo < bag_n;
+  const unsigned int end = has_work ? static_cast<unsigned int>(min(static_cast<unsigned long long>(bag_n), lo + chunk)) : 0u;
+  const unsigned int begin = static_cast<unsigned int>(has_work ? lo : 0ull);
+
+  PkWarp w;
+  w.lane = lane;
+  w.lt_mask = (1u << lane) - 1u;
+  w.q_idx = sh.q_idx[warp];
+  w.q_pose = sh.q_pose[warp];
+  w.qn = 0;
+  const unsigned int smem_base = static_cast<unsigned int>(__cvta_generic_to_shared(smem_hist));
+  const int n_items_per_batch = a.n_bags * PK_MAX_POSES;
+  const int fin_stride = max(1, static_cast<int>(gridDim.x) / n_items_per_batch);
+
+  // ---- first batch ----
+  if (solve_mode) {
+    static_assert(sizeof(NmMachine) % 8 == 0, "NmMachine is copied as 8-byte words");
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&a.solve->nm);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.nm);
+    for (int i = t; i < static_cast<int>(sizeof(NmMachine) / 8); i += PK_THREADS) dst[i] = src[i];
+    if (t < 16) sh.init_T[t] = a.solve->init_T[t];
+    __syncthreads();
+    if (t < sh.nm.n_cand) pk_pose_of_candidate(sh, t);
+    if (t == 0) sh.n_poses = sh.nm.n_cand;
+  } else {
+    const int pc = min(PK_MAX_POSES, a.n_total);
+    if (t < pc) pk_pose_from_list(sh, t, a.poses_in + 12 * static_cast<size_t>(t));
+    if (t == 0) sh.n_poses = pc;
+  }
+  if (t == 0) {
+    sh.seq_base = *a.seq_counter;
+    sh.trace_count = 0;
+    sh.poses_scored = 0ull;
+  }
+  __syncthreads();
+
+  for (unsigned long long batch = 0;; batch++) {
+    const int n_poses = sh.n_poses;
+    if (n_poses == 0) break;
+    const int buf = static_cast<int>(batch & 1ull);
+    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 0);
+    if (t == 0) {
+      float tm = 0.f;
+      for (int p = 0; p < n_poses; p++) tm = fmaxf(tm, sh.pose32[p][3].x);
+      sh.tmax = tm;
+    }
+    // ---- (A) histograms of this block's slice -----------------------------------------------------------------------
+    const int per_copy = n_poses * a.nb;
+    w.hist_addr = smem_base + 4u * static_cast<unsigned int>((warp % a.copies) * per_copy);
+    float4 qk[K];
+    unsigned int tpos = begin;
+    const bool first_full = has_work && tpos + 32u * K <= end;
+    if (first_full) pk_load_tile<K>(B.points, tpos, end, lane, qk);  // in flight while the copies are zeroed
+    for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
+    __syncthreads();
+    if (has_work) {
+      while (tpos + 32u * K <= end) {
+        float4 nxt[K];
+        const bool more = tpos + 64u * K <= end;
+        if (more) pk_load_tile<K>(B.points, tpos + 32u * K, end, lane, nxt);
+        pk_tile<MODEL, K, false, ATOM>(a, sh, B, n_poses, w, tpos, end, qk);
+        tpos += 32u * K;
+        if (more) {
+#pragma unroll
+          for (int j = 0; j < K; j++) qk[j] = nxt[j];
+        }
+      }
+      float4 q1[1], n1[1];
+      if (tpos < end) pk_load_tile<1>(B.points, tpos, end, lane, q1);
+      while (tpos < end) {
+        const bool more = tpos + 32u < end;
+        if (more) pk_load_tile<1>(B.points, tpos + 32u, end, lane, n1);
+        pk_tile<MODEL, 1, true, ATOM>(a, sh, B, n_poses, w, tpos, end, q1);
+        tpos += 32u;
+        if (more) q1[0] = n1[0];
+      }
+    }
+    if (w.qn > 0) {
+      pk_drain32<MODEL>(a, sh, B, w, 0, w.qn);
+      w.qn = 0;
+    }
+    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 1);
+    __syncthreads();
+    // ---- merge into the global accumulators -----------------------------------------------------------------------------
+    // pose-list mode runs ahead of the finalizers: buffer `buf` must have been finalized (zeroed) for batch - 2 first.
+    // (Nelder-Mead mode: seeing the scores of batch - 1 already implies it.)
+    if (!solve_mode && batch >= 2) {
+      if (!pk_wait_counter(a, sh, a.fin_done + buf, static_cast<unsigned int>((batch >> 1) * static_cast<unsigned long long>(n_items_per_batch)))) return;
+    }
+    {
+      int* g = a.ghist + (static_cast<size_t>(buf) * a.n_bags + bag) * PK_MAX_POSES * a.nb;
+      for (int k = t; k < per_copy; k += PK_THREADS) {
+        int s = 0;
+        for (int c = 0; c < a.copies; c++) s += smem_hist[c * per_copy + k];
+        if (s) atomicAdd(g + k, s);
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) atomicAdd(a.arrive + buf * PK_MAX_BAGS + bag, 1u);
+    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 2);
+    // ---- (B) finalize the (bag, pose) items this block owns ---------------------------------------------------------------
+    const unsigned long long seq = sh.seq_base + batch + 1ull;
+    const int slot = static_cast<int>(seq & 1ull);
+    const unsigned long long tag = ((seq & 0x7fffffffull) | 0x80000000ull) << 32;  // never 0 (mailboxes start zeroed)
+    for (int item = 0; item < a.n_bags * n_poses; item++) {
+      const int ib = item / n_poses, ip = item % n_poses;
+      if (static_cast<int>((static_cast<long long>(ib * PK_MAX_POSES + ip) * fin_stride) % gridDim.x) != static_cast<int>(blockIdx.x)) continue;
+      const unsigned int expected = static_cast<unsigned int>(((batch >> 1) + 1ull) * static_cast<unsigned long long>(a.bag[ib].block_count));
+      if (!pk_wait_counter(a, sh, a.arrive + buf * PK_MAX_BAGS + ib, expected)) return;
+      if (item == 0 && t == 0) pk_stamp(a, batch, 3);
+      int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
+      int* ho = (a.hist_out && ib == 0) ? a.hist_out + (static_cast<size_t>(batch) * PK_MAX_POSES + ip) * a.nb : nullptr;
+      const double nid = pk_block_nid(sh, g, a.nb, a.bins, ho, smem_hist);
+      if (solve_mode) {
+        // the score goes to every rank's mailbox (NVLink peer stores when world > 1), tagged words
+        if (t < a.world) {
+          const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(nid));
+          volatile unsigned long long* dst = a.box[t]->w[slot][(a.rank * a.n_bags + ib) * PK_MAX_POSES + ip];
+          dst[0] = tag | (bits & 0xffffffffull);
+          dst[1] = tag | (bits >> 32);
+        }
+      } else {
+        if (t == 0) {
+          // pose-list mode: sum over the launch's bags in bag order needs all of them; single-bag launches store directly
+          if (a.n_bags == 1) a.scores_out[batch * PK_MAX_POSES + ip] = nid;
+          else a.scores_out[(batch * PK_MAX_POSES + ip) * a.n_bags + ib] = nid;  // per-bag scores; the host adds them in order
+          __threadfence();
+          atomicAdd(a.fin_done + buf, 1u);
+        }
+      }
+      if (item == 0 && t == 0) pk_stamp(a, batch, 4);
+      __syncthreads();
+    }
+    if (!solve_mode) {
+      // ---- next chunk of the pose list (only the last chunk can be partial, and no merge ever waits for it) ----
+      const long long next0 = static_cast<long long>(batch + 1ull) * PK_MAX_POSES;
+      const int pc = static_cast<int>(max(0ll, min(static_cast<long long>(PK_MAX_POSES), static_cast<long long>(a.n_total) - next0)));
+      __syncthreads();
+      if (t < pc) pk_pose_from_list(sh, t, a.poses_in + 12 * static_cast<size_t>(next0 + t));
+      if (t == 0) sh.n_poses = pc;
+      __syncthreads();
+      continue;
+    }
+    // ---- (C) all scores of the batch -> sum over ranks and bags -> Nelder-Mead step -> next poses ---------------------------
+    const int n_words = a.world * a.n_bags * n_poses;
+    bool timed_out = false;
+    if (t < n_words) {
+      const int src = t / n_poses, p = t % n_poses;  // src = rank * n_bags + bag
+      volatile unsigned long long* wsrc = a.box[a.rank]->w[slot][src * PK_MAX_POSES + p];
+      const unsigned long long t0 = global_ns();
+      unsigned int spins = 0;
+      unsigned long long wl, wh;
+      for (;;) {
+        wl = wsrc[0], wh = wsrc[1];
+        if ((wl & 0xffffffff00000000ull) == tag && (wh & 0xffffffff00000000ull) == tag) break;
+        if ((++spins & 255u) == 0) {
+          if (ld_acquire_u32(a.abort_flag) != 0u) {
+            timed_out = true;
+            break;
+          }
+          if (global_ns() - t0 > a.timeout_ns) {
+            atomicExch(a.abort_flag, 1u);
+            if (a.error_host) *reinterpret_cast<volatile int*>(a.error_host) = 1;
+            timed_out = true;
+            break;
+          }
+        }
+      }
+      sh.parts[src * PK_MAX_POSES + p] = __longlong_as_double(static_cast<long long>((wh << 32) | (wl & 0xffffffffull)));
+    }
+    if (__syncthreads_or(timed_out ? 1 : 0)) return;
+    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 5);
+    if (t < n_poses) {
+      double total = 0.0;
+      for (int s = 0; s < a.world * a.n_bags; s++) total += sh.parts[s * PK_MAX_POSES + t];  // (rank, bag) order: identical everywhere
+      sh.ys[t] = total;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      nm_warp_step(sh.nm, sh.ys, lane);
+      if (blockIdx.x == 0) {  // reference-order evaluations of this batch, for the callback replay on the host (posted writes)
+        const int n_obs = sh.nm.n_obs;
+        const int base = sh.trace_count;
+        for (int k = 0; k < n_obs; k++) {
+          if (base + k < a.trace_cap) {
+            double* e = a.trace_host + static_cast<size_t>(base + k) * (NM_MAX_N + 1);
+            if (lane < sh.nm.n) e[lane] = sh.nm.obs_x[k][lane];
+            if (lane == 0) e[NM_MAX_N] = sh.nm.obs_y[k];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          sh.trace_count = base + n_obs;
+          sh.poses_scored += static_cast<unsigned long long>(n_poses);
+        }
+      }
+      const int n_next = sh.nm.n_cand;  // 0 when finished
+      if (lane < n_next) pk_pose_of_candidate(sh, lane);
+      if (lane == 0) sh.n_poses = n_next;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 6);
+  }
+
+  // ---- results (block 0) ----
+  if (blockIdx.x == 0) {
+    if (solve_mode) {
+      const unsigned long long batches = static_cast<unsigned long long>(sh.nm.num_batches);
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&sh.nm);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&a.result_host->nm);
+      for (int i = t; i < static_cast<int>(sizeof(NmMachine) / 8); i += PK_THREADS) dst[i] = src[i];
+      if (t == 0) {
+        a.result_host->batches = batches;
+        a.result_host->poses = sh.poses_scored;
+        a.result_host->trace_count = sh.trace_count;
+        *a.seq_counter = sh.seq_base + batches;  // every rank runs the same number of exchanges
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0 && a.done_host && solve_mode) *reinterpret_cast<volatile unsigned long long*>(a.done_host) = a.done_seq;
+  }
+}
+
+// debug / test kernel: the lean classifier AND the exact path on every (point, pose); a.dbg: [0] point-poses,
+// [1] verdicts deferred to the exact path, [2] kept verdicts that disagree with the exact path (must be 0)
+template <int MODEL>
+__global__ void __launch_bounds__(NID_THREADS) nid_lean_verify_kernel(const __grid_constant__ NidArgs a, const __grid_constant__ LeanCam lc) {
+  const float4* __restrict__ pts = static_cast<const float4*>(a.points);
+  unsigned long long total = 0, uncertain = 0, mismatch = 0;
+  float tmax = 0.f;
+  for (int p = 0; p < a.n_poses; p++) tmax = fmaxf(tmax, a.pose32[p][12]);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const float4 q = __ldg(pts + i);
+    const float delta = (5.25f * F32_U) * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + tmax);
+    for (int p = 0; p < a.n_poses; p++) {
+      total++;
+      const LeanVerdict v = classify_lean<MODEL>(a.fast, lc, a.width, a.pose32[p], q.x, q.y, q.z, delta);
+      const int pe = exact_pixel_hd<MODEL>(a.cam, a.cos_fov, a.width, a.height, a.pose[p], q.x, q.y, q.z);
+      if (v.uncertain) {
+        uncertain++;
+      } else if (v.accept ? (v.idx != pe) : (pe != -1)) {
+        mismatch++;
+      }
+    }
+  }
+  atomicAdd(a.dbg + 0, total);
+  atomicAdd(a.dbg + 1, uncertain);
+  atomicAdd(a.dbg + 2, mismatch);
+}
+
+}  // namespace vlcal

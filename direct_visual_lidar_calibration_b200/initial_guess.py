@@ -31,20 +31,30 @@ def pose_grid(T_center: np.ndarray, n_rot=(8, 8, 8), n_trans=(2, 4, 4), rot_half
     return np.stack(out)
 
 
-def score_poses(cost: CostCalculatorNID, poses: np.ndarray, rank: int = 0, world: int = 1, chunk: int = 4096) -> np.ndarray:
-    """NID of every pose; with world > 1 this rank scores poses[rank::world] and the full vector is assembled with
-    torch.distributed.all_gather_object (host side)."""
+def score_poses(cost: CostCalculatorNID, poses: np.ndarray, rank: int = 0, world: int = 1) -> np.ndarray:
+    """NID of every pose.  One persistent launch scores this rank's whole share of the list (vlcal_nid_score_poses);
+    with world > 1 rank r scores poses[r::world] and the full vector is assembled with one all_gather of the device
+    tensors (NCCL) -- the only exchange of the whole search."""
+    from .cost import score_poses as _score
+
     mine = poses[rank::world]
-    vals = np.concatenate([cost.calculate_batch(mine[i : i + chunk]) for i in range(0, len(mine), chunk)]) if len(mine) else np.zeros(0)
+    vals = _score([cost], mine) if len(mine) else np.zeros(0)
     if world == 1:
         return vals
+    import torch
     import torch.distributed as dist
 
-    parts = [None] * world
-    dist.all_gather_object(parts, vals)
+    per = (len(poses) + world - 1) // world  # ranks at the tail may hold one pose less: pad to a common length
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    local = torch.full((per,), float("nan"), dtype=torch.float64, device=dev)
+    local[: len(vals)] = torch.from_numpy(vals).to(dev)
+    parts = torch.empty((world, per), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(parts, local)
+    parts = parts.cpu().numpy()
     full = np.empty(len(poses))
     for r in range(world):
-        full[r::world] = parts[r]
+        k = len(poses[r::world])
+        full[r::world] = parts[r, :k]
     return full
 
 

@@ -120,6 +120,13 @@ int vlcal_nid_evaluate(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_p
 int vlcal_nid_evaluate_async(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses);
 int vlcal_nid_wait(vlcal_nid_ctx* ctx, double* nid_out, int32_t* hist_out);
 
+/* the objective of visual_camera_calibration.cpp:105-110 for a pose LIST of any length: nid_out[p] = sum over the contexts
+ * (bags, in the order given) of CostCalculatorNID::calculate(T_p).  One persistent launch scores every pose on every bag
+ * (pose-grid search, BASELINE config 5: 16 384 poses x 5 M points); contexts must share camera, image size, bins and
+ * device for that -- otherwise it falls back to one batched evaluation per context.  Every score equals the one
+ * vlcal_nid_evaluate returns for that pose, bit for bit. */
+int vlcal_nid_score_poses(vlcal_nid_ctx* const* ctxs, int n_ctxs, const double* T_camera_lidar, int n_poses, double* nid_out);
+
 /* mode B evaluation with the reference's parameterisation: T_params = P x 7 doubles [qx qy qz qw tx ty tz]
  * (Sophus::SE3d storage, include/vlcal/costs/nid_cost.hpp:38).  ok_out[p] = 0 where the reference functor returns
  * false (non-finite NID, :98-102).  hist_out: optional P x bins x bins doubles (un-normalised). */
@@ -147,9 +154,17 @@ int vlcal_nid_max_poses_per_launch(void);
 int vlcal_nid_set_profiling(vlcal_nid_ctx* ctx, int enable);
 int vlcal_nid_get_profile(vlcal_nid_ctx* ctx, int64_t* kernel_launches, double* kernel_ms_total, int64_t* poses_total);
 int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
+/* passes over the cloud since the last reset: a persistent launch (one per inner solve / pose list) carries one pass per
+ * Nelder-Mead batch / chunk of 8 poses, a round-1 launch is one pass.  Algorithmic bytes = passes x (16 N + W H). */
+int vlcal_nid_get_profile_passes(vlcal_nid_ctx* ctx, int64_t* passes);
+/* measurement hook for the persistent solve: call with stamps_out == NULL to arm (the next persistent solve on this
+ * context records %globaltimer stamps for its first `capacity` batches), then again with a buffer of capacity x 8 words:
+ * per batch {block 0 enters, main loop done, merged + arrived, finalizer: all blocks arrived, score published,
+ * block 0: all scores seen, next poses ready, unused}. */
+int vlcal_nid_debug_solve_stamps(vlcal_nid_ctx* ctx, int capacity, uint64_t* stamps_out, int* n_out);
 /* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck; 2 or 4 points per lane and
  * tile, chosen from the camera model and the cloud size), 1 = exact fp64 only, 2 = filter forced to 2 points,
- * 3 = filter forced to 4 points */
+ * 3 = filter forced to 4 points, 4 = round-1 kernels (one launch per batch; the persistent kernel is not used) */
 int vlcal_nid_set_kernel_variant(vlcal_nid_ctx* ctx, int variant);
 
 /* measurement hook: one launch (n_poses <= 8) with %globaltimer stamps; out_us = {main loop done, merged, ticket, finalize done,
@@ -212,7 +227,12 @@ int vlcal_view_cull(
 /* ---- solver surface ------------------------------------------------------------------ */
 
 /* how vlcal_estimate_pose_nelder_mead* / vlcal_calibrate_nelder_mead iterate (process-wide):
- *   0 / 1 host loop (default): one launch per Nelder-Mead batch, scores published to mapped host memory, host polls.
+ *   0 auto (default): 3 where possible, else 1.
+ *   3 persistent kernel: the whole inner solve is ONE cooperative launch -- candidates scored on every local bag, summed
+ *     over bags and (peer exchange) ranks, Nelder-Mead machine stepped redundantly by every block in shared memory.
+ *     Needs float4 clouds, bins <= 32, one camera / image size / device, no host all-reduce callback; VLCAL_ERR_UNSUPPORTED
+ *     otherwise.  params.callback is delivered after the solve from the evaluation trace, in the reference's order.
+ *   1 host loop: one launch per Nelder-Mead batch, scores published to mapped host memory, host polls.
  *   2 device-resident loop (one local bag; scores local or summed by the in-kernel peer exchange): the state machine
  *     advances inside the kernel's finalizing block, launches are enqueued back to back; VLCAL_ERR_UNSUPPORTED otherwise.
  * Both loops run the same state machine (bit-identical trajectory, tests/test_gpu_parity.py).  Measured on B200 at the C2

@@ -230,8 +230,9 @@ def test_inner_solve_follows_oracle_evaluation_by_evaluation(gpu, oracle):
 
 
 def test_device_resident_loop_equals_host_loop_and_oracle(gpu, oracle):
-    """The Nelder-Mead state machine advanced inside the kernel's finalizing block (solver mode 2) must walk exactly the
-    trajectory of the host loop (mode 1) and of the oracle: same x, y, iterations, evaluations, callback sequence."""
+    """The Nelder-Mead state machine advanced inside the kernel's finalizing block (solver mode 2) and inside every block of
+    the persistent cooperative kernel (mode 3, warp-parallel step) must walk exactly the trajectory of the host loop
+    (mode 1) and of the oracle: same x, y, iterations, evaluations, callback sequence."""
     V = gpu
     bag = _synthetic_bag(40000, cfg=6)
     cam = V.create_camera(bag["camera_model"], bag["intrinsics"], bag["distortion"])
@@ -240,7 +241,7 @@ def test_device_resident_loop_equals_host_loop_and_oracle(gpu, oracle):
     params.max_inner_iterations = 100
     out = {}
     try:
-        for mode in (1, 2):
+        for mode in (1, 2, 3):
             V.set_solver_mode(mode)
             calib = V.VisualCameraCalibration(cam, [data], params)
             T, r = calib.estimate_pose_nelder_mead(bag["T_init"])
@@ -248,6 +249,11 @@ def test_device_resident_loop_equals_host_loop_and_oracle(gpu, oracle):
     finally:
         V.set_solver_mode(0)
     (Th, rh, trh, sth), (Td, rd, trd, std) = out[1], out[2]
+    Tp, rp, trp, stp = out[3]
+    assert np.array_equal(Th, Tp) and np.array_equal(rh["x"], rp["x"]) and rh["y"] == rp["y"]
+    assert rh["num_iterations"] == rp["num_iterations"] and rh["num_evaluations"] == rp["num_evaluations"] and rh["converged"] == rp["converged"]
+    assert rh["num_batches"] == rp["num_batches"] and rh["num_evaluations_computed"] == rp["num_evaluations_computed"]
+    assert trh == trp
     assert np.array_equal(Th, Td) and np.array_equal(rh["x"], rd["x"]) and rh["y"] == rd["y"]
     assert rh["num_iterations"] == rd["num_iterations"] and rh["num_evaluations"] == rd["num_evaluations"] and rh["converged"] == rd["converged"]
     assert rh["num_batches"] == rd["num_batches"] and rh["num_evaluations_computed"] == rd["num_evaluations_computed"]
@@ -260,12 +266,58 @@ def test_device_resident_loop_equals_host_loop_and_oracle(gpu, oracle):
     assert np.abs(Td - ref["T"]).max() == 0.0 and abs(rd["y"] - ref["y"]) < NID_TOL
     # max_inner_iterations = 0: the loop body never runs, the result is the un-sorted x0 (nelder_mead.hpp:49,99)
     params.max_inner_iterations = 0
+    for mode in (2, 3):
+        try:
+            V.set_solver_mode(mode)
+            T0, r0 = V.VisualCameraCalibration(cam, [data], params).estimate_pose_nelder_mead(bag["T_init"])
+        finally:
+            V.set_solver_mode(0)
+        assert r0["num_evaluations"] == 7 and np.array_equal(r0["x"], np.zeros(6)) and np.abs(T0 - bag["T_init"]).max() < 1e-15
+
+
+def test_persistent_solve_two_bags_one_launch(gpu, oracle):
+    """Several bags per GPU: the persistent kernel partitions its grid over the bags and sums their scores in bag order;
+    the trajectory must be the host loop's (one launch per bag and batch) and the oracle's."""
+    V = gpu
+    b1, b2 = _synthetic_bag(30000, cfg=4), _synthetic_bag(9000, cfg=5)
+    cam = V.create_camera(b1["camera_model"], b1["intrinsics"], b1["distortion"])
+    ds = [V.VisualLiDARData(b["image"], b["points"], b["intensities"]) for b in (b1, b2)]
+    params = V.VisualCameraCalibrationParams()
+    params.max_inner_iterations = 60
+    out = {}
     try:
-        V.set_solver_mode(2)
-        T0, r0 = V.VisualCameraCalibration(cam, [data], params).estimate_pose_nelder_mead(bag["T_init"])
+        for mode in (1, 3):
+            V.set_solver_mode(mode)
+            calib = V.VisualCameraCalibration(cam, ds, params)
+            T, r = calib.estimate_pose_nelder_mead(b1["T_init"])
+            out[mode] = (T, r, [c for _, c in calib.trace])
     finally:
         V.set_solver_mode(0)
-    assert r0["num_evaluations"] == 7 and np.array_equal(r0["x"], np.zeros(6)) and np.abs(T0 - bag["T_init"]).max() < 1e-15
+    (Th, rh, trh), (Tp, rp, trp) = out[1], out[3]
+    assert np.array_equal(Th, Tp) and np.array_equal(rh["x"], rp["x"]) and rh["y"] == rp["y"] and trh == trp
+    assert rh["num_evaluations"] == rp["num_evaluations"] and rh["num_batches"] == rp["num_batches"]
+    ocam = oracle.create_camera(b1["camera_model"], b1["intrinsics"], b1["distortion"])
+    op = oracle.default_calib_params()
+    op.max_inner_iterations = 60
+    ref = oracle.estimate_pose_nelder_mead(ocam, [(b["image"], b["points"], b["intensities"]) for b in (b1, b2)], b1["T_init"], op)
+    assert np.array_equal(rp["x"], ref["x"]) and rp["num_evaluations"] == ref["num_evaluations"] and np.abs(Tp - ref["T"]).max() == 0.0
+
+
+def test_score_poses_equals_calculate(gpu, oracle):
+    """vlcal_nid_score_poses (one persistent launch for a pose list of any length, several bags) == calculate() per pose."""
+    V = gpu
+    pr1, pr2 = util.random_problem("plumb_bob", n=60000, seed=3), util.random_problem("plumb_bob", n=25000, seed=4)
+    pr2["image"], pr2["intrinsics"], pr2["distortion"] = pr1["image"][::-1].copy(), pr1["intrinsics"], pr1["distortion"]
+    c1, c2 = _cost(V, pr1), _cost(V, pr2)
+    Ts = util.random_poses(pr1["T"], 37, seed=5, rot_deg=2.0, trans=0.1)  # 37: four full chunks of 8 and a partial one
+    got = V.score_poses([c1, c2], Ts)
+    a, b = c1.calculate_batch(Ts), c2.calculate_batch(Ts)
+    assert np.array_equal(got, a + b, equal_nan=True)
+    singles = np.array([c1.calculate(T) for T in Ts[:5]])
+    assert np.array_equal(singles, a[:5], equal_nan=True)
+    assert np.array_equal(V.score_poses([c1], Ts), a, equal_nan=True)
+    ref_nid, _ = _oracle_eval(oracle, pr1, Ts[:3])
+    _assert_close_nid(a[:3], ref_nid)
 
 
 def test_device_resident_loop_full_calibrate_single_bag(gpu, oracle):
@@ -380,6 +432,9 @@ def test_filter_kernel_is_bit_identical_to_exact_kernel(gpu, oracle, model):
     cost.set_kernel_variant(3)  # filter kernel, 4 points per thread
     nid_4, hist_4 = cost.calculate_batch(Ts, return_hist=True)
     assert np.array_equal(hist_f, hist_4) and np.array_equal(nid_f, nid_4, equal_nan=True)
+    cost.set_kernel_variant(4)  # round-1 filter kernel (one launch per 8 poses)
+    nid_r, hist_r = cost.calculate_batch(Ts, return_hist=True)
+    assert np.array_equal(hist_f, hist_r) and np.array_equal(nid_f, nid_r, equal_nan=True)
     cost.set_kernel_variant(1)  # exact fp64 kernel
     nid_e, hist_e = cost.calculate_batch(Ts, return_hist=True)
     assert int(np.abs(hist_f - hist_e).sum()) == 0 and hist_f.sum() > 100000
@@ -397,6 +452,11 @@ def test_filter_error_bound_is_sound(gpu, model):
         pr = _adversarial_problem(model, 400000, seed=seed)
         Ts = util.random_poses(pr["T"], 24, seed=seed, rot_deg=rot, trans=trans)
         cost = _cost(gpu, pr)
+        n_pp, deferred, mismatches, _ = cost.debug_filter_check(Ts)  # lean classifier (what the default kernel runs)
+        assert n_pp == 400000 * 24
+        assert mismatches == 0
+        assert deferred / n_pp < 0.2
+        cost.set_kernel_variant(4)  # round-1 filter: also reports how much of its bound the fp32 error uses
         n_pp, deferred, mismatches, ratio = cost.debug_filter_check(Ts)
         assert n_pp == 400000 * 24
         assert mismatches == 0
