@@ -142,6 +142,10 @@ class CostCalculatorNID:
         _lib.check(self._L.vlcal_nid_get_profile_passes(self._ctx, C.byref(passes)))
         return {"kernel_launches": launches.value, "kernel_ms_total": ms.value, "poses_total": poses.value, "passes": passes.value}
 
+    def set_poses_per_pass(self, k: int):
+        """Poses per pass over the cloud in pose-list evaluations (1..8, default 8); measurement hook, results unchanged."""
+        _lib.check(self._L.vlcal_nid_set_poses_per_pass(self._ctx, int(k)))
+
     def arm_solve_stamps(self, capacity: int = 64):
         """The next persistent solve on this cost object records %globaltimer stamps for its first `capacity` batches."""
         _lib.check(self._L.vlcal_nid_debug_solve_stamps(self._ctx, int(capacity), None, None))

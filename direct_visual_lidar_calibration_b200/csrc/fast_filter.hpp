@@ -165,6 +165,22 @@ inline LeanCam make_lean_cam(const CameraParams& cam, const FastCam& f, int widt
     // the chord / maxima must be finite and the certain zone non-empty somewhere
     if (!std::isfinite(c.l0c) || !std::isfinite(c.lsc) || !std::isfinite(c.m16c) || !std::isfinite(c.K3) || !(c.hx0 > 0.0f) || !(c.hy0 > 0.0f)) return c;
   }
+  if (cam.model == CAM_EQUIRECTANGULAR) {
+    // own rounding budget: the custom atan2 (LEAN_ATAN_ERR_TURNS) instead of the atan2f / asinf allowances of project_fast
+    constexpr double SAFETY = 2.0;
+    const double Wd = width, Hd = height;
+    const double W = std::fabs(cam.intr[0]), H = std::fabs(cam.intr[1]);
+    if (!(cam.intr[0] > 0.0) || !(cam.intr[1] > 0.0) || W >= (1 << 21) || H >= (1 << 21)) return c;
+    c.eq_su = static_cast<float>(cam.intr[0]);
+    c.eq_sv = static_cast<float>(2.0 * cam.intr[1]);
+    c.cxh = static_cast<float>(0.5 * cam.intr[0] - 0.5);
+    c.cyh = static_cast<float>(0.5 * cam.intr[1] - 0.5);
+    const double cu = SAFETY * (W * LEAN_ATAN_ERR_TURNS + 4.0 * U * (W + Wd + 1.0));
+    const double cv = SAFETY * (2.0 * H * LEAN_ATAN_ERR_TURNS + 4.0 * U * (H + Hd + 1.0));
+    c.hx0 = dn(0.5 - cu);
+    c.hy0 = dn(0.5 - cv);
+    if (!(c.hx0 > 0.0f) || !(c.hy0 > 0.0f)) return c;
+  }
   c.enabled = 1;
   return c;
 }

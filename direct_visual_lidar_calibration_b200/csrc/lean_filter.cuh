@@ -49,7 +49,31 @@ struct LeanCam {
   float m16c;             // max of M16 over [0, R2B]
   float hx0, hy0;         // 0.5 - cu, 0.5 - cv
   float nsfx, nsfy;       // -sfx, -sfy
+  float eq_su, eq_sv;     // equirectangular: u' = lon_turns * W + cxh, v' = lat_turns * 2H + cyh
 };
+
+// atan2(a, b) / (2 pi) in turns, (-0.5, 0.5]: octant reduction + odd minimax polynomial of degree 13 on [0, 1] (fitted for
+// this file, tools/fit_atan_turns.py; fp32 Horner error <= 5.3e-8 turns) -- 20 instructions and one MUFU.RCP against ~40
+// for atan2f, whose special cases (infinities, signed zeros, denormals) the filter does not need: every degenerate input
+// comes out NaN or lands on a pixel edge, i.e. "uncertain".  Absolute error <= 1.1e-7 turns (polynomial 5.3e-8, quotient
+// rounding 1.4e-8, octant folds 4.5e-8); LEAN_ATAN_ERR_TURNS is what the error bound charges for it.
+constexpr double LEAN_ATAN_ERR_TURNS = 2.5e-7;
+VL_HD float lean_atan2_turns(float a, float b) {
+  const float ax = fabsf(a), bx = fabsf(b);
+  const float mx = fmaxf(ax, bx), mn = fminf(ax, bx);
+  const float t = mn * VL_RCPF(mx);
+  const float s = t * t;
+  float p = fmaf(s, 0.0010841299081221223f, -0.005348276346921921f);
+  p = fmaf(s, p, 0.012672499753534794f);
+  p = fmaf(s, p, -0.021061519160866737f);
+  p = fmaf(s, p, 0.03152511641383171f);
+  p = fmaf(s, p, -0.0530262365937233f);
+  p = fmaf(s, p, 0.15915432572364807f);
+  p = p * t;                          // atan(mn / mx) / 2pi in [0, 1/8]
+  p = ax > bx ? 0.25f - p : p;        // first quadrant
+  p = b < 0.0f ? 0.5f - p : p;        // upper half plane
+  return copysignf(p, a);
+}
 
 struct LeanVerdict {
   bool accept;     // the reference certainly counts this point at pixel `idx`
@@ -121,6 +145,33 @@ VL_HD LeanVerdict classify_lean(const FastCam& f, const LeanCam& c, int width, c
     const bool base = (pcz > delta) & (rho < 0.01f);
     const bool pass = base & (fov_m < c.T2lo);
     const bool rej = (base & (r2 > fmaf(c.K3, rho, c.T2hi))) | (pcz < -delta);
+    return lean_tail(c, width, up, vp, hx, hy, pass, rej);
+  } else if constexpr (MODEL == CAM_EQUIRECTANGULAR) {
+    // u = W (0.5 + atan2(x, z) / 2pi),  v = H (0.5 + asin(y / |p|) / pi) = H (0.5 + 2 atan2(y, |(x, z)|) / 2pi)
+    // (equirectangular.hpp:21-27).  Input-error terms as validated in round 1 (project_fast): |d lon| <= 1.5 delta / rxz,
+    // |d asin| <= 1.03 (2.9 delta / |p| + 4u) |p| / rxz (an upper bound for the atan2 form as well, rxz <= |p|).
+    const float xx = pcx * pcx;
+    const float rxz2 = fmaf(pcz, pcz, xx);
+    const float n2 = fmaf(pcy, pcy, rxz2);
+    const float inv_n = LEAN_RSQRT(n2);
+    const float nrm = n2 * inv_n;
+    const float inv_rxz = LEAN_RSQRT(rxz2);
+    const float rxz = rxz2 * inv_rxz;
+    const float g = fmaf(-f.cos_fov, nrm, pcz);  // :32 (cos_fov = -1 for the full sphere: only the antipode is uncertain)
+    const float mf = fmaf(3.0f, delta, (12.0f * F32_U) * nrm);
+    const float lon = lean_atan2_turns(pcx, pcz);
+    const float lat = lean_atan2_turns(pcy, rxz);
+    const float up = fmaf(lon, c.eq_su, c.cxh);
+    const float vp = fmaf(lat, c.eq_sv, c.cyh);
+    const float t_lon = (1.5f * delta) * inv_rxz;
+    const float t_by = fmaf(2.9f * delta, inv_n, 4.0f * F32_U);
+    const float t_asn = (1.03f * t_by) * (nrm * inv_rxz);
+    const float hx = fmaf(c.nsfx, t_lon, c.hx0);
+    const float hy = fmaf(c.nsfy, t_asn, c.hy0);
+    // away from the |p|^2 < 1e-3 branch (:15), from the poles and from the seam's ill-conditioning
+    const bool ok = (n2 > 2e-3f) & (rxz > 40.0f * delta) & (rxz > 0.05f * nrm);
+    const bool pass = ok & (g > mf);
+    const bool rej = g < -mf;
     return lean_tail(c, width, up, vp, hx, hy, pass, rej);
   } else {
     // other models: round-1 projection + bound (project_fast), FoV from |p| (these models need it anyway)

@@ -956,6 +956,15 @@ int vlcal_nid_get_profile_passes(vlcal_nid_ctx* ctx, int64_t* passes) {
   return VLCAL_OK;
 }
 
+int vlcal_nid_set_poses_per_pass(vlcal_nid_ctx* ctx, int poses_per_pass) {
+  if (!ctx || poses_per_pass < 1 || poses_per_pass > PK_MAX_POSES) {
+    set_last_error("poses_per_pass must be in [1, 8]");
+    return VLCAL_ERR_INVALID_ARGUMENT;
+  }
+  ctx->pk_chunk = poses_per_pass;
+  return VLCAL_OK;
+}
+
 int vlcal_nid_debug_solve_stamps(vlcal_nid_ctx* ctx, int capacity, uint64_t* stamps_out, int* n_out) {
   if (!ctx || capacity < 0) return VLCAL_ERR_INVALID_ARGUMENT;
   if (!stamps_out) {  // arm: the next persistent solve on this context records `capacity` batches

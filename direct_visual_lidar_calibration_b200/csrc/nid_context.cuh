@@ -124,6 +124,7 @@ struct vlcal_nid_ctx {
   int64_t passes = 0;  // passes over the cloud (a persistent launch carries one per Nelder-Mead batch / pose chunk)
   double kernel_ms_accum = 0.0;
   // debug: globaltimer stamps of the persistent kernel's batches (vlcal_nid_debug_solve_stamps)
+  int pk_chunk = 8;  // poses per pass of the persistent kernel's pose-list mode (vlcal_nid_set_poses_per_pass)
   int pk_stamps_cap = 0;
   std::vector<unsigned long long> pk_stamps;
 

@@ -373,12 +373,13 @@ int pk_score_poses(vlcal_nid_ctx* const* ctxs, int n_ctxs, const double* T_colma
   scratch.device = d_poses.device = d_scores.device = d_hist.device = c0->device;
   VL_CUDA(MemPool::instance().device_alloc(c0->device, L.total, &scratch.p));
   VL_CUDA(cudaMemsetAsync(scratch.p, 0, L.total, c0->stream));
-  const int n_chunks = (n_poses + PK_MAX_POSES - 1) / PK_MAX_POSES;
+  const int chunk = std::max(1, std::min(PK_MAX_POSES, c0->pk_chunk));
+  const int n_chunks = (n_poses + chunk - 1) / chunk;
   const size_t pose_bytes = sizeof(double) * 12 * static_cast<size_t>(n_poses);
-  const size_t score_count = static_cast<size_t>(n_chunks) * PK_MAX_POSES * n_ctxs;
+  const size_t score_count = static_cast<size_t>(n_chunks) * chunk * n_ctxs;
   VL_CUDA(MemPool::instance().device_alloc(c0->device, pose_bytes, &d_poses.p));
   VL_CUDA(MemPool::instance().device_alloc(c0->device, sizeof(double) * score_count, &d_scores.p));
-  if (hist_out) VL_CUDA(MemPool::instance().device_alloc(c0->device, sizeof(int) * static_cast<size_t>(n_chunks) * PK_MAX_POSES * nb, &d_hist.p));
+  if (hist_out) VL_CUDA(MemPool::instance().device_alloc(c0->device, sizeof(int) * static_cast<size_t>(n_chunks) * chunk * nb, &d_hist.p));
   PinBuf host;
   VL_CUDA(MemPool::instance().pinned_alloc(std::max(pose_bytes, sizeof(double) * score_count) + 64, &host.p));
   double* hpose = static_cast<double*>(host.p);
@@ -393,6 +394,7 @@ int pk_score_poses(vlcal_nid_ctx* const* ctxs, int n_ctxs, const double* T_colma
   pk_fill_common(a, ctxs, n_ctxs, g, grid, static_cast<char*>(scratch.p), L);
   a.poses_in = static_cast<const double*>(d_poses.p);
   a.n_total = n_poses;
+  a.chunk = chunk;
   a.scores_out = static_cast<double*>(d_scores.p);
   a.hist_out = hist_out ? static_cast<int*>(d_hist.p) : nullptr;
   int* h_error = reinterpret_cast<int*>(static_cast<char*>(host.p) + std::max(pose_bytes, sizeof(double) * score_count));

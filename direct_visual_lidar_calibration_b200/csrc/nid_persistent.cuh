@@ -88,6 +88,7 @@ struct PkArgs {
   int trace_cap;
   const double* poses_in;    // pose-list mode: [n_total][12] row-major 3x4 [R|t]
   int n_total;
+  int chunk;                 // pose-list mode: poses per pass over the cloud (8; smaller only for roofline measurements)
   double* scores_out;        // pose-list mode: [n_total] (sum over bags of this launch)
   int* hist_out;             // optional [n_total][nb] (bag 0 only)
   // synchronisation scratch (zero on entry)
@@ -652,8 +653,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
   w.q_pose = sh.q_pose[warp];
   w.qn = 0;
   const unsigned int smem_base = static_cast<unsigned int>(__cvta_generic_to_shared(smem_hist));
-  const int n_items_per_batch = a.n_bags * PK_MAX_POSES;
-  const int fin_stride = max(1, static_cast<int>(gridDim.x) / n_items_per_batch);
+  const int n_items_per_batch = a.n_bags * (solve_mode ? PK_MAX_POSES : a.chunk);  // finalizer items of a full pose-list chunk
+  const int fin_stride = max(1, static_cast<int>(gridDim.x) / (a.n_bags * PK_MAX_POSES));
 
   // ---- first batch ----
   if (solve_mode) {
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     if (t < sh.nm.n_cand) pk_pose_of_candidate(sh, t);
     if (t == 0) sh.n_poses = sh.nm.n_cand;
   } else {
-    const int pc = min(PK_MAX_POSES, a.n_total);
+    const int pc = min(a.chunk, a.n_total);
     if (t < pc) pk_pose_from_list(sh, t, a.poses_in + 12 * static_cast<size_t>(t));
     if (t == 0) sh.n_poses = pc;
   }
@@ -753,7 +754,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       if (!pk_wait_counter(a, sh, a.arrive + buf * PK_MAX_BAGS + ib, expected)) return;
       if (item == 0 && t == 0) pk_stamp(a, batch, 3);
       int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
-      int* ho = (a.hist_out && ib == 0) ? a.hist_out + (static_cast<size_t>(batch) * PK_MAX_POSES + ip) * a.nb : nullptr;
+      int* ho = (a.hist_out && ib == 0) ? a.hist_out + (static_cast<size_t>(batch) * a.chunk + ip) * a.nb : nullptr;
       const double nid = pk_block_nid(sh, g, a.nb, a.bins, ho, smem_hist);
       if (solve_mode) {
         // the score goes to every rank's mailbox (NVLink peer stores when world > 1), tagged words
@@ -766,8 +767,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       } else {
         if (t == 0) {
           // pose-list mode: sum over the launch's bags in bag order needs all of them; single-bag launches store directly
-          if (a.n_bags == 1) a.scores_out[batch * PK_MAX_POSES + ip] = nid;
-          else a.scores_out[(batch * PK_MAX_POSES + ip) * a.n_bags + ib] = nid;  // per-bag scores; the host adds them in order
+          if (a.n_bags == 1) a.scores_out[batch * a.chunk + ip] = nid;
+          else a.scores_out[(batch * a.chunk + ip) * a.n_bags + ib] = nid;  // per-bag scores; the host adds them in order
           __threadfence();
           atomicAdd(a.fin_done + buf, 1u);
         }
@@ -777,8 +778,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     }
     if (!solve_mode) {
       // ---- next chunk of the pose list (only the last chunk can be partial, and no merge ever waits for it) ----
-      const long long next0 = static_cast<long long>(batch + 1ull) * PK_MAX_POSES;
-      const int pc = static_cast<int>(max(0ll, min(static_cast<long long>(PK_MAX_POSES), static_cast<long long>(a.n_total) - next0)));
+      const long long next0 = static_cast<long long>(batch + 1ull) * a.chunk;
+      const int pc = static_cast<int>(max(0ll, min(static_cast<long long>(a.chunk), static_cast<long long>(a.n_total) - next0)));
       __syncthreads();
       if (t < pc) pk_pose_from_list(sh, t, a.poses_in + 12 * static_cast<size_t>(next0 + t));
       if (t == 0) sh.n_poses = pc;

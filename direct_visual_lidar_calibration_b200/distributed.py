@@ -2,8 +2,11 @@
 
 `PeerExchange` wraps vlcal_nid_p2p_*: each rank allocates a mailbox on its GPU, the 64-byte cudaIpc handles are
 all-gathered once through torch.distributed, and afterwards every NID evaluation of an attached cost object returns the
-SUM OVER RANKS -- the exchange happens inside the histogram kernel's finalizing block with P2P stores over NVLink
-(csrc/nid_kernels.cuh: nid_peer_allreduce); no collective is launched per Nelder-Mead batch."""
+SUM OVER RANKS -- the exchange happens inside the kernels with P2P stores over NVLink: the persistent solve
+(csrc/nid_persistent.cuh) stores every (bag, pose) score into every rank's mailbox and every block of every rank adds
+them in (rank, bag) order; the round-1 kernels do it in their finalizing block (csrc/nid_kernels.cuh: nid_peer_allreduce).
+No collective is launched per Nelder-Mead batch.  The mailboxes are cudaIpc-shared, so ranks may also share one GPU
+(tests/test_gpu_parity.py runs the exchange with two processes on device 0)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -35,7 +38,9 @@ class PeerExchange:
         import torch
         import torch.distributed as dist
 
-        mine = torch.tensor(list(self.ipc_handle), dtype=torch.uint8, device=f"cuda:{self.device}")
+        # NCCL moves device tensors, gloo host tensors (CPU tests; several ranks sharing one GPU)
+        dev = f"cuda:{self.device}" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor(list(self.ipc_handle), dtype=torch.uint8, device=dev)
         gathered = [torch.zeros_like(mine) for _ in range(self.world)]
         dist.all_gather(gathered, mine)
         self.connect([bytes(g.cpu().tolist()) for g in gathered])

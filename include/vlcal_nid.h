@@ -157,6 +157,10 @@ int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx);
 /* passes over the cloud since the last reset: a persistent launch (one per inner solve / pose list) carries one pass per
  * Nelder-Mead batch / chunk of 8 poses, a round-1 launch is one pass.  Algorithmic bytes = passes x (16 N + W H). */
 int vlcal_nid_get_profile_passes(vlcal_nid_ctx* ctx, int64_t* passes);
+/* measurement hook: poses carried by one pass over the cloud in pose-list evaluations (vlcal_nid_evaluate /
+ * vlcal_nid_score_poses) of this context, 1..8 (default 8).  Results do not depend on it; bench.py uses 1 to measure the
+ * P = 1 roofline point (one pose per 16 N + W H algorithmic bytes). */
+int vlcal_nid_set_poses_per_pass(vlcal_nid_ctx* ctx, int poses_per_pass);
 /* measurement hook for the persistent solve: call with stamps_out == NULL to arm (the next persistent solve on this
  * context records %globaltimer stamps for its first `capacity` batches), then again with a buffer of capacity x 8 words:
  * per batch {block 0 enters, main loop done, merged + arrived, finalizer: all blocks arrived, score published,

@@ -277,6 +277,11 @@ def nid_cost_bspline_grad(cam, image_u8, points_xyzw, intensities, bins, T_param
     return bool(ok), float(out.value), grad
 
 
+def set_bag_threads(n: int):
+    """Threads of the objective's loop over bags (0 = one per bag like the reference's OpenMP loop, 1 = serial)."""
+    lib().orc_set_bag_threads(int(n))
+
+
 def default_calib_params() -> CalibParams:
     p = CalibParams()
     lib().orc_calib_default_params(C.byref(p))

@@ -865,6 +865,11 @@ void orc_calib_default_params(orc_calib_params* p) { /* visual_camera_calibratio
   p->nelder_mead_convergence_criteria = 1e-8;
 }
 
+/* threads of the objective's loop over bags (visual_camera_calibration.cpp:107): 0 = one per bag, 1 = serial */
+#define ORC_MAX_BAGS 64
+static int g_bag_threads = 0;
+void orc_set_bag_threads(int n) { g_bag_threads = n < 0 ? 0 : n; }
+
 typedef struct {
   const orc_camera* cam;
   int n_bags;
@@ -882,9 +887,24 @@ static double calib_objective(const double* x, void* user) { /* :103-119 */
   orc_se3_expmap_gtsam(x, E);
   orc_isometry_mul(c->init_T, E, T); /* :104 */
   double sum_costs = 0.0;
-  for (int i = 0; i < c->n_bags; i++) { /* :107-110 (OpenMP over bags in the reference) */
-    const orc_bag* b = &c->bags[i];
-    sum_costs += orc_nid_calculate(c->cam, b->image, b->width, b->height, b->row_stride, b->points_xyzw, b->intensities, b->n, c->bins, c->max_fovs[i], T, NULL);
+  /* :107-110 `#pragma omp parallel for reduction(+ : sum_costs)` over the bags: one thread per cost object, each serial
+   * over its points.  The per-bag values are added in bag order afterwards, so the result does not depend on the team
+   * size (the reference's reduction order is unspecified; with one bag there is nothing to reorder). */
+  double per_bag[ORC_MAX_BAGS];
+  const int nb = c->n_bags;
+  if (nb <= ORC_MAX_BAGS && g_bag_threads != 1 && nb > 1) {
+    const int team = g_bag_threads > 0 ? (g_bag_threads < nb ? g_bag_threads : nb) : nb;
+#pragma omp parallel for schedule(static) num_threads(team)
+    for (int i = 0; i < nb; i++) {
+      const orc_bag* b = &c->bags[i];
+      per_bag[i] = orc_nid_calculate(c->cam, b->image, b->width, b->height, b->row_stride, b->points_xyzw, b->intensities, b->n, c->bins, c->max_fovs[i], T, NULL);
+    }
+    for (int i = 0; i < nb; i++) sum_costs += per_bag[i];
+  } else {
+    for (int i = 0; i < nb; i++) {
+      const orc_bag* b = &c->bags[i];
+      sum_costs += orc_nid_calculate(c->cam, b->image, b->width, b->height, b->row_stride, b->points_xyzw, b->intensities, b->n, c->bins, c->max_fovs[i], T, NULL);
+    }
   }
   if (sum_costs < c->best_cost) { /* :112-116 */
     c->best_cost = sum_costs;

@@ -229,6 +229,10 @@ int orc_nid_cost_bspline_grad(
   double* grad_out,
   double* hist_out);
 
+/* team size of the objective's OpenMP loop over bags (visual_camera_calibration.cpp:107): 0 = one thread per bag
+ * (the reference's behaviour on a host with enough cores), 1 = serial.  Results do not depend on it. */
+void orc_set_bag_threads(int n);
+
 #ifdef __cplusplus
 }
 #endif

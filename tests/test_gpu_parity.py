@@ -562,6 +562,27 @@ def test_fused_peer_exchange_matches_nccl_and_single_gpu(gpu):
     assert "POSE_SHARD_CHECK world=2" in out.stdout and "identical=True" in out.stdout.split("POSE_SHARD_CHECK")[1]
 
 
+def test_persistent_exchange_two_ranks_on_one_gpu(gpu):
+    """The in-kernel score exchange of the persistent solve (tagged words in cudaIpc-shared mailboxes, summed in (rank, bag)
+    order by every block of every rank) with TWO processes on ONE GPU -- so that the single-GPU test box covers it: one
+    and two bags per rank and the mixed spinning / non-repetitive dataset of BASELINE config 4; every rank must end with
+    the bits of the single-process solve over all bags (one launch) and of the round-1 host loop."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, VLCAL_DIST_SINGLE_GPU="1", VLCAL_SYNC_TIMEOUT_MS="30000", OMP_NUM_THREADS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "dist_check_pk.py")],
+        capture_output=True, text=True, timeout=900, env=env,
+    )
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("PK_DIST_CHECK")]
+    assert len(lines) == 3, out.stdout[-3000:]
+    for ln in lines:
+        assert "ranks_identical=True equals_single_process_one_launch=True equals_host_loop=True" in ln, ln
+
+
 def test_pose_grid_search_finds_the_basin(gpu, oracle):
     """Config-5 style coarse grid: every score equals the oracle's, and the best grid pose is the one nearest the truth."""
     from direct_visual_lidar_calibration_b200 import initial_guess as IG
