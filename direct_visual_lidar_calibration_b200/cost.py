@@ -158,6 +158,13 @@ class CostCalculatorNID:
         _lib.check(self._L.vlcal_nid_debug_solve_stamps(self._ctx, int(capacity), buf, C.byref(n)))
         return np.ctypeslib.as_array(buf).reshape(capacity, 8)[: n.value].copy()
 
+    def block_times(self, capacity: int = 2048):
+        """(n_blocks, 4) uint64 ns stamps of one batch of the last stamped persistent solve: enter, zeroed, main loop done, arrived."""
+        buf = (C.c_uint64 * (4 * capacity))()
+        n = C.c_int()
+        _lib.check(self._L.vlcal_nid_debug_block_times(self._ctx, int(capacity), buf, C.byref(n)))
+        return np.ctypeslib.as_array(buf).reshape(capacity, 4)[: n.value].copy()
+
     def close(self):
         if self._ctx:
             self._L.vlcal_nid_destroy(self._ctx)

@@ -143,18 +143,18 @@ inline LeanCam make_lean_cam(const CameraParams& cam, const FastCam& f, int widt
     if (!(cs >= 0.05)) return c;  // make_fast_cam already requires it
     const double T2 = 1.0 / (cs * cs) - 1.0;  // tan^2(max_fov)
     const double sT = std::sqrt(T2);
-    // a point that certainly passes the FoV test has r2 < T2, hence r2b = fma(r2, 1.001, 1e-6) <= R2B
+    // e = L (rho (1 + mh) + 4u mh) + M16 with L = sum l_i t^i, mh = (1 + t) / 2, M16 = sum m_i t^i  (t = r2b), expanded:
+    //   A(t) = L(t) (1.5 + 0.5 t),  B(t) = L(t) (2u + 2u t) + M16(t)   -- all coefficients non-negative
+    const double l[5] = {f.l0, f.l1, f.l2, f.l3, 0.0};
+    const double m[5] = {f.m0, f.m1, f.m2, f.m3, f.m4};
+    for (int i = 0; i < 5; i++) {
+      const double lm1 = i > 0 ? l[i - 1] : 0.0;
+      c.ea[i] = up((1.5 * l[i] + 0.5 * lm1) * (1.0 + 8 * U));
+      c.eb[i] = up((2.0 * U * (l[i] + lm1) + m[i]) * (1.0 + 8 * U));
+    }
+    // FoV margin: 3 exy over the disc a point that certainly passes the FoV test can lie in (r2 < T2, r2b <= R2B)
     const double R2B = (1.001 * T2 + 1e-6) * (1.0 + 1e-6);
-    const double l0 = f.l0, l1 = f.l1, l2 = f.l2, l3 = f.l3;
-    const double L_at = l0 + R2B * (l1 + R2B * (l2 + R2B * l3));
-    const double S = R2B > 0.0 ? (L_at - l0) / R2B : 0.0;  // chord slope of the convex L over [0, R2B]
-    c.l0c = up((l0 + 1e-6 * S) * (1.0 + 8 * U));
-    c.lsc = up(1.001 * S * (1.0 + 8 * U));
-    const double M16_at = f.m0 + R2B * (f.m1 + R2B * (f.m2 + R2B * (f.m3 + R2B * f.m4)));
-    c.m16c = up(M16_at * (1.0 + 8 * U));
     const double MH = 0.5 * R2B + 0.5;  // mh = (1 + r2b) / 2 <= MH
-    c.C1 = up(1.0 + MH);
-    c.C2 = up(4.0 * U * MH);
     c.C1x3 = up(3.0 * (1.0 + MH));
     c.C2x3 = up(12.0 * U * MH);
     c.T2lo = dn(T2 * (1.0 - 1e-6));
@@ -163,7 +163,9 @@ inline LeanCam make_lean_cam(const CameraParams& cam, const FastCam& f, int widt
     c.cxh = static_cast<float>(cam.intr[2] - 0.5);
     c.cyh = static_cast<float>(cam.intr[3] - 0.5);
     // the chord / maxima must be finite and the certain zone non-empty somewhere
-    if (!std::isfinite(c.l0c) || !std::isfinite(c.lsc) || !std::isfinite(c.m16c) || !std::isfinite(c.K3) || !(c.hx0 > 0.0f) || !(c.hy0 > 0.0f)) return c;
+    for (int i = 0; i < 5; i++)
+      if (!std::isfinite(c.ea[i]) || !std::isfinite(c.eb[i])) return c;
+    if (!std::isfinite(c.K3) || !std::isfinite(c.C1x3) || !(c.hx0 > 0.0f) || !(c.hy0 > 0.0f)) return c;
   }
   if (cam.model == CAM_EQUIRECTANGULAR) {
     // own rounding budget: the custom atan2 (LEAN_ATAN_ERR_TURNS) instead of the atan2f / asinf allowances of project_fast

@@ -11,12 +11,10 @@
 //     (u in (-1, 0) -> column 0, cost_calculator_nid.cpp:37) is the clamp max(rint(u'), 0) with the lower bound at -1;
 //   * pinhole-type models decide the FoV cone (:32) from r^2 = x^2 + y^2 of the normalised point, which the
 //     distortion polynomial needs anyway:  z/|p| >= cos(fov)  <=>  z > 0 and r^2 <= tan^2(fov).  No |p|, no rsqrt;
-//   * the error bound E is the round-1 bound (fast_filter.hpp, camera_models.cuh:project_fast) relaxed to what is cheap:
-//     the Jacobian bound L(r^2) (convex, positive coefficients) is replaced by its chord over [0, R2B], the rounding
-//     polynomial M16 and the (1 + r)/2 factors by their maxima over the same interval, R2B = the largest r^2 a point
-//     that certainly passes the FoV test can have.  Every replacement is an upper bound of the validated quantity, so
-//     soundness carries over; the deferral rate rises from ~2 % to ~3 % at C2 and the bound costs 5 instructions
-//     instead of 14;
+//   * the error bound E is the round-1 bound (fast_filter.hpp, camera_models.cuh:project_fast), e = L exy + M16 with
+//     exy = rho (1 + mh) + 4u mh, multiplied out on the host into e = rho A(r2b) + B(r2b): two degree-4 Horner chains
+//     and one FMA instead of five dependent polynomial / product steps (same value up to the upward rounding of the
+//     coefficients, so soundness carries over);
 //   * verdicts are three predicates (accept / uncertain / otherwise rejected) built from FSETP chains: no SEL / integer
 //     verdict codes.
 //
@@ -42,11 +40,9 @@ struct LeanCam {
   // pinhole-type FoV test on r^2
   float T2lo;             // pass   iff r2 + 3 exy (1 + r2) < T2lo
   float T2hi, K3;         // reject iff rho < 0.01 and r2 > T2hi + K3 rho
-  // relaxed error bound
-  float C1, C2;           // exy <= rho C1 + C2
-  float C1x3, C2x3;
-  float l0c, lsc;         // L(r2) <= l0c + lsc r2   (chord, r2b = 1.001 r2 + 1e-6 folded in)
-  float m16c;             // max of M16 over [0, R2B]
+  // error bound of the plumb_bob projection: e = rho A(r2b) + B(r2b), A = L (1 + mh), B = 4u L mh + M16 (fast_filter.hpp)
+  float ea[5], eb[5];
+  float C1x3, C2x3;       // FoV margin only: 3 exy <= rho C1x3 + C2x3 on the FoV disc (the band it widens holds ~0.001 % of the points)
   float hx0, hy0;         // 0.5 - cu, 0.5 - cv
   float nsfx, nsfy;       // -sfx, -sfy
   float eq_su, eq_sv;     // equirectangular: u' = lon_turns * W + cxh, v' = lat_turns * 2H + cyh
@@ -133,10 +129,14 @@ VL_HD LeanVerdict classify_lean(const FastCam& f, const LeanCam& c, int width, c
     const float yd = fmaf(yn, rc, fmaf(2.0f * p2, xy, p1 * fmaf(2.0f, y2, r2)));
     const float up = fmaf(f.fx, xd, c.cxh);
     const float vp = fmaf(f.fy, yd, c.cyh);
-    // error bound (see header): e <= L exy + M16
-    const float exy = fmaf(rho, c.C1, c.C2);
-    const float L = fmaf(c.lsc, r2, c.l0c);
-    const float e = fmaf(L, exy, c.m16c);
+    // error bound: e = L exy + M16 of the round-1 filter, exy = rho (1 + mh) + 4u mh, with the products expanded on the host
+    // into two polynomials of r2b: e = rho A(r2b) + B(r2b)  (positive coefficients, rounded up).  Evaluated PER POINT: maxima
+    // or chords over the FoV disc are 3-4x looser on lenses whose distortion folds back (the C2 camera: max_fov = 59 deg
+    // although the image corner sits at 48 deg) and deferred 10 % of the point-poses instead of 3 %.
+    const float r2b = fmaf(r2, 1.001f, 1e-6f);
+    const float A = fmaf(r2b, fmaf(r2b, fmaf(r2b, fmaf(r2b, c.ea[4], c.ea[3]), c.ea[2]), c.ea[1]), c.ea[0]);
+    const float B = fmaf(r2b, fmaf(r2b, fmaf(r2b, fmaf(r2b, c.eb[4], c.eb[3]), c.eb[2]), c.eb[1]), c.eb[0]);
+    const float e = fmaf(rho, A, B);
     const float hx = fmaf(c.nsfx, e, c.hx0);
     const float hy = fmaf(c.nsfy, e, c.hy0);
     // FoV cone from r2 (derivation: DESIGN.md section 4; needs z certainly positive and rho small)

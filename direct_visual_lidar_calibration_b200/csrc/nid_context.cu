@@ -979,6 +979,15 @@ int vlcal_nid_debug_solve_stamps(vlcal_nid_ctx* ctx, int capacity, uint64_t* sta
   return VLCAL_OK;
 }
 
+int vlcal_nid_debug_block_times(vlcal_nid_ctx* ctx, int capacity_blocks, uint64_t* times_out, int* n_blocks) {
+  if (!ctx || capacity_blocks < 0 || !times_out || !n_blocks) return VLCAL_ERR_INVALID_ARGUMENT;
+  const int have = static_cast<int>(ctx->pk_block_times.size() / 4);
+  const int n = std::min(capacity_blocks, have);
+  for (int i = 0; i < 4 * n; i++) times_out[i] = ctx->pk_block_times[i];
+  *n_blocks = n;
+  return VLCAL_OK;
+}
+
 int vlcal_nid_reset_profile(vlcal_nid_ctx* ctx) {
   if (!ctx) return VLCAL_ERR_INVALID_ARGUMENT;
   VL_CUDA(cudaSetDevice(ctx->device));

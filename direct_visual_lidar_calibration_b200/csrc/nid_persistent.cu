@@ -260,10 +260,13 @@ int pk_solve(
   stamps.device = c0->device;
   if (c0->pk_stamps_cap > 0) {
     const size_t bytes = sizeof(unsigned long long) * PK_STAMP_SLOTS * static_cast<size_t>(c0->pk_stamps_cap);
-    VL_CUDA(MemPool::instance().device_alloc(c0->device, bytes, &stamps.p));
-    VL_CUDA(cudaMemsetAsync(stamps.p, 0, bytes, c0->stream));
+    const size_t block_bytes = sizeof(unsigned long long) * 4 * static_cast<size_t>(grid);
+    VL_CUDA(MemPool::instance().device_alloc(c0->device, bytes + block_bytes, &stamps.p));
+    VL_CUDA(cudaMemsetAsync(stamps.p, 0, bytes + block_bytes, c0->stream));
     a.stamps = static_cast<unsigned long long*>(stamps.p);
     a.stamps_cap = c0->pk_stamps_cap;
+    a.block_times = a.stamps + static_cast<size_t>(PK_STAMP_SLOTS) * c0->pk_stamps_cap;
+    a.block_times_batch = std::min(8, c0->pk_stamps_cap - 1);
   }
 
   ProfileEvents ev{};
@@ -312,6 +315,8 @@ int pk_solve(
     VL_CUDA(cudaStreamSynchronize(c0->stream));
     c0->pk_stamps.resize(static_cast<size_t>(PK_STAMP_SLOTS) * c0->pk_stamps_cap);
     VL_CUDA(cudaMemcpy(c0->pk_stamps.data(), stamps.p, sizeof(unsigned long long) * c0->pk_stamps.size(), cudaMemcpyDeviceToHost));
+    c0->pk_block_times.resize(static_cast<size_t>(4) * grid);
+    VL_CUDA(cudaMemcpy(c0->pk_block_times.data(), a.block_times, sizeof(unsigned long long) * c0->pk_block_times.size(), cudaMemcpyDeviceToHost));
   }
   // scratch goes back to the pool: the kernel has published its last word, nothing else is enqueued on it
   VL_CUDA(cudaStreamSynchronize(c0->stream));

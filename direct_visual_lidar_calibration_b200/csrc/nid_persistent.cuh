@@ -105,6 +105,8 @@ struct PkArgs {
   unsigned long long done_seq;
   unsigned long long* stamps;       // optional [cap][PK_STAMP_SLOTS] globaltimer stamps per batch
   int stamps_cap;
+  unsigned long long* block_times;  // optional [grid][4]: every block's {enter, hist zeroed, main loop done, arrived} stamps of batch block_times_batch
+  int block_times_batch;
 };
 
 struct PkShared {
@@ -640,7 +642,9 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
   const unsigned int bag_n = Bc.n, bag_block_begin = static_cast<unsigned int>(Bc.block_begin), bag_block_count = static_cast<unsigned int>(Bc.block_count);
   const unsigned int warps_total = bag_block_count * PK_WARPS;
   const unsigned int warp_global = (blockIdx.x - bag_block_begin) * PK_WARPS + warp;
-  const unsigned int chunk = ((bag_n + warps_total - 1) / warps_total + 31u) & ~31u;
+  // points per warp: whole K-row tiles (a warp whose slice ends in single-row tiles runs them without instruction-level
+  // parallelism: at C2 that was 2 of its 3 tiles)
+  const unsigned int chunk = ((bag_n + warps_total - 1) / warps_total + (32u * K - 1u)) / (32u * K) * (32u * K);
   const unsigned long long lo = static_cast<unsigned long long>(warp_global) * chunk;
   const bool has_work = lo < bag_n;
   const unsigned int end = has_work ? static_cast<unsigned int>(min(static_cast<unsigned long long>(bag_n), lo + chunk)) : 0u;
@@ -683,6 +687,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     if (n_poses == 0) break;
     const int buf = static_cast<int>(batch & 1ull);
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 0);
+    const bool time_block = a.block_times != nullptr && batch == static_cast<unsigned long long>(a.block_times_batch) && t == 0;
+    if (time_block) a.block_times[4 * blockIdx.x + 0] = global_ns();
     if (t == 0) {
       float tm = 0.f;
       for (int p = 0; p < n_poses; p++) tm = fmaxf(tm, sh.pose32[p][3].x);
@@ -697,6 +703,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     if (first_full) pk_load_tile<K>(B.points, tpos, end, lane, qk);  // in flight while the copies are zeroed
     for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
     __syncthreads();
+    if (time_block) a.block_times[4 * blockIdx.x + 1] = global_ns();
     if (has_work) {
       while (tpos + 32u * K <= end) {
         float4 nxt[K];
@@ -725,6 +732,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     }
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 1);
     __syncthreads();
+    if (time_block) a.block_times[4 * blockIdx.x + 2] = global_ns();
     // ---- merge into the global accumulators -----------------------------------------------------------------------------
     // pose-list mode runs ahead of the finalizers: buffer `buf` must have been finalized (zeroed) for batch - 2 first.
     // (Nelder-Mead mode: seeing the scores of batch - 1 already implies it.)
@@ -743,6 +751,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     __syncthreads();
     if (t == 0) atomicAdd(a.arrive + buf * PK_MAX_BAGS + bag, 1u);
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 2);
+    if (time_block) a.block_times[4 * blockIdx.x + 3] = global_ns();
     // ---- (B) finalize the (bag, pose) items this block owns ---------------------------------------------------------------
     const unsigned long long seq = sh.seq_base + batch + 1ull;
     const int slot = static_cast<int>(seq & 1ull);

@@ -166,6 +166,9 @@ int vlcal_nid_set_poses_per_pass(vlcal_nid_ctx* ctx, int poses_per_pass);
  * per batch {block 0 enters, main loop done, merged + arrived, finalizer: all blocks arrived, score published,
  * block 0: all scores seen, next poses ready, unused}. */
 int vlcal_nid_debug_solve_stamps(vlcal_nid_ctx* ctx, int capacity, uint64_t* stamps_out, int* n_out);
+/* with the stamps armed, every block of the persistent solve also records {enters the batch, histogram copies zeroed, main
+ * loop done, arrived} for one batch (the 9th): capacity_blocks x 4 words out, *n_blocks = blocks of that launch */
+int vlcal_nid_debug_block_times(vlcal_nid_ctx* ctx, int capacity_blocks, uint64_t* times_out, int* n_blocks);
 /* kernel selection for A/B measurements: 0 = default (fp32 filter + exact fp64 recheck; 2 or 4 points per lane and
  * tile, chosen from the camera model and the cloud size), 1 = exact fp64 only, 2 = filter forced to 2 points,
  * 3 = filter forced to 4 points, 4 = round-1 kernels (one launch per batch; the persistent kernel is not used) */

@@ -12,6 +12,8 @@ namespace vlcal {  // members whose reference translation units (frame_cpu.cpp, 
 FrameCPU::FrameCPU() {}
 FrameCPU::~FrameCPU() {}
 VisualLiDARData::~VisualLiDARData() {}
+NIDCostParams::NIDCostParams() { bins = 16; }  // src/vlcal/calib/cost_calculator_nid.cpp:7-9
+NIDCostParams::~NIDCostParams() {}
 }  // namespace vlcal
 
 int main() {
@@ -23,6 +25,15 @@ int main() {
   frame->num_points = N, frame->points = pts.data(), frame->intensities = intens.data();
   const cv::Mat image(H, W, CV_8UC1, pixels.data(), static_cast<size_t>(W));
   try {
+    {  // the reference's own factory behind the parameter view: CostCalculatorNIDCuda(proj, data, params)
+      const auto proj = vlcal::create_camera_with_params("plumb_bob", std::vector<double>{60.0, 60.0, 32.0, 24.0}, std::vector<double>{});
+      auto data = std::make_shared<vlcal::VisualLiDARData>();
+      data->image = image;
+      data->points = frame;
+      const Eigen::Vector2d uv = proj->project(Eigen::Vector3d(0.1, 0.05, 2.0));  // forwarded to the reference's PinholeProjection
+      std::shared_ptr<vlcal::CostCalculator> cost = std::make_shared<vlcal::CostCalculatorNIDCuda>(proj, data, vlcal::NIDCostParams());
+      std::printf("VIEW u=%.6f nid=%.17g\n", uv[0], cost->calculate(Eigen::Isometry3d::Identity()));
+    }
     const Sophus::SE3d init;
     auto* fn = new vlcal::MultiNIDCostFunction(init);
     fn->add(std::make_shared<vlcal::NIDCostCuda>("plumb_bob", std::vector<double>{60.0, 60.0, 32.0, 24.0}, std::vector<double>{}, image, frame, 16));

@@ -52,6 +52,8 @@ def test_shim_matches_python_surface_and_oracle(gpu, oracle, tmp_path):
     cam = gpu.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
     ref = gpu.CostCalculatorNID(cam, gpu.VisualLiDARData(pr["image"], pr["points"], pr["intensities"])).calculate(pr["T"])
     assert vals[0] == ref and vals[1] == ref and vals[2] == ref
+    assert vals[3] == ref  # CostCalculatorNIDCuda(proj, data, params): the reference's constructor shape, through CameraParamsView
+    assert vals[4] == 1.0 and vals[5] == 1.0  # a camera without the view throws; unknown model -> nullptr like the reference
     ocam = oracle.create_camera("plumb_bob", pr["intrinsics"], pr["distortion"])
     onid = oracle.nid_calculate(ocam, pr["image"], pr["points"], pr["intensities"], 16, oracle.estimate_camera_fov(ocam, pr["W"], pr["H"]), pr["T"])[0]
     assert abs(vals[0] - onid) < 1e-12
@@ -67,7 +69,7 @@ def test_bindings_compile_inside_the_reference_tree(vlcal, tmp_path):
     exe = str(tmp_path / "cpp_bfgs")
     libdir = os.path.dirname(vlcal.library_path())
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-w", "-I", os.path.join(ROOT, "oracle", "ref_standin"), "-I", os.path.join(REFERENCE, "include"), "-I", os.path.join(ROOT, "include"),
-           os.path.join(HERE, "cpp_bfgs_main.cpp"), "-o", exe, "-L", libdir, "-lvlcal_nid", f"-Wl,-rpath,{libdir}"]
+           os.path.join(HERE, "cpp_bfgs_main.cpp"), os.path.join(REFERENCE, "src", "camera", "create_camera.cpp"), "-o", exe, "-L", libdir, "-lvlcal_nid", f"-Wl,-rpath,{libdir}"]
     subprocess.run(cmd, check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     if vlcal.device_count() > 0:

@@ -93,6 +93,13 @@ def main():
             med = {n: float(np.median(rows[:, i])) for i, n in enumerate(names)}
             nxt = (st[1:, 0] - st[:-1, 0]) * 1e-3
             print(json.dumps(dict(base, what="stamps_us_median", batches=int(len(st)), phases=med, batch_period_us=float(np.median(nxt)))), flush=True)
+            bt = cost.block_times().astype(np.int64)
+            if len(bt):
+                t0 = bt[:, 0].min()
+                rel = (bt - t0) * 1e-3
+                q = lambda v: [float(np.percentile(v, p)) for p in (0, 10, 50, 90, 100)]
+                print(json.dumps(dict(base, what="block_times_us_p0_p10_p50_p90_p100", blocks=int(len(bt)), enter=q(rel[:, 0]), zeroed=q(rel[:, 1]), main_done=q(rel[:, 2]), arrived=q(rel[:, 3]),
+                                      main_duration=q(rel[:, 2] - rel[:, 1]))), flush=True)
 
     if args.grid_poses > 0:
         rng = np.random.default_rng(0)
