@@ -6,7 +6,8 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "libvlcal_nid.so")
+# VLCAL_LIB: an alternative build of the same library (A/B measurements of compile-time kernel shapes, `make -C csrc alt`)
+_LIB_PATH = os.environ.get("VLCAL_LIB") or os.path.join(_PKG, "libvlcal_nid.so")
 _CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0

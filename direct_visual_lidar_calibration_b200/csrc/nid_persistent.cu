@@ -61,7 +61,7 @@ static std::map<std::tuple<int, const void*, size_t>, int> g_pk_occupancy;
 static int pk_geometry(int device, int num_sms, PkKernel kernel, int nb, PkGeom* g) {
   // histogram copies for 8 poses (the initial simplex of a 6-D solve is 7) -- two copies while they fit 64 KB
   const size_t per_copy = static_cast<size_t>(PK_MAX_POSES) * nb * sizeof(int);
-  g->copies = per_copy * 2 <= 64 * 1024 ? 2 : 1;
+  g->copies = static_cast<int>(std::max<size_t>(1, std::min<size_t>(PK_WARPS / 4, (64 * 1024) / per_copy)));  // one copy per four warps
   const size_t scratch = static_cast<size_t>(nb) * 8 + 64 * 8 * 2 + 64 * 4 * 2;  // pk_block_nid staging (aliases the copies)
   g->smem = std::max(per_copy * g->copies, scratch);
   std::lock_guard<std::mutex> lock(g_pk_mu);
@@ -122,7 +122,7 @@ struct PinBuf {
 
 // device scratch of one launch, one allocation, zeroed by one memset
 struct PkScratchLayout {
-  size_t ghist, arrive, fin_done, abort_flag, seq, box, solve, total;
+  size_t ghist, arrive, fin_done, tile_next, abort_flag, seq, box, solve, total;
   PkScratchLayout(int n_bags, int nb) {
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -133,6 +133,7 @@ struct PkScratchLayout {
     ghist = take(sizeof(int) * 2 * n_bags * PK_MAX_POSES * nb);
     arrive = take(sizeof(unsigned int) * 2 * PK_MAX_BAGS);
     fin_done = take(sizeof(unsigned int) * 2);
+    tile_next = take(sizeof(unsigned int) * 2 * PK_MAX_BAGS);
     abort_flag = take(sizeof(unsigned int));
     seq = take(sizeof(unsigned long long));
     box = take(sizeof(PkMailbox));
@@ -170,6 +171,15 @@ void pk_fill_common(PkArgs& a, vlcal_nid_ctx* const* ctxs, int n_ctxs, const PkG
   a.ghist = reinterpret_cast<int*>(scratch + L.ghist);
   a.arrive = reinterpret_cast<unsigned int*>(scratch + L.arrive);
   a.fin_done = reinterpret_cast<unsigned int*>(scratch + L.fin_done);
+  a.tile_next = reinterpret_cast<unsigned int*>(scratch + L.tile_next);
+  {  // dynamic split once a warp's share is a few claims long (below that the static slices are as balanced as tiles can be)
+    static const int force = [] {
+      const char* e = std::getenv("VLCAL_PK_DYNAMIC");
+      return e ? std::atoi(e) : -1;
+    }();
+    const long long per_warp = total_points / (static_cast<long long>(grid) * PK_WARPS);
+    a.dynamic_tiles = force >= 0 ? (force != 0) : (per_warp >= 768);
+  }
   a.abort_flag = reinterpret_cast<unsigned int*>(scratch + L.abort_flag);
   a.seq_counter = reinterpret_cast<unsigned long long*>(scratch + L.seq);
   a.box[0] = reinterpret_cast<PkMailbox*>(scratch + L.box);

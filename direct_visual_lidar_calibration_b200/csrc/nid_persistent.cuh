@@ -32,7 +32,10 @@
 
 namespace vlcal {
 
-constexpr int PK_THREADS = 256;
+#ifndef PK_THREADS_CFG
+#define PK_THREADS_CFG 256  // threads per block; the A/B build (make alt) uses 768 threads and one block per SM
+#endif
+constexpr int PK_THREADS = PK_THREADS_CFG;
 constexpr int PK_WARPS = PK_THREADS / 32;
 constexpr int PK_MAX_POSES = 8;
 constexpr int PK_MAX_BAGS = 8;
@@ -40,6 +43,7 @@ constexpr int PK_MAX_WORDS = 256;  // world x bags x 8 score words per batch, on
 constexpr int PK_QUEUE = 64;
 constexpr int PK_MAX_BINS = 32;    // nb <= 1024: the finalizing block keeps its share of the joint histogram in registers
 constexpr int PK_STAMP_SLOTS = 8;
+constexpr unsigned int PK_TILE_ROWS = 4;  // dynamic split: a claim is PK_TILE_ROWS tiles of 32 * K points
 #ifndef PK_MIN_BLOCKS
 #define PK_MIN_BLOCKS 3  // blocks per SM the register allocation must allow (<= 85 registers per thread)
 #endif
@@ -95,6 +99,8 @@ struct PkArgs {
   int* ghist;                // [2][n_bags][8][nb]
   unsigned int* arrive;      // [2][PK_MAX_BAGS]
   unsigned int* fin_done;    // [2]
+  unsigned int* tile_next;   // [2][PK_MAX_BAGS] dynamic split: next unclaimed tile of the batch (zeroed again by the finalizer)
+  int dynamic_tiles;
   unsigned int* abort_flag;  // set by any block that timed out: everybody leaves
   PkMailbox* box[P2P_MAX_RANKS];  // box[r]: rank r's mailbox as mapped here (self included; world == 1: local scratch)
   int world, rank;
@@ -367,20 +373,79 @@ static __device__ __noinline__ void nm_warp_step(NmMachine& s, const double* ys,
   __syncwarp();
 }
 
-// T = init_T * Expmap(x) of candidate k (visual_camera_calibration.cpp:104) -> shared pose slots
-static __device__ __noinline__ void pk_pose_of_candidate(PkShared& sh, int k) {
-  double E[16], T[16];
-  se3_expmap_gtsam_hd(&sh.nm.cand[k][1], E);
-  isometry_mul_hd(sh.init_T, E, T);
-  double tmax = 0.0;
+// T = init_T * Expmap(x) (visual_camera_calibration.cpp:104) for the n_cand <= 8 pending candidates, by one warp: lane 3c + i
+// computes row i of candidate c.  Same operations in the same order as se3_expmap_gtsam_hd + isometry_mul_hd (se3_math.cuh)
+// for every matrix entry (the rows of R, t and of the product are independent of each other), so the poses are
+// bit-identical to the serial code; the serial version cost ~3 us of every Nelder-Mead batch on one lane.
+static __device__ __noinline__ void pk_poses_of_candidates(PkShared& sh, int n_cand, int lane) {
+  const int c = lane / 3, i = lane - 3 * c;
+  const bool active = c < n_cand;
+  double* Erow = &sh.parts[0];  // scratch [8][3][4]: rows of E = Expmap(x) (sh.parts is free between the score sum and the next batch)
+  if (active) {
+    const double* xi = &sh.nm.cand[c][1];
+    const xd w[3] = {xd(xi[0]), xd(xi[1]), xd(xi[2])};
+    const xd v[3] = {xd(xi[3]), xd(xi[4]), xd(xi[5])};
+    const xd theta2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
+    const xd zero(0.0);
+    const xd W[3][3] = {{zero, -w[2], w[1]}, {w[2], zero, -w[0]}, {-w[1], w[0], zero}};
+    xd Ri[3], ti;
+    if (theta2.v <= DBL_EPSILON) {  // nearZero: R = I + W, t = v
 #pragma unroll
-  for (int r = 0; r < 3; r++) {
+      for (int j = 0; j < 3; j++) {
+        xd e(0.0);
 #pragma unroll
-    for (int c = 0; c < 4; c++) sh.pose64[k][4 * r + c] = T[r + 4 * c];
-    sh.pose32[k][r] = make_float4(static_cast<float>(T[r]), static_cast<float>(T[r + 4]), static_cast<float>(T[r + 8]), static_cast<float>(T[r + 12]));
-    tmax = fmax(tmax, fabs(T[r + 12]));
+        for (int r = 0; r < 3; r++)
+          if (r == i) e = W[r][j] + xd(r == j ? 1.0 : 0.0);
+        Ri[j] = e;
+      }
+      ti = i == 0 ? v[0] : (i == 1 ? v[1] : v[2]);
+    } else {
+      const xd theta = xsqrt(theta2);
+      const xd sin_theta(sin(theta.v));
+      const xd s2(sin((theta / xd(2.0)).v));
+      const xd one_minus_cos = xd(2.0) * s2 * s2;
+      xd K[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) K[r][j] = W[r][j] / theta;
+      xd Krow[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) Krow[j] = i == 0 ? K[0][j] : (i == 1 ? K[1][j] : K[2][j]);
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const xd KKij = Krow[0] * K[0][j] + Krow[1] * K[1][j] + Krow[2] * K[2][j];
+        Ri[j] = xd(i == j ? 1.0 : 0.0) + sin_theta * Krow[j] + one_minus_cos * KKij;
+      }
+      const xd wv = (w[0] * v[0] + w[1] * v[1]) + w[2] * v[2];
+      const xd cr[3] = {w[1] * v[2] - w[2] * v[1], w[2] * v[0] - w[0] * v[2], w[0] * v[1] - w[1] * v[0]};
+      const xd Rc = Ri[0] * cr[0] + Ri[1] * cr[1] + Ri[2] * cr[2];
+      const xd ci = i == 0 ? cr[0] : (i == 1 ? cr[1] : cr[2]);
+      const xd wi = i == 0 ? w[0] : (i == 1 ? w[1] : w[2]);
+      ti = (ci - Rc + wi * wv) / theta2;
+    }
+    double* e = Erow + (c * 3 + i) * 4;
+    e[0] = Ri[0].v, e[1] = Ri[1].v, e[2] = Ri[2].v, e[3] = ti.v;
   }
-  sh.pose32[k][3] = make_float4(nextafterf(static_cast<float>(tmax), INFINITY), 0.f, 0.f, 0.f);  // max|t| rounded up
+  __syncwarp();
+  if (active) {
+    // row i of init_T * E:  linear = Ra Rb, translation = Ra tb + ta   (isometry_mul_hd)
+    const double* E0 = Erow + (c * 3) * 4;
+    const xd a0(sh.init_T[i]), a1(sh.init_T[i + 4]), a2(sh.init_T[i + 8]), a3(sh.init_T[i + 12]);
+    double T[4];
+#pragma unroll
+    for (int j = 0; j < 3; j++) T[j] = (a0 * xd(E0[j]) + a1 * xd(E0[4 + j]) + a2 * xd(E0[8 + j])).v;
+    T[3] = ((a0 * xd(E0[3]) + a1 * xd(E0[7]) + a2 * xd(E0[11])) + a3).v;
+#pragma unroll
+    for (int j = 0; j < 4; j++) sh.pose64[c][4 * i + j] = T[j];
+    sh.pose32[c][i] = make_float4(static_cast<float>(T[0]), static_cast<float>(T[1]), static_cast<float>(T[2]), static_cast<float>(T[3]));
+  }
+  __syncwarp();
+  if (active && i == 0) {
+    const double tmax = fmax(fmax(fabs(sh.pose64[c][3]), fabs(sh.pose64[c][7])), fabs(sh.pose64[c][11]));
+    sh.pose32[c][3] = make_float4(nextafterf(static_cast<float>(tmax), INFINITY), 0.f, 0.f, 0.f);  // max|t| rounded up
+  }
+  __syncwarp();
 }
 
 // pose-list mode: pose k of the chunk from its row-major 3x4 doubles
@@ -618,6 +683,34 @@ __device__ __forceinline__ void pk_load_tile(const float4* __restrict__ pts, uns
   }
 }
 
+// points [tpos, end) of the cloud: K-row tiles with the next tile's rows in flight, then single-row tiles for the rest;
+// qk holds the first K-row tile when `first_loaded`
+template <int MODEL, int K, int ATOM>
+__device__ __forceinline__ void pk_range(const PkArgs& a, const PkShared& sh, const PkBagRegs& B, int n_poses, PkWarp& w, unsigned int tpos, unsigned int end, float4 (&qk)[K], bool first_loaded) {
+  const int lane = w.lane;
+  if (!first_loaded && tpos + 32u * K <= end) pk_load_tile<K>(B.points, tpos, end, lane, qk);
+  while (tpos + 32u * K <= end) {
+    float4 nxt[K];
+    const bool more = tpos + 64u * K <= end;
+    if (more) pk_load_tile<K>(B.points, tpos + 32u * K, end, lane, nxt);
+    pk_tile<MODEL, K, false, ATOM>(a, sh, B, n_poses, w, tpos, end, qk);
+    tpos += 32u * K;
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < K; j++) qk[j] = nxt[j];
+    }
+  }
+  float4 q1[1], n1[1];
+  if (tpos < end) pk_load_tile<1>(B.points, tpos, end, lane, q1);
+  while (tpos < end) {
+    const bool more = tpos + 32u < end;
+    if (more) pk_load_tile<1>(B.points, tpos + 32u, end, lane, n1);
+    pk_tile<MODEL, 1, true, ATOM>(a, sh, B, n_poses, w, tpos, end, q1);
+    tpos += 32u;
+    if (more) q1[0] = n1[0];
+  }
+}
+
 __device__ __forceinline__ void pk_stamp(const PkArgs& a, unsigned long long batch, int slot) {
   if (a.stamps && batch < static_cast<unsigned long long>(a.stamps_cap)) a.stamps[batch * PK_STAMP_SLOTS + slot] = global_ns();
 }
@@ -668,7 +761,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     for (int i = t; i < static_cast<int>(sizeof(NmMachine) / 8); i += PK_THREADS) dst[i] = src[i];
     if (t < 16) sh.init_T[t] = a.solve->init_T[t];
     __syncthreads();
-    if (t < sh.nm.n_cand) pk_pose_of_candidate(sh, t);
+    if (warp == 0) pk_poses_of_candidates(sh, sh.nm.n_cand, lane);
     if (t == 0) sh.n_poses = sh.nm.n_cand;
   } else {
     const int pc = min(a.chunk, a.n_total);
@@ -687,6 +780,11 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     if (n_poses == 0) break;
     const int buf = static_cast<int>(batch & 1ull);
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 0);
+    // pose-list mode runs ahead of the finalizers: buffer `buf` (accumulators, tile counter) must have been finalized for
+    // chunk batch - 2 first.  (Nelder-Mead mode: seeing the scores of batch - 1 already implies it.)
+    if (!solve_mode && batch >= 2) {
+      if (!pk_wait_counter(a, sh, a.fin_done + buf, static_cast<unsigned int>((batch >> 1) * static_cast<unsigned long long>(n_items_per_batch)))) return;
+    }
     const bool time_block = a.block_times != nullptr && batch == static_cast<unsigned long long>(a.block_times_batch) && t == 0;
     if (time_block) a.block_times[4 * blockIdx.x + 0] = global_ns();
     if (t == 0) {
@@ -694,36 +792,46 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       for (int p = 0; p < n_poses; p++) tm = fmaxf(tm, sh.pose32[p][3].x);
       sh.tmax = tm;
     }
-    // ---- (A) histograms of this block's slice -----------------------------------------------------------------------
+    // ---- (A) histograms of this block's share of the cloud ----------------------------------------------------------
     const int per_copy = n_poses * a.nb;
     w.hist_addr = smem_base + 4u * static_cast<unsigned int>((warp % a.copies) * per_copy);
+    // Static split (small clouds): the warp's fixed slice, its first tile in flight while the copies are zeroed.
+    // Dynamic split (large clouds): warps claim tiles of PK_TILE_ROWS * 32 * K points from a per-bag counter, so that a
+    // block whose points cost more (deferred rechecks, rejected rows) does not hold the whole grid back -- at C3 the slowest
+    // block of the static split finished its slice 33 % after the fastest.  The next claim is in flight while the current
+    // tile is processed.
+    const bool dynamic = a.dynamic_tiles != 0;
     float4 qk[K];
-    unsigned int tpos = begin;
-    const bool first_full = has_work && tpos + 32u * K <= end;
-    if (first_full) pk_load_tile<K>(B.points, tpos, end, lane, qk);  // in flight while the copies are zeroed
+    bool preloaded = !dynamic && has_work && begin + 32u * K <= end;
+    if (preloaded) pk_load_tile<K>(B.points, begin, end, lane, qk);
     for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
     __syncthreads();
     if (time_block) a.block_times[4 * blockIdx.x + 1] = global_ns();
-    if (has_work) {
-      while (tpos + 32u * K <= end) {
-        float4 nxt[K];
-        const bool more = tpos + 64u * K <= end;
-        if (more) pk_load_tile<K>(B.points, tpos + 32u * K, end, lane, nxt);
-        pk_tile<MODEL, K, false, ATOM>(a, sh, B, n_poses, w, tpos, end, qk);
-        tpos += 32u * K;
-        if (more) {
-#pragma unroll
-          for (int j = 0; j < K; j++) qk[j] = nxt[j];
-        }
+    {
+      constexpr unsigned int TILE = 32u * K * PK_TILE_ROWS;
+      const unsigned int n_tiles = (bag_n + TILE - 1u) / TILE;
+      unsigned int* ctr = a.tile_next + buf * PK_MAX_BAGS + bag;
+      unsigned int cur = 0;
+      if (dynamic) {
+        if (lane == 0) cur = atomicAdd(ctr, 1u);
+        cur = __shfl_sync(0xffffffffu, cur, 0);
       }
-      float4 q1[1], n1[1];
-      if (tpos < end) pk_load_tile<1>(B.points, tpos, end, lane, q1);
-      while (tpos < end) {
-        const bool more = tpos + 32u < end;
-        if (more) pk_load_tile<1>(B.points, tpos + 32u, end, lane, n1);
-        pk_tile<MODEL, 1, true, ATOM>(a, sh, B, n_poses, w, tpos, end, q1);
-        tpos += 32u;
-        if (more) q1[0] = n1[0];
+      bool more_ranges = dynamic ? cur < n_tiles : has_work;
+      while (more_ranges) {
+        unsigned int pending = 0, rb = begin, re = end;
+        if (dynamic) {
+          if (lane == 0) pending = atomicAdd(ctr, 1u);
+          rb = cur * TILE;
+          re = min(bag_n, rb + TILE);
+        }
+        pk_range<MODEL, K, ATOM>(a, sh, B, n_poses, w, rb, re, qk, preloaded);
+        preloaded = false;
+        if (dynamic) {
+          cur = __shfl_sync(0xffffffffu, pending, 0);
+          more_ranges = cur < n_tiles;
+        } else {
+          more_ranges = false;
+        }
       }
     }
     if (w.qn > 0) {
@@ -734,11 +842,6 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     __syncthreads();
     if (time_block) a.block_times[4 * blockIdx.x + 2] = global_ns();
     // ---- merge into the global accumulators -----------------------------------------------------------------------------
-    // pose-list mode runs ahead of the finalizers: buffer `buf` must have been finalized (zeroed) for batch - 2 first.
-    // (Nelder-Mead mode: seeing the scores of batch - 1 already implies it.)
-    if (!solve_mode && batch >= 2) {
-      if (!pk_wait_counter(a, sh, a.fin_done + buf, static_cast<unsigned int>((batch >> 1) * static_cast<unsigned long long>(n_items_per_batch)))) return;
-    }
     {
       int* g = a.ghist + (static_cast<size_t>(buf) * a.n_bags + bag) * PK_MAX_POSES * a.nb;
       for (int k = t; k < per_copy; k += PK_THREADS) {
@@ -762,6 +865,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       const unsigned int expected = static_cast<unsigned int>(((batch >> 1) + 1ull) * static_cast<unsigned long long>(a.bag[ib].block_count));
       if (!pk_wait_counter(a, sh, a.arrive + buf * PK_MAX_BAGS + ib, expected)) return;
       if (item == 0 && t == 0) pk_stamp(a, batch, 3);
+      if (ip == 0 && t == 0) a.tile_next[buf * PK_MAX_BAGS + ib] = 0u;  // every block of the bag is past its claims: ready for batch + 2
       int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
       int* ho = (a.hist_out && ib == 0) ? a.hist_out + (static_cast<size_t>(batch) * a.chunk + ip) * a.nb : nullptr;
       const double nid = pk_block_nid(sh, g, a.nb, a.bins, ho, smem_hist);
@@ -849,7 +953,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
         }
       }
       const int n_next = sh.nm.n_cand;  // 0 when finished
-      if (lane < n_next) pk_pose_of_candidate(sh, lane);
+      pk_poses_of_candidates(sh, n_next, lane);
       if (lane == 0) sh.n_poses = n_next;
     }
     __syncthreads();
