@@ -75,6 +75,7 @@ struct LeanVerdict {
   bool accept;     // the reference certainly counts this point at pixel `idx`
   bool uncertain;  // within the error bound of a decision edge: ask the exact path
   int idx;         // iy * W + ix, meaningful when accept
+  int ixb, iyb;    // ix + LEAN_MAGIC_BITS, iy + LEAN_MAGIC_BITS (the rounded coordinates as they come out of the magic add)
 };
 
 #define LEAN_RCP(x) VL_RCPF(x)
@@ -107,6 +108,7 @@ VL_HD LeanVerdict lean_tail(const LeanCam& c, int width, float up, float vp, flo
   // truncation toward zero: rint(u') == -1 (u in (-1, 0)) is column 0
   const int ixb = max(LEAN_F2I(tx), LEAN_MAGIC_BITS), iyb = max(LEAN_F2I(ty), LEAN_MAGIC_BITS);
   v.idx = iyb * width + ixb - c.idx_bias;
+  v.ixb = ixb, v.iyb = iyb;
   return v;
 }
 

@@ -979,6 +979,12 @@ int vlcal_nid_debug_solve_stamps(vlcal_nid_ctx* ctx, int capacity, uint64_t* sta
   return VLCAL_OK;
 }
 
+int vlcal_nid_debug_tma_stats(vlcal_nid_ctx* ctx, uint64_t stats[2]) {
+  if (!ctx || !stats) return VLCAL_ERR_INVALID_ARGUMENT;
+  stats[0] = ctx->pk_tma_stats[0], stats[1] = ctx->pk_tma_stats[1];
+  return VLCAL_OK;
+}
+
 int vlcal_nid_debug_block_times(vlcal_nid_ctx* ctx, int capacity_blocks, uint64_t* times_out, int* n_blocks) {
   if (!ctx || capacity_blocks < 0 || !times_out || !n_blocks) return VLCAL_ERR_INVALID_ARGUMENT;
   const int have = static_cast<int>(ctx->pk_block_times.size() / 4);

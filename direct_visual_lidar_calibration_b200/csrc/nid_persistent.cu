@@ -4,6 +4,8 @@
 // (CostCalculatorNID::calculate per pose, src/vlcal/calib/cost_calculator_nid.cpp:21-67) in ONE launch.
 #include "nid_persistent.cuh"
 
+#include <cuda.h>  // CUtensorMap + cuTensorMapEncodeTiled's signature (resolved through cudaGetDriverEntryPoint: no libcuda link)
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -33,6 +35,51 @@ static PkKernel pk_pick_ka(int k, int atom) {
   return atom ? nid_persistent_kernel<MODEL, 2, 1> : nid_persistent_kernel<MODEL, 2, 0>;
 }
 
+static int pk_tma_requested() {
+  static const int v = [] {
+    const char* e = std::getenv("VLCAL_PK_TMA");
+    return e ? std::atoi(e) : 0;  // A/B on B200 (profiles/): the staged window does not pay for its index arithmetic -> off
+  }();
+  return v;
+}
+
+// TMA variant: instantiated for the C2 shape only (plumb_bob, 2 points per lane, merged increments)
+static PkKernel pk_pick_tma(int model, int k) {
+  if (model == CAM_PLUMB_BOB && k == 2) return nid_persistent_kernel<CAM_PLUMB_BOB, 2, 0, true>;
+  return nullptr;
+}
+
+// tensor map of an image-bin plane: u8, W x H, tight rows, box 256 x 1, out-of-bounds bytes read as zero
+static int pk_make_tensor_map(const uint8_t* img, int width, int height, PkTensorMap* out) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) {
+    set_last_error("cuTensorMapEncodeTiled is not available from this driver");
+    return VLCAL_ERR_UNSUPPORTED;
+  }
+  static_assert(sizeof(CUtensorMap) == sizeof(PkTensorMap), "CUtensorMap is 128 bytes");
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(height)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(width)};  // bytes between rows (multiple of 16: checked by the caller)
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(PK_TMA_BOX_W), 1u};
+  const cuuint32_t estride[2] = {1u, 1u};
+  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(img), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    return VLCAL_ERR_CUDA;
+  }
+  std::memcpy(out, &m, sizeof(m));
+  return VLCAL_OK;
+}
+
 static PkKernel pk_pick(int model, int k) {
   static const int atom = [] {
     const char* e = std::getenv("VLCAL_PK_ATOM");
@@ -58,17 +105,18 @@ struct PkGeom {
 static std::mutex g_pk_mu;
 static std::map<std::tuple<int, const void*, size_t>, int> g_pk_occupancy;
 
-static int pk_geometry(int device, int num_sms, PkKernel kernel, int nb, PkGeom* g) {
+static int pk_geometry(int device, int num_sms, PkKernel kernel, int nb, PkGeom* g, bool tma = false) {
   // histogram copies for 8 poses (the initial simplex of a 6-D solve is 7) -- two copies while they fit 64 KB
   const size_t per_copy = static_cast<size_t>(PK_MAX_POSES) * nb * sizeof(int);
   g->copies = static_cast<int>(std::max<size_t>(1, std::min<size_t>(PK_WARPS / 4, (64 * 1024) / per_copy)));  // one copy per four warps
   const size_t scratch = static_cast<size_t>(nb) * 8 + 64 * 8 * 2 + 64 * 4 * 2;  // pk_block_nid staging (aliases the copies)
   g->smem = std::max(per_copy * g->copies, scratch);
+  if (tma) g->smem = ((g->smem + 127) & ~static_cast<size_t>(127)) + PK_TMA_BYTES;
   std::lock_guard<std::mutex> lock(g_pk_mu);
   const auto key = std::make_tuple(device, reinterpret_cast<const void*>(kernel), g->smem);
   auto it = g_pk_occupancy.find(key);
   if (it == g_pk_occupancy.end()) {
-    VL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(100 * 1024)));
+    VL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(128 * 1024)));
     int nblk = 0;
     VL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kernel, PK_THREADS, g->smem));
     it = g_pk_occupancy.emplace(key, std::max(1, nblk)).first;
@@ -86,13 +134,21 @@ static unsigned long long pk_timeout_ns() {
   return v;
 }
 
+// Points per lane and tile (K).  A warp's static slice is rounded up to whole K-row tiles, so K = 4 only pays when that
+// rounding wastes little (at C2, 188 points per warp: K = 4 would run 256-point slices on 73 % of the warps and idle the
+// rest; K = 2 runs 192-point slices on all of them).  Large clouds (dynamic split) and the models with transcendental
+// calls take K = 2: lighter register footprint, 3 blocks per SM without spills in the hot loop.
 static int pk_points_per_lane(const vlcal_nid_ctx* ctx, long long total_points) {
   if (const char* e = std::getenv("VLCAL_PK_KPT")) return std::atoi(e) == 4 ? 4 : 2;
   if (ctx->variant == 2) return 2;
   if (ctx->variant == 3) return 4;
   const bool heavy = ctx->cam.model == CAM_FISHEYE || ctx->cam.model == CAM_EQUIRECTANGULAR || ctx->cam.model == CAM_ATAN;
-  const long long points_per_warp = total_points / (static_cast<long long>(ctx->num_sms) * 2 * PK_WARPS);
-  return (!heavy && points_per_warp >= 96 && points_per_warp <= 1100) ? 4 : 2;
+  if (heavy) return 2;
+  const long long warps = static_cast<long long>(ctx->num_sms) * PK_MIN_BLOCKS * PK_WARPS;
+  const long long ppw = (total_points + warps - 1) / warps;
+  if (ppw >= 768) return 2;  // dynamic split
+  const long long r4 = (ppw + 127) / 128 * 128, r2 = (ppw + 63) / 64 * 64;
+  return (r4 == r2 && ppw >= 128) ? 4 : 2;
 }
 
 bool pk_supported(vlcal_nid_ctx* const* ctxs, int n_ctxs) {
@@ -122,7 +178,7 @@ struct PinBuf {
 
 // device scratch of one launch, one allocation, zeroed by one memset
 struct PkScratchLayout {
-  size_t ghist, arrive, fin_done, tile_next, abort_flag, seq, box, solve, total;
+  size_t ghist, arrive, fin_done, tile_next, abort_flag, seq, tma_stats, box, solve, total;
   PkScratchLayout(int n_bags, int nb) {
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -136,6 +192,7 @@ struct PkScratchLayout {
     tile_next = take(sizeof(unsigned int) * 2 * PK_MAX_BAGS);
     abort_flag = take(sizeof(unsigned int));
     seq = take(sizeof(unsigned long long));
+    tma_stats = take(sizeof(unsigned long long) * 2);
     box = take(sizeof(PkMailbox));
     solve = take(sizeof(PkSolve));
     total = o;
@@ -206,10 +263,15 @@ int pk_solve(
   VL_CUDA(cudaSetDevice(c0->device));
   long long total_points = 0;
   for (int i = 0; i < n_ctxs; i++) total_points += ctxs[i]->cloud->n;
-  PkKernel kernel = pk_pick(c0->cam.model, pk_points_per_lane(c0, total_points));
+  const int kpt = pk_points_per_lane(c0, total_points);
+  PkKernel kernel = pk_pick(c0->cam.model, kpt);
+  // TMA variant (A/B): image windows staged in shared memory; needs 16-byte row pitches and 128-byte aligned histogram copies
+  const size_t hist_bytes = static_cast<size_t>(std::max<size_t>(1, std::min<size_t>(PK_WARPS / 4, (64 * 1024) / (static_cast<size_t>(PK_MAX_POSES) * c0->bins * c0->bins * 4)))) * PK_MAX_POSES * c0->bins * c0->bins * 4;
+  const bool use_tma = pk_tma_requested() != 0 && pk_pick_tma(c0->cam.model, kpt) != nullptr && c0->image->width % 16 == 0 && hist_bytes % 128 == 0;
+  if (use_tma) kernel = pk_pick_tma(c0->cam.model, kpt);
   PkGeom g;
   {
-    const int rc = pk_geometry(c0->device, c0->num_sms, kernel, c0->bins * c0->bins, &g);
+    const int rc = pk_geometry(c0->device, c0->num_sms, kernel, c0->bins * c0->bins, &g, use_tma);
     if (rc != VLCAL_OK) return rc;
   }
   const int grid = pk_grid_size(g, ctxs, n_ctxs);
@@ -255,6 +317,13 @@ int pk_solve(
   PkArgs a;
   pk_fill_common(a, ctxs, n_ctxs, g, grid, sp, L);
   a.solve = reinterpret_cast<const PkSolve*>(sp + L.solve);
+  if (use_tma) {
+    for (int i = 0; i < n_ctxs; i++) {
+      const int rc = pk_make_tensor_map(ctxs[i]->d_bin_image, c0->image->width, c0->image->height, &a.tmap[i]);
+      if (rc != VLCAL_OK) return rc;
+    }
+    a.tma_stats = reinterpret_cast<unsigned long long*>(sp + L.tma_stats);
+  }
   a.result_host = h_result;
   a.trace_host = h_trace;
   a.trace_cap = trace_cap;
@@ -330,6 +399,7 @@ int pk_solve(
   }
   // scratch goes back to the pool: the kernel has published its last word, nothing else is enqueued on it
   VL_CUDA(cudaStreamSynchronize(c0->stream));
+  if (use_tma) VL_CUDA(cudaMemcpy(c0->pk_tma_stats, sp + L.tma_stats, sizeof(c0->pk_tma_stats), cudaMemcpyDeviceToHost));
 
   const NmMachine& fin = h_result->nm;
   // the objective's side effects in the reference's evaluation order (:112-116)

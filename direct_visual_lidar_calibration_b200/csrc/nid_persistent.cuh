@@ -24,6 +24,7 @@
 // Several bags per GPU: the grid is partitioned over the bags in proportion to their sizes (one tail for all bags).
 #pragma once
 
+#include <climits>
 #include <cstdint>
 
 #include "exact_classify.cuh"
@@ -43,7 +44,14 @@ constexpr int PK_MAX_WORDS = 256;  // world x bags x 8 score words per batch, on
 constexpr int PK_QUEUE = 64;
 constexpr int PK_MAX_BINS = 32;    // nb <= 1024: the finalizing block keeps its share of the joint histogram in registers
 constexpr int PK_STAMP_SLOTS = 8;
-constexpr unsigned int PK_TILE_ROWS = 4;  // dynamic split: a claim is PK_TILE_ROWS tiles of 32 * K points
+constexpr unsigned int PK_TILE_ROWS = 4;
+// TMA variant (A/B, VLCAL_PK_TMA=1): the block's window of the image-bin plane staged in shared memory once per solve
+constexpr int PK_TMA_BYTES = 48 * 1024;  // shared memory of the window
+constexpr int PK_TMA_BOX_W = 256;        // one TMA box = 256 x 1 bytes of a row (boxes of a row are contiguous in shared memory)
+constexpr int PK_TMA_HALO = 12;          // pixels around the bounding box of the block's points at the start pose
+struct alignas(64) PkTensorMap {         // a CUtensorMap (cuTensorMapEncodeTiled), opaque here
+  unsigned long long opaque[16];
+};  // dynamic split: a claim is PK_TILE_ROWS tiles of 32 * K points
 #ifndef PK_MIN_BLOCKS
 #define PK_MIN_BLOCKS 3  // blocks per SM the register allocation must allow (<= 85 registers per thread)
 #endif
@@ -76,6 +84,7 @@ struct PkResult {
 };
 
 struct PkArgs {
+  PkTensorMap tmap[PK_MAX_BAGS];  // TMA variant: tensor map of each bag's image-bin plane (u8, W x H, box 256 x 1)
   // camera + image geometry (shared by all bags of the launch: one camera, equal image sizes)
   int width, height, bins, nb;
   double cos_fov;
@@ -111,6 +120,7 @@ struct PkArgs {
   unsigned long long done_seq;
   unsigned long long* stamps;       // optional [cap][PK_STAMP_SLOTS] globaltimer stamps per batch
   int stamps_cap;
+  unsigned long long* tma_stats;    // TMA variant: [0] gathers served from the shared-memory window, [1] gathers that escaped it
   unsigned long long* block_times;  // optional [grid][4]: every block's {enter, hist zeroed, main loop done, arrived} stamps of batch block_times_batch
   int block_times_batch;
 };
@@ -129,6 +139,10 @@ struct PkShared {
   unsigned long long poses_scored;
   unsigned long long seq_base;
   int s_cnt[PK_WARPS];
+  // TMA variant: the staged window [box_h][box_w] of the image-bin plane (origin biased like LeanVerdict::ixb / iyb)
+  alignas(8) unsigned long long tma_bar;
+  int bb_min_x, bb_max_x, bb_min_y, bb_max_y;
+  int box_x0b, box_y0b, box_w, box_h;
   unsigned int q_idx[PK_WARPS][PK_QUEUE];
   unsigned char q_pose[PK_WARPS][PK_QUEUE];
 };
@@ -162,6 +176,16 @@ __device__ __forceinline__ int ldg_u8_or_neg(bool pred, const uint8_t* p) {
 __device__ __forceinline__ int ldg_u8_or_zero(bool pred, const uint8_t* p) {
   int v;
   asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tmov.u32 %0, 0;\n\t@q ld.global.nc.u8 %0, [%2];\n\t}" : "=r"(v) : "r"(static_cast<int>(pred)), "l"(p));
+  return v;
+}
+
+// TMA variant: the image bin from the staged window (shared memory) when the pixel lies inside it, from global memory
+// otherwise; `neg` = -1 (ATOM == 0: the sign is the "counted" flag) or 0
+__device__ __forceinline__ int gather_u8_window(bool in_window, bool outside, unsigned int smem_addr, const uint8_t* p, int neg) {
+  int v;
+  asm("{\n\t.reg .pred q, r;\n\tsetp.ne.b32 q, %1, 0;\n\tsetp.ne.b32 r, %2, 0;\n\tmov.u32 %0, %5;\n\t@q ld.shared.u8 %0, [%3];\n\t@r ld.global.nc.u8 %0, [%4];\n\t}"
+      : "=r"(v)
+      : "r"(static_cast<int>(in_window)), "r"(static_cast<int>(outside)), "r"(smem_addr), "l"(p), "r"(neg));
   return v;
 }
 
@@ -566,6 +590,11 @@ static __device__ __noinline__ double pk_block_nid(PkShared& sh, int* __restrict
 
 struct PkWarp {
   unsigned int hist_addr;  // shared-memory byte address of this warp's histogram copy [P][nb]
+  // TMA variant
+  unsigned int win_addr;   // shared-memory byte address of the staged image window
+  int win_x0b, win_y0b;
+  unsigned int win_w, win_h;
+  unsigned int n_window, n_escaped;
   unsigned int* q_idx;
   unsigned char* q_pose;
   int qn;
@@ -597,7 +626,7 @@ __device__ __noinline__ void pk_drain32(const PkArgs& a, const PkShared& sh, con
 // one tile = 32*K consecutive points starting at `tile`, swept over the P poses of the batch; the image-bin gathers of
 // pose p stay in flight while pose p+1 is classified and are consumed by the histogram increments one iteration later.
 // PARTIAL: the tile may reach past `end` (only the single-row tiles at the end of a warp's slice).
-template <int MODEL, int K, bool PARTIAL, int ATOM>
+template <int MODEL, int K, bool PARTIAL, int ATOM, bool TMA>
 __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, const PkBagRegs& B, int n_poses, PkWarp& w, unsigned int tile, unsigned int end, const float4 (&q)[K]) {
   float px[K], py[K], pz[K], dl[K];
   unsigned int lb[K];
@@ -616,7 +645,7 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
   unsigned int pend_off = 0;
   for (int p = 0; p <= n_poses; p++) {
     bool acc[K], unc[K];
-    int pix[K];
+    int pix[K], wx[K], wy[K];
     bool any_unc = false;
     if (p < n_poses) {
       const float4 r0 = sh.pose32[p][0], r1 = sh.pose32[p][1], r2 = sh.pose32[p][2];
@@ -627,6 +656,7 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
         acc[j] = PARTIAL ? (v.accept & valid0) : v.accept;
         unc[j] = PARTIAL ? (v.uncertain & valid0) : v.uncertain;
         pix[j] = v.idx;
+        if constexpr (TMA) wx[j] = v.ixb, wy[j] = v.iyb;
         any_unc = any_unc | unc[j];
       }
     }
@@ -642,7 +672,15 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
       pend_off = 4u * static_cast<unsigned int>(p * a.nb);
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        if constexpr (ATOM == 0) {
+        if constexpr (TMA) {
+          const unsigned int dx = static_cast<unsigned int>(wx[j] - w.win_x0b), dy = static_cast<unsigned int>(wy[j] - w.win_y0b);
+          const bool inw = acc[j] & (dx < w.win_w) & (dy < w.win_h);
+          const bool out = acc[j] & !inw;
+          pend_bin[j] = gather_u8_window(inw, out, w.win_addr + dy * w.win_w + dx, B.bin_image + pix[j], ATOM == 0 ? -1 : 0);
+          if constexpr (ATOM != 0) pend_inc[j] = acc[j] ? 1 : 0;
+          w.n_window += inw ? 1u : 0u;
+          w.n_escaped += out ? 1u : 0u;
+        } else if constexpr (ATOM == 0) {
           pend_bin[j] = ldg_u8_or_neg(acc[j], B.bin_image + pix[j]);
         } else {
           pend_bin[j] = ldg_u8_or_zero(acc[j], B.bin_image + pix[j]);
@@ -685,7 +723,7 @@ __device__ __forceinline__ void pk_load_tile(const float4* __restrict__ pts, uns
 
 // points [tpos, end) of the cloud: K-row tiles with the next tile's rows in flight, then single-row tiles for the rest;
 // qk holds the first K-row tile when `first_loaded`
-template <int MODEL, int K, int ATOM>
+template <int MODEL, int K, int ATOM, bool TMA>
 __device__ __forceinline__ void pk_range(const PkArgs& a, const PkShared& sh, const PkBagRegs& B, int n_poses, PkWarp& w, unsigned int tpos, unsigned int end, float4 (&qk)[K], bool first_loaded) {
   const int lane = w.lane;
   if (!first_loaded && tpos + 32u * K <= end) pk_load_tile<K>(B.points, tpos, end, lane, qk);
@@ -693,7 +731,7 @@ __device__ __forceinline__ void pk_range(const PkArgs& a, const PkShared& sh, co
     float4 nxt[K];
     const bool more = tpos + 64u * K <= end;
     if (more) pk_load_tile<K>(B.points, tpos + 32u * K, end, lane, nxt);
-    pk_tile<MODEL, K, false, ATOM>(a, sh, B, n_poses, w, tpos, end, qk);
+    pk_tile<MODEL, K, false, ATOM, TMA>(a, sh, B, n_poses, w, tpos, end, qk);
     tpos += 32u * K;
     if (more) {
 #pragma unroll
@@ -705,7 +743,7 @@ __device__ __forceinline__ void pk_range(const PkArgs& a, const PkShared& sh, co
   while (tpos < end) {
     const bool more = tpos + 32u < end;
     if (more) pk_load_tile<1>(B.points, tpos + 32u, end, lane, n1);
-    pk_tile<MODEL, 1, true, ATOM>(a, sh, B, n_poses, w, tpos, end, q1);
+    pk_tile<MODEL, 1, true, ATOM, TMA>(a, sh, B, n_poses, w, tpos, end, q1);
     tpos += 32u;
     if (more) q1[0] = n1[0];
   }
@@ -718,9 +756,9 @@ __device__ __forceinline__ void pk_stamp(const PkArgs& a, unsigned long long bat
 // stamps per batch: 0 block 0 enters the batch, 1 block 0 main loop done, 2 block 0 merged + arrived,
 //                   3 finalizer of item 0: all blocks arrived, 4 finalizer of item 0: score published,
 //                   5 block 0: all scores seen, 6 block 0: next poses ready
-template <int MODEL, int K, int ATOM>
+template <int MODEL, int K, int ATOM, bool TMA = false>
 __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kernel(const __grid_constant__ PkArgs a) {
-  extern __shared__ int smem_hist[];
+  extern __shared__ __align__(128) int smem_hist[];
   __shared__ PkShared sh;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const bool solve_mode = a.solve != nullptr;
@@ -772,8 +810,79 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     sh.seq_base = *a.seq_counter;
     sh.trace_count = 0;
     sh.poses_scored = 0ull;
+    sh.bb_min_x = sh.bb_min_y = INT_MAX;
+    sh.bb_max_x = sh.bb_max_y = INT_MIN;
+    sh.box_w = sh.box_h = 0;
   }
   __syncthreads();
+  w.win_addr = 0, w.win_x0b = w.win_y0b = 0, w.win_w = w.win_h = 0, w.n_window = w.n_escaped = 0;
+  if constexpr (TMA) {
+    // ---- stage this block's window of the image-bin plane once for the whole solve (static split, Nelder-Mead mode) ----
+    // bounding box of the block's points at the first candidate (= the start pose), grown by a halo for the poses the solve
+    // will visit; pixels outside the window fall back to the global gather (counted in tma_stats[1])
+    const unsigned int win_base = smem_base + 4u * static_cast<unsigned int>(a.copies * PK_MAX_POSES * a.nb);  // 128-byte aligned (host)
+    if (solve_mode && !a.dynamic_tiles) {
+      int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+      if (has_work) {
+        const float4 r0 = sh.pose32[0][0], r1 = sh.pose32[0][1], r2 = sh.pose32[0][2];
+        const float Pm[12] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, r1.w, r2.w};
+        const float tm = sh.pose32[0][3].x;
+        for (unsigned int i = begin + lane; i < end; i += 32u) {
+          const float4 q = __ldg(B.points + i);
+          const float dl = (5.25f * F32_U) * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + tm);
+          const LeanVerdict v = classify_lean<MODEL>(a.fast, a.lean, a.width, Pm, q.x, q.y, q.z, dl);
+          if (v.accept) mnx = min(mnx, v.ixb), mxx = max(mxx, v.ixb), mny = min(mny, v.iyb), mxy = max(mxy, v.iyb);
+        }
+      }
+      mnx = __reduce_min_sync(0xffffffffu, mnx), mny = __reduce_min_sync(0xffffffffu, mny);
+      mxx = __reduce_max_sync(0xffffffffu, mxx), mxy = __reduce_max_sync(0xffffffffu, mxy);
+      if (lane == 0 && mnx <= mxx) {
+        atomicMin(&sh.bb_min_x, mnx), atomicMax(&sh.bb_max_x, mxx);
+        atomicMin(&sh.bb_min_y, mny), atomicMax(&sh.bb_max_y, mxy);
+      }
+      __syncthreads();
+      const unsigned int bar = static_cast<unsigned int>(__cvta_generic_to_shared(&sh.tma_bar));
+      if (t == 0 && sh.bb_min_x <= sh.bb_max_x) {
+        const int x0 = ((sh.bb_min_x - LEAN_MAGIC_BITS) - PK_TMA_HALO) & ~15;  // pixel coordinates; may be negative: TMA zero-fills
+        const int x1 = (sh.bb_max_x - LEAN_MAGIC_BITS) + PK_TMA_HALO;
+        const int y0 = (sh.bb_min_y - LEAN_MAGIC_BITS) - PK_TMA_HALO;
+        const int y1 = (sh.bb_max_y - LEAN_MAGIC_BITS) + PK_TMA_HALO;
+        const int nbx = (x1 - x0 + PK_TMA_BOX_W) / PK_TMA_BOX_W;
+        int rows = y1 - y0 + 1;
+        if (nbx * PK_TMA_BOX_W <= PK_TMA_BYTES) {
+          rows = min(rows, PK_TMA_BYTES / (nbx * PK_TMA_BOX_W));
+          sh.box_x0b = x0 + LEAN_MAGIC_BITS, sh.box_y0b = y0 + LEAN_MAGIC_BITS;
+          sh.box_w = nbx * PK_TMA_BOX_W, sh.box_h = rows;
+          asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(static_cast<unsigned int>(rows * nbx * PK_TMA_BOX_W)) : "memory");
+          const unsigned long long tmap = reinterpret_cast<unsigned long long>(&a.tmap[bag]);
+          for (int r = 0; r < rows; r++) {
+            for (int bx = 0; bx < nbx; bx++) {
+              const unsigned int dst = win_base + static_cast<unsigned int>((r * nbx + bx) * PK_TMA_BOX_W);
+              asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tmap),
+                           "r"(x0 + bx * PK_TMA_BOX_W), "r"(y0 + r), "r"(bar)
+                           : "memory");
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (sh.box_w > 0) {  // every thread waits for the bytes (phase 0); bounded, so that a refused descriptor cannot hang the GPU
+        unsigned int done = 0;
+        for (int spin = 0; spin < (1 << 22) && !done; spin++) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+        }
+        if (!done) {
+          atomicExch(a.abort_flag, 1u);
+          if (a.error_host) *reinterpret_cast<volatile int*>(a.error_host) = 2;
+        }
+        w.win_addr = win_base, w.win_x0b = sh.box_x0b, w.win_y0b = sh.box_y0b;
+        w.win_w = static_cast<unsigned int>(sh.box_w), w.win_h = static_cast<unsigned int>(sh.box_h);
+      }
+    }
+  }
 
   for (unsigned long long batch = 0;; batch++) {
     const int n_poses = sh.n_poses;
@@ -824,7 +933,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
           rb = cur * TILE;
           re = min(bag_n, rb + TILE);
         }
-        pk_range<MODEL, K, ATOM>(a, sh, B, n_poses, w, rb, re, qk, preloaded);
+        pk_range<MODEL, K, ATOM, TMA>(a, sh, B, n_poses, w, rb, re, qk, preloaded);
         preloaded = false;
         if (dynamic) {
           cur = __shfl_sync(0xffffffffu, pending, 0);
@@ -960,6 +1069,15 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 6);
   }
 
+  if constexpr (TMA) {
+    if (a.tma_stats) {
+      const unsigned int nw = __reduce_add_sync(0xffffffffu, w.n_window), ne = __reduce_add_sync(0xffffffffu, w.n_escaped);
+      if (lane == 0) {
+        atomicAdd(a.tma_stats + 0, static_cast<unsigned long long>(nw));
+        atomicAdd(a.tma_stats + 1, static_cast<unsigned long long>(ne));
+      }
+    }
+  }
   // ---- results (block 0) ----
   if (blockIdx.x == 0) {
     if (solve_mode) {

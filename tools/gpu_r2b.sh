@@ -12,6 +12,7 @@ ALT=$PWD/direct_visual_lidar_calibration_b200/libvlcal_nid_alt.so
 VLCAL_LIB=$ALT timeout 300 python tools/pk_probe.py --config C2 --modes 3 --stamps --tag t768 >> gpurun_out/r2b_probe.jsonl 2>> gpurun_out/r2b_probe.err
 VLCAL_LIB=$ALT VLCAL_PK_KPT=2 timeout 300 python tools/pk_probe.py --config C2 --modes 3 --stamps --tag t768_kpt2 >> gpurun_out/r2b_probe.jsonl 2>> gpurun_out/r2b_probe.err
 VLCAL_LIB=$ALT timeout 600 python tools/pk_probe.py --config C3 --modes 3 --stamps --reps 3 --tag t768 >> gpurun_out/r2b_probe.jsonl 2>> gpurun_out/r2b_probe.err
+VLCAL_PK_TMA=1 VLCAL_PK_KPT=2 timeout 300 python tools/pk_probe.py --config C2 --modes 1,3 --stamps --tag tma_kpt2 >> gpurun_out/r2b_probe.jsonl 2>> gpurun_out/r2b_probe.err
 VLCAL_PK_DYNAMIC=0 timeout 600 python tools/pk_probe.py --config C3 --modes 3 --stamps --reps 3 --tag static >> gpurun_out/r2b_probe.jsonl 2>> gpurun_out/r2b_probe.err
 cat gpurun_out/r2b_probe.jsonl
 tail -5 gpurun_out/r2b_probe.err
