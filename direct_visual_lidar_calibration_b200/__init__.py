@@ -17,13 +17,14 @@ There is no CPU fallback: without the built library or without a CUDA device eve
 from ._lib import VlcalError, build_library, device_count, library_path, load_library, set_solver_mode
 from .camera import GenericCamera, create_camera
 from .cost import CostCalculatorNID, NIDCost, NIDCostParams, VisualLiDARData, score_poses
-from .culling import ViewCulling, ViewCullingParams
+from .culling import ViewCulling, ViewCullingParams, generate_lidar_image
 from .nelder_mead import NelderMead, NelderMeadParams
 from . import bfgs
 from .calibration import RegistrationType, VisualCameraCalibration, VisualCameraCalibrationParams, estimate_camera_fov, se3_expmap
 
 __all__ = [
     "score_poses",
+    "generate_lidar_image",
     "VlcalError", "build_library", "device_count", "library_path", "load_library", "set_solver_mode",
     "GenericCamera", "create_camera",
     "CostCalculatorNID", "NIDCost", "NIDCostParams", "VisualLiDARData",

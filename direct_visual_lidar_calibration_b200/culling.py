@@ -46,3 +46,25 @@ class ViewCulling:
         """Returns (points[idx], intensities[idx]) like FrameCPU sample() (frame_cpu.cpp:281-331)."""
         idx = self.cull_indices(points, T_camera_lidar)
         return np.asarray(points)[idx], np.asarray(intensities)[idx]
+
+
+def generate_lidar_image(proj: GenericCamera, image_size, T_camera_lidar, points, intensities, device: int = -1):
+    """vlcal::generate_lidar_image(proj, image_size=(W,H), T_camera_lidar, points) (src/vlcal/preprocess/generate_lidar_image.cpp:8-41)
+    -> (intensity image float64 (H,W), point-index map int32 (H,W)); identical to the reference's images."""
+    L = _lib.load_library()
+    pts = np.asarray(points, dtype=np.float64)
+    if pts.shape[1] == 3:
+        pts = np.concatenate([pts, np.ones((pts.shape[0], 1))], axis=1)
+    pts = np.ascontiguousarray(pts)
+    ins = np.ascontiguousarray(np.asarray(intensities, dtype=np.float64).reshape(-1))
+    W, H = int(image_size[0]), int(image_size[1])
+    inten = np.empty((H, W))
+    index = np.empty((H, W), dtype=np.int32)
+    T = T_to_colmajor(T_camera_lidar)
+    _lib.check(
+        L.vlcal_generate_lidar_image(
+            device, proj.model_id, _dp(proj.intrinsics), proj.intrinsics.size, _dp(proj.distortion), proj.distortion.size, W, H, _dp(T),
+            pts.ctypes.data, ins.ctypes.data, pts.shape[0], inten.ctypes.data, index.ctypes.data,
+        )
+    )
+    return inten, index

@@ -235,6 +235,27 @@ int vlcal_view_cull(
   int32_t* indices_out,
   int64_t* n_kept);
 
+/* ---- LiDAR intensity image: vlcal::generate_lidar_image (src/vlcal/preprocess/generate_lidar_image.cpp:8-41) ----------
+ * The rendering `preprocess` / `initial_guess_*` use: per pixel the projected point with the smallest squared range (of
+ * equal ones the last), same FoV / projection / truncation rules as the NID cost, FoV from estimate_camera_fov(camera,
+ * {width, height}).  intensity_image_out: H x W doubles (CV_64FC1; 0 where no point lands), index_image_out: H x W int32
+ * (CV_32SC1; -1 where no point lands).  Exact: both images equal the reference's bit for bit. */
+int vlcal_generate_lidar_image(
+  int device,
+  int camera_model,
+  const double* intrinsics,
+  int n_intrinsics,
+  const double* distortion,
+  int n_distortion,
+  int width,
+  int height,
+  const double T_camera_lidar[16],
+  const double* points_xyzw,
+  const double* intensities,
+  int64_t n_points,
+  double* intensity_image_out,
+  int32_t* index_image_out);
+
 /* ---- solver surface ------------------------------------------------------------------ */
 
 /* how vlcal_estimate_pose_nelder_mead* / vlcal_calibrate_nelder_mead iterate (process-wide):

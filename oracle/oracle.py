@@ -117,6 +117,10 @@ def lib():
         L.orc_nid_from_hist.restype = C.c_double
         L.orc_view_cull.argtypes = [C.POINTER(Camera), C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int64, dp, C.c_void_p]
         L.orc_view_cull.restype = C.c_int64
+        L.orc_generate_lidar_image.argtypes = [C.POINTER(Camera), C.c_int, C.c_int, dp, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_generate_lidar_image.restype = None
+        L.orc_set_bag_threads.argtypes = [C.c_int]
+        L.orc_set_bag_threads.restype = None
         L.orc_nid_cost_bspline.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, dp, dp, C.c_void_p]
         L.orc_nid_cost_bspline.restype = C.c_int
         L.orc_nid_cost_bspline_grad.argtypes = [C.POINTER(Camera), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, dp, dp, C.c_void_p, C.c_void_p]
@@ -248,6 +252,16 @@ def view_cull(cam, width, height, max_fov, enable_depth, points_xyzw, T):
     t = T_to_colmajor(T)
     m = lib().orc_view_cull(C.byref(cam), int(width), int(height), float(max_fov), int(bool(enable_depth)), pts.ctypes.data, pts.shape[0], _dp(t), idx.ctypes.data)
     return idx[:m].copy()
+
+
+def generate_lidar_image(cam, width, height, T, points_xyzw, intensities):
+    """generate_lidar_image (generate_lidar_image.cpp:8-41) -> (intensity image float64 (H,W), index map int32 (H,W))."""
+    pts, ins = _f64(points_xyzw).reshape(-1, 4), _f64(intensities).reshape(-1)
+    inten = np.empty((height, width))
+    index = np.empty((height, width), dtype=np.int32)
+    t = T_to_colmajor(T)
+    lib().orc_generate_lidar_image(C.byref(cam), int(width), int(height), _dp(t), pts.ctypes.data, ins.ctypes.data, pts.shape[0], inten.ctypes.data, index.ctypes.data)
+    return inten, index
 
 
 def nid_cost_bspline(cam, image_u8, points_xyzw, intensities, bins, T_params7):

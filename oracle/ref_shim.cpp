@@ -25,6 +25,7 @@
 #include <dfo/nelder_mead.hpp>
 #include <vlcal/calib/cost_calculator_nid.hpp>
 #include <vlcal/calib/view_culling.hpp>
+#include <vlcal/preprocess/generate_lidar_image.hpp>
 #include <vlcal/calib/visual_camera_calibration.hpp>
 #include <vlcal/common/estimate_fov.hpp>
 #include <vlcal/costs/nid_cost.hpp>
@@ -230,6 +231,20 @@ int ref_calibrate_nelder_mead(
     for (int r = 0; r < 4; r++) T_out[r + 4 * c] = T.matrix()(r, c);
   }
   *callback_count = count;
+  return 0;
+}
+
+// vlcal::generate_lidar_image (src/vlcal/preprocess/generate_lidar_image.cpp:8-41): intensity image (CV_64FC1) + index map (CV_32SC1)
+int ref_generate_lidar_image(void* cam, int width, int height, const double* T_colmajor, const double* points_xyzw, const double* intensities, int64_t n, double* intensity_out, int32_t* index_out) {
+  const RefCamera* rc = static_cast<const RefCamera*>(cam);
+  const auto frame = frame_over(points_xyzw, intensities, n);
+  const auto images = vlcal::generate_lidar_image(rc->proj, Eigen::Vector2i(width, height), isometry_from_colmajor(T_colmajor), frame);
+  for (int r = 0; r < height; r++) {
+    for (int c = 0; c < width; c++) {
+      intensity_out[static_cast<size_t>(r) * width + c] = images.first.at<double>(r, c);
+      index_out[static_cast<size_t>(r) * width + c] = images.second.at<std::int32_t>(r, c);
+    }
+  }
   return 0;
 }
 

@@ -41,6 +41,9 @@ public:
         } else if (type == CV_32SC1) {
           const int i = static_cast<int>(s.v[0]);
           std::memcpy(p, &i, 4);
+        } else if (type == CV_64FC1) {
+          const double d = s.v[0];
+          std::memcpy(p, &d, 8);
         } else {
           *p = static_cast<unsigned char>(s.v[0]);
         }

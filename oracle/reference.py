@@ -48,6 +48,8 @@ def lib():
         L.ref_nid_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_view_cull.restype = C.c_int64
         L.ref_view_cull.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.ref_generate_lidar_image.restype = C.c_int
+        L.ref_generate_lidar_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.ref_nid_cost_bspline.restype = C.c_int
         L.ref_nid_cost_bspline.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_calibrate_nelder_mead.restype = C.c_int
@@ -128,6 +130,16 @@ def view_cull(cam: Camera, width, height, enable_depth, points_xyzw, T) -> np.nd
     t = _colmajor(T)
     m = lib().ref_view_cull(cam.handle, int(width), int(height), int(bool(enable_depth)), pts.ctypes.data, pts.shape[0], t.ctypes.data, idx.ctypes.data)
     return idx[:m].copy()
+
+
+def generate_lidar_image(cam: Camera, width, height, T, points_xyzw, intensities):
+    """vlcal::generate_lidar_image(proj, {W,H}, T, points) -> (intensity image float64 (H,W), index map int32 (H,W))."""
+    pts, ins = _f64(points_xyzw).reshape(-1, 4), _f64(intensities).reshape(-1)
+    inten = np.empty((height, width))
+    index = np.empty((height, width), dtype=np.int32)
+    t = _colmajor(T)
+    lib().ref_generate_lidar_image(cam.handle, int(width), int(height), t.ctypes.data, pts.ctypes.data, ins.ctypes.data, pts.shape[0], inten.ctypes.data, index.ctypes.data)
+    return inten, index
 
 
 def nid_cost_bspline(cam: Camera, image_u8, points_xyzw, intensities, bins, T_params7):

@@ -664,6 +664,61 @@ double orc_nid_calculate_omp(
   return nid;
 }
 
+/* ----------------------------------------------------------------------------------------
+ * generate_lidar_image   src/vlcal/preprocess/generate_lidar_image.cpp:8-41
+ * LiDAR intensity image (CV_64FC1, 0 where no point lands) and point-index map (CV_32SC1, -1 where no point lands): per
+ * pixel the point with the smallest squared range wins; of several points with the SAME squared range the last one does
+ * (:31 skips only when the stored value is strictly smaller).
+ * ---------------------------------------------------------------------------------------- */
+void orc_generate_lidar_image(
+  const orc_camera* cam,
+  int width,
+  int height,
+  const double T[16],
+  const double* points_xyzw,
+  const double* intensities,
+  int64_t n,
+  double* intensity_image,
+  int32_t* index_image) {
+  const double camera_fov = orc_estimate_camera_fov(cam, width, height); /* :10 */
+  const double min_z = cos(camera_fov);                                  /* :11 */
+  const size_t npix = (size_t)width * (size_t)height;
+  double* sq_dist_image = (double*)malloc(sizeof(double) * (npix > 0 ? npix : 1));
+  for (size_t i = 0; i < npix; i++) { /* :13-15 */
+    sq_dist_image[i] = DBL_MAX;
+    intensity_image[i] = 0.0;
+    index_image[i] = -1;
+  }
+  for (int64_t i = 0; i < n; i++) { /* :17 */
+    const double* pt = points_xyzw + 4 * i;
+    double pc[3];
+    for (int r = 0; r < 3; r++) { /* :19 */
+      pc[r] = ((M4(T, r, 0) * pt[0] + M4(T, r, 1) * pt[1]) + M4(T, r, 2) * pt[2]) + M4(T, r, 3) * pt[3];
+    }
+    const double n2 = sqnorm3(pc); /* :21 head<3>().normalized().z() */
+    const double nz = n2 > 0.0 ? pc[2] / sqrt(n2) : pc[2];
+    if (nz < min_z) {
+      continue;
+    }
+    double uv[2];
+    orc_project(cam, pc, uv); /* :25 */
+    const int ix = orc_cast_int(uv[0]);
+    const int iy = orc_cast_int(uv[1]);
+    if (ix < 0 || iy < 0 || ix >= width || iy >= height) { /* :26-28 */
+      continue;
+    }
+    const double sq_dist = sqnorm3(pc); /* :30 */
+    const size_t p = (size_t)iy * (size_t)width + (size_t)ix;
+    if (sq_dist_image[p] < sq_dist) { /* :31-33 */
+      continue;
+    }
+    sq_dist_image[p] = sq_dist; /* :35-37 */
+    intensity_image[p] = intensities[i];
+    index_image[p] = (int32_t)i;
+  }
+  free(sq_dist_image);
+}
+
 /* ------------------------------------------------------------------------------------------
  * ViewCulling::cull   src/vlcal/calib/view_culling.cpp:21-92
  * ---------------------------------------------------------------------------------------- */

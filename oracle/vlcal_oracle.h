@@ -229,6 +229,10 @@ int orc_nid_cost_bspline_grad(
   double* grad_out,
   double* hist_out);
 
+/* generate_lidar_image (src/vlcal/preprocess/generate_lidar_image.cpp:8-41): intensity_image[H*W] doubles, index_image[H*W] */
+void orc_generate_lidar_image(
+  const orc_camera* cam, int width, int height, const double T[16], const double* points_xyzw, const double* intensities, int64_t n, double* intensity_image, int32_t* index_image);
+
 /* team size of the objective's OpenMP loop over bags (visual_camera_calibration.cpp:107): 0 = one thread per bag
  * (the reference's behaviour on a host with enough cores), 1 = serial.  Results do not depend on it. */
 void orc_set_bag_threads(int n);

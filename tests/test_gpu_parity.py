@@ -621,6 +621,21 @@ def test_persistent_exchange_two_ranks_on_one_gpu(gpu):
         assert "ranks_identical=True equals_single_process_one_launch=True equals_host_loop=True" in ln, ln
 
 
+@pytest.mark.parametrize("model", util.MODELS)
+def test_generate_lidar_image_equals_the_oracle(gpu, oracle, model):
+    """K5 (generate_lidar_image.cpp:8-41 on the GPU): intensity image and index map identical to the oracle's, incl. ties."""
+    for f32 in (True, False):
+        pr = util.random_problem(model, n=60000, seed=6, f32=f32)
+        pts = np.concatenate([pr["points"], pr["points"][:3000]])
+        ins = np.concatenate([pr["intensities"], (pr["intensities"][:3000] + 0.5) % 1.0])
+        cam = gpu.create_camera(model, pr["intrinsics"], pr["distortion"])
+        inten, index = gpu.generate_lidar_image(cam, (pr["W"], pr["H"]), pr["T"], pts, ins)
+        ocam = oracle.create_camera(model, pr["intrinsics"], pr["distortion"])
+        ref_inten, ref_index = oracle.generate_lidar_image(ocam, pr["W"], pr["H"], pr["T"], pts, ins)
+        assert np.array_equal(index, ref_index) and np.array_equal(inten, ref_inten)
+        assert (index >= 0).sum() > 1000 and (index >= 60000).sum() > 10
+
+
 def test_pose_grid_search_finds_the_basin(gpu, oracle):
     """Config-5 style coarse grid: every score equals the oracle's, and the best grid pose is the one nearest the truth."""
     from direct_visual_lidar_calibration_b200 import initial_guess as IG

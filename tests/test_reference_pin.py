@@ -342,3 +342,18 @@ def test_mode_b_golden_fixtures_match_reference_and_oracle(ref):
             assert ok_r and ok_o and nid_r == nid_o == g["nid_jet_functor"][k]
             assert np.array_equal(grad_r, g["grad"][k]) and np.array_equal(grad_o, g["grad"][k])
             assert ref.nid_cost_bspline(rc, g["image"], pts, ins, 16, tp)[1] == g["nid_double_functor"][k] == O.nid_cost_bspline(oc, g["image"], pts, ins, 16, tp)[1]
+
+
+@pytest.mark.parametrize("model", U.MODELS)
+def test_generate_lidar_image_equals_the_reference(model):
+    """generate_lidar_image (src/vlcal/preprocess/generate_lidar_image.cpp:8-41): the oracle's intensity image and index map
+    equal the reference's own code bit for bit, including the tie rule (of equal squared ranges the last point wins)."""
+    pr = U.random_problem(model, n=30000, seed=5)
+    pts = np.concatenate([pr["points"], pr["points"][:2000]])  # exact duplicates: equal squared ranges
+    ins = np.concatenate([pr["intensities"], (pr["intensities"][:2000] + 0.5) % 1.0])
+    cam = O.create_camera(model, pr["intrinsics"], pr["distortion"])
+    rcam = R.Camera(model, pr["intrinsics"], pr["distortion"])
+    a = O.generate_lidar_image(cam, pr["W"], pr["H"], pr["T"], pts, ins)
+    b = R.generate_lidar_image(rcam, pr["W"], pr["H"], pr["T"], pts, ins)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert (a[1] >= 30000).sum() > 100  # duplicates won their pixels
