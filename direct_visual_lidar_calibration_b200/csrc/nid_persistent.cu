@@ -134,21 +134,12 @@ static unsigned long long pk_timeout_ns() {
   return v;
 }
 
-// Points per lane and tile (K).  A warp's static slice is rounded up to whole K-row tiles, so K = 4 only pays when that
-// rounding wastes little (at C2, 188 points per warp: K = 4 would run 256-point slices on 73 % of the warps and idle the
-// rest; K = 2 runs 192-point slices on all of them).  Large clouds (dynamic split) and the models with transcendental
-// calls take K = 2: lighter register footprint, 3 blocks per SM without spills in the hot loop.
-static int pk_points_per_lane(const vlcal_nid_ctx* ctx, long long total_points) {
+// Points per lane and tile (K).  Tiles are dealt to the warps round-robin, so K = 4 (128-point tiles) needs a cloud large
+// enough for several tiles per warp to stay balanced -- and there the lighter register footprint of K = 2 (3 blocks per SM
+// without spills in the hot loop) measured faster anyway.  K = 4 remains as variant 3 / VLCAL_PK_KPT=4 for A/B runs.
+static int pk_points_per_lane(const vlcal_nid_ctx* ctx, long long /*total_points*/) {
   if (const char* e = std::getenv("VLCAL_PK_KPT")) return std::atoi(e) == 4 ? 4 : 2;
-  if (ctx->variant == 2) return 2;
-  if (ctx->variant == 3) return 4;
-  const bool heavy = ctx->cam.model == CAM_FISHEYE || ctx->cam.model == CAM_EQUIRECTANGULAR || ctx->cam.model == CAM_ATAN;
-  if (heavy) return 2;
-  const long long warps = static_cast<long long>(ctx->num_sms) * PK_MIN_BLOCKS * PK_WARPS;
-  const long long ppw = (total_points + warps - 1) / warps;
-  if (ppw >= 768) return 2;  // dynamic split
-  const long long r4 = (ppw + 127) / 128 * 128, r2 = (ppw + 63) / 64 * 64;
-  return (r4 == r2 && ppw >= 128) ? 4 : 2;
+  return ctx->variant == 3 ? 4 : 2;
 }
 
 bool pk_supported(vlcal_nid_ctx* const* ctxs, int n_ctxs) {
@@ -228,15 +219,6 @@ void pk_fill_common(PkArgs& a, vlcal_nid_ctx* const* ctxs, int n_ctxs, const PkG
   a.ghist = reinterpret_cast<int*>(scratch + L.ghist);
   a.arrive = reinterpret_cast<unsigned int*>(scratch + L.arrive);
   a.fin_done = reinterpret_cast<unsigned int*>(scratch + L.fin_done);
-  a.tile_next = reinterpret_cast<unsigned int*>(scratch + L.tile_next);
-  {  // dynamic split once a warp's share is a few claims long (below that the static slices are as balanced as tiles can be)
-    static const int force = [] {
-      const char* e = std::getenv("VLCAL_PK_DYNAMIC");
-      return e ? std::atoi(e) : -1;
-    }();
-    const long long per_warp = total_points / (static_cast<long long>(grid) * PK_WARPS);
-    a.dynamic_tiles = force >= 0 ? (force != 0) : (per_warp >= 768);
-  }
   a.abort_flag = reinterpret_cast<unsigned int*>(scratch + L.abort_flag);
   a.seq_counter = reinterpret_cast<unsigned long long*>(scratch + L.seq);
   a.box[0] = reinterpret_cast<PkMailbox*>(scratch + L.box);

@@ -51,7 +51,7 @@ constexpr int PK_TMA_BOX_W = 256;        // one TMA box = 256 x 1 bytes of a row
 constexpr int PK_TMA_HALO = 12;          // pixels around the bounding box of the block's points at the start pose
 struct alignas(64) PkTensorMap {         // a CUtensorMap (cuTensorMapEncodeTiled), opaque here
   unsigned long long opaque[16];
-};  // dynamic split: a claim is PK_TILE_ROWS tiles of 32 * K points
+};
 #ifndef PK_MIN_BLOCKS
 #define PK_MIN_BLOCKS 3  // blocks per SM the register allocation must allow (<= 85 registers per thread)
 #endif
@@ -108,8 +108,6 @@ struct PkArgs {
   int* ghist;                // [2][n_bags][8][nb]
   unsigned int* arrive;      // [2][PK_MAX_BAGS]
   unsigned int* fin_done;    // [2]
-  unsigned int* tile_next;   // [2][PK_MAX_BAGS] dynamic split: next unclaimed tile of the batch (zeroed again by the finalizer)
-  int dynamic_tiles;
   unsigned int* abort_flag;  // set by any block that timed out: everybody leaves
   PkMailbox* box[P2P_MAX_RANKS];  // box[r]: rank r's mailbox as mapped here (self included; world == 1: local scratch)
   int world, rank;
@@ -217,8 +215,9 @@ __device__ __forceinline__ void nm_warp_finish(NmMachine& s, int lane) {
   __syncwarp();
 }
 
+// M: compile-time bound of the simplex size m = n + 1 (7 for the 6-D pose solve; the generic instance covers n <= 8)
+template <int M>
 static __device__ void nm_warp_loop_top(NmMachine& s, int lane) {
-  constexpr int M = NM_MAX_N + 1;
   const int n = s.n, m = n + 1;
   if (s.it >= s.params.max_iterations) {
     nm_warp_finish(s, lane);
@@ -317,6 +316,11 @@ static __device__ void nm_warp_loop_top(NmMachine& s, int lane) {
   __syncwarp();
 }
 
+__device__ __forceinline__ void nm_warp_loop_top_dispatch(NmMachine& s, int lane) {
+  if (s.n == 6) nm_warp_loop_top<7>(s, lane);
+  else nm_warp_loop_top<NM_MAX_N + 1>(s, lane);
+}
+
 // consume the scores ys[0..n_cand) of the pending batch (one warp, all 32 lanes call)
 static __device__ __noinline__ void nm_warp_step(NmMachine& s, const double* ys, int lane) {
   const int n = s.n, m = n + 1;
@@ -335,7 +339,7 @@ static __device__ __noinline__ void nm_warp_step(NmMachine& s, const double* ys,
       __syncwarp();
       nm_warp_observe(s, lane, s.x[k], ys[k]);
     }
-    nm_warp_loop_top(s, lane);
+    nm_warp_loop_top_dispatch(s, lane);
   } else if (phase == 1) {
     const double f0 = s.x[0][0], fn1 = s.x[n - 1][0], fn = s.x[n][0];
     const double y0 = ys[0], y1 = ys[1], y2 = ys[2], y3 = ys[3];
@@ -382,7 +386,7 @@ static __device__ __noinline__ void nm_warp_step(NmMachine& s, const double* ys,
     if (!shrink) {
       if (lane == 0) s.it++;
       __syncwarp();
-      nm_warp_loop_top(s, lane);
+      nm_warp_loop_top_dispatch(s, lane);
     }
   } else if (phase == 2) {
     for (int j = 1; j < m; j++) {
@@ -392,7 +396,7 @@ static __device__ __noinline__ void nm_warp_step(NmMachine& s, const double* ys,
     }
     if (lane == 0) s.it++;
     __syncwarp();
-    nm_warp_loop_top(s, lane);
+    nm_warp_loop_top_dispatch(s, lane);
   }
   __syncwarp();
 }
@@ -428,11 +432,10 @@ static __device__ __noinline__ void pk_poses_of_candidates(PkShared& sh, int n_c
       const xd sin_theta(sin(theta.v));
       const xd s2(sin((theta / xd(2.0)).v));
       const xd one_minus_cos = xd(2.0) * s2 * s2;
-      xd K[3][3];
-#pragma unroll
-      for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) K[r][j] = W[r][j] / theta;
+      // K = W / theta entry by entry: the six non-zero entries are +-w_k / theta -- IEEE division is sign-symmetric, so three
+      // divisions give the same bits as the nine of the serial code -- and 0 / theta = +0
+      const xd k0 = w[0] / theta, k1 = w[1] / theta, k2 = w[2] / theta;
+      const xd K[3][3] = {{zero, -k2, k1}, {k2, zero, -k0}, {-k1, k0, zero}};
       xd Krow[3];
 #pragma unroll
       for (int j = 0; j < 3; j++) Krow[j] = i == 0 ? K[0][j] : (i == 1 ? K[1][j] : K[2][j]);
@@ -755,7 +758,7 @@ __device__ __forceinline__ void pk_stamp(const PkArgs& a, unsigned long long bat
 
 // stamps per batch: 0 block 0 enters the batch, 1 block 0 main loop done, 2 block 0 merged + arrived,
 //                   3 finalizer of item 0: all blocks arrived, 4 finalizer of item 0: score published,
-//                   5 block 0: all scores seen, 6 block 0: next poses ready
+//                   5 block 0: all scores seen, 7 block 0: Nelder-Mead machine stepped, 6 block 0: next poses ready
 template <int MODEL, int K, int ATOM, bool TMA = false>
 __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kernel(const __grid_constant__ PkArgs a) {
   extern __shared__ __align__(128) int smem_hist[];
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     // bounding box of the block's points at the first candidate (= the start pose), grown by a halo for the poses the solve
     // will visit; pixels outside the window fall back to the global gather (counted in tma_stats[1])
     const unsigned int win_base = smem_base + 4u * static_cast<unsigned int>(a.copies * PK_MAX_POSES * a.nb);  // 128-byte aligned (host)
-    if (solve_mode && !a.dynamic_tiles) {
+    if (solve_mode) {
       int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
       if (has_work) {
         const float4 r0 = sh.pose32[0][0], r1 = sh.pose32[0][1], r2 = sh.pose32[0][2];
@@ -904,44 +907,46 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     // ---- (A) histograms of this block's share of the cloud ----------------------------------------------------------
     const int per_copy = n_poses * a.nb;
     w.hist_addr = smem_base + 4u * static_cast<unsigned int>((warp % a.copies) * per_copy);
-    // Static split (small clouds): the warp's fixed slice, its first tile in flight while the copies are zeroed.
-    // Dynamic split (large clouds): warps claim tiles of PK_TILE_ROWS * 32 * K points from a per-bag counter, so that a
-    // block whose points cost more (deferred rechecks, rejected rows) does not hold the whole grid back -- at C3 the slowest
-    // block of the static split finished its slice 33 % after the fastest.  The next claim is in flight while the current
-    // tile is processed.
-    const bool dynamic = a.dynamic_tiles != 0;
-    float4 qk[K];
-    bool preloaded = !dynamic && has_work && begin + 32u * K <= end;
-    if (preloaded) pk_load_tile<K>(B.points, begin, end, lane, qk);
-    for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
-    __syncthreads();
-    if (time_block) a.block_times[4 * blockIdx.x + 1] = global_ns();
-    {
-      constexpr unsigned int TILE = 32u * K * PK_TILE_ROWS;
-      const unsigned int n_tiles = (bag_n + TILE - 1u) / TILE;
-      unsigned int* ctr = a.tile_next + buf * PK_MAX_BAGS + bag;
-      unsigned int cur = 0;
-      if (dynamic) {
-        if (lane == 0) cur = atomicAdd(ctr, 1u);
-        cur = __shfl_sync(0xffffffffu, cur, 0);
-      }
-      bool more_ranges = dynamic ? cur < n_tiles : has_work;
-      while (more_ranges) {
-        unsigned int pending = 0, rb = begin, re = end;
-        if (dynamic) {
-          if (lane == 0) pending = atomicAdd(ctr, 1u);
-          rb = cur * TILE;
-          re = min(bag_n, rb + TILE);
+    if constexpr (TMA) {
+      // TMA variant: contiguous slice per warp (its image window must be compact)
+      float4 qk[K];
+      const bool preloaded = has_work && begin + 32u * K <= end;
+      if (preloaded) pk_load_tile<K>(B.points, begin, end, lane, qk);
+      for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
+      __syncthreads();
+      if (time_block) a.block_times[4 * blockIdx.x + 1] = global_ns();
+      if (has_work) pk_range<MODEL, K, ATOM, TMA>(a, sh, B, n_poses, w, begin, end, qk, preloaded);
+    } else {
+      // Interleaved split: tile k (32 * K consecutive points of the tile-ordered cloud) goes to warp k mod W of the bag, so
+      // every warp -- and every block: its 8 warps take 8 neighbouring tiles per round -- samples the whole image instead of
+      // owning one region.  With contiguous slices the cost of a slice followed its region (deferred rechecks, histogram bin
+      // collisions, cache hit rates): the slowest block finished 35 % (C2) / 14 % (C3) after the median one, and every
+      // Nelder-Mead batch waits for the slowest.  (Claiming tiles from an atomic counter was measured too: no better than
+      // the contiguous split at 256-point claims -- one claim is ~20 us of work for a warp -- and finer claims serialise on
+      // the counter.)  The next tile's rows are in flight while the current one is swept over the poses.
+      constexpr unsigned int TP = 32u * K;
+      unsigned int tile = warp_global;
+      float4 qk[K];
+      bool full = static_cast<unsigned long long>(tile) * TP + TP <= bag_n;
+      if (full) pk_load_tile<K>(B.points, tile * TP, bag_n, lane, qk);
+      for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
+      __syncthreads();
+      if (time_block) a.block_times[4 * blockIdx.x + 1] = global_ns();
+      while (full) {
+        const unsigned int ntile = tile + warps_total;
+        const bool nfull = static_cast<unsigned long long>(ntile) * TP + TP <= bag_n;
+        float4 nxt[K];
+        if (nfull) pk_load_tile<K>(B.points, ntile * TP, bag_n, lane, nxt);
+        pk_tile<MODEL, K, false, ATOM, TMA>(a, sh, B, n_poses, w, tile * TP, bag_n, qk);
+        tile = ntile;
+        full = nfull;
+        if (nfull) {
+#pragma unroll
+          for (int j = 0; j < K; j++) qk[j] = nxt[j];
         }
-        pk_range<MODEL, K, ATOM, TMA>(a, sh, B, n_poses, w, rb, re, qk, preloaded);
-        preloaded = false;
-        if (dynamic) {
-          cur = __shfl_sync(0xffffffffu, pending, 0);
-          more_ranges = cur < n_tiles;
-        } else {
-          more_ranges = false;
-        }
       }
+      // the cloud's ragged last tile (fewer than 32 * K points) belongs to whichever warp's sequence reaches it
+      if (static_cast<unsigned long long>(tile) * TP < bag_n) pk_range<MODEL, K, ATOM, TMA>(a, sh, B, n_poses, w, tile * TP, bag_n, qk, false);
     }
     if (w.qn > 0) {
       pk_drain32<MODEL>(a, sh, B, w, 0, w.qn);
@@ -959,9 +964,13 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
         if (s) atomicAdd(g + k, s);
       }
     }
-    __threadfence();
+    // every thread's reductions are ordered before the barrier, the barrier before thread 0's fence, the fence before the
+    // arrival: one gpu-scope fence per block instead of one per thread (the pattern of cooperative-groups grid sync)
     __syncthreads();
-    if (t == 0) atomicAdd(a.arrive + buf * PK_MAX_BAGS + bag, 1u);
+    if (t == 0) {
+      __threadfence();
+      atomicAdd(a.arrive + buf * PK_MAX_BAGS + bag, 1u);
+    }
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 2);
     if (time_block) a.block_times[4 * blockIdx.x + 3] = global_ns();
     // ---- (B) finalize the (bag, pose) items this block owns ---------------------------------------------------------------
@@ -974,7 +983,6 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       const unsigned int expected = static_cast<unsigned int>(((batch >> 1) + 1ull) * static_cast<unsigned long long>(a.bag[ib].block_count));
       if (!pk_wait_counter(a, sh, a.arrive + buf * PK_MAX_BAGS + ib, expected)) return;
       if (item == 0 && t == 0) pk_stamp(a, batch, 3);
-      if (ip == 0 && t == 0) a.tile_next[buf * PK_MAX_BAGS + ib] = 0u;  // every block of the bag is past its claims: ready for batch + 2
       int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
       int* ho = (a.hist_out && ib == 0) ? a.hist_out + (static_cast<size_t>(batch) * a.chunk + ip) * a.nb : nullptr;
       const double nid = pk_block_nid(sh, g, a.nb, a.bins, ho, smem_hist);
@@ -1045,6 +1053,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     __syncthreads();
     if (warp == 0) {
       nm_warp_step(sh.nm, sh.ys, lane);
+      if (blockIdx.x == 0 && lane == 0) pk_stamp(a, batch, 7);
       if (blockIdx.x == 0) {  // reference-order evaluations of this batch, for the callback replay on the host (posted writes)
         const int n_obs = sh.nm.n_obs;
         const int base = sh.trace_count;
