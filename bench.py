@@ -97,6 +97,10 @@ def make_inputs(args, bag_index):
     return bag
 
 
+def _make_inputs_star(ab):
+    return make_inputs(*ab)
+
+
 def config_dict(args, world, n_points, W, H):
     """Identical in both arms (the driver compares them): what is computed, on what, and the bounded sample the CPU arm times."""
     cfg = CONFIGS[args.config]
@@ -203,7 +207,13 @@ def run_reference(args, rank, world):
         return
     cfg = CONFIGS[args.config]
     it = cfg["ref_iterations"] if args.ref_iterations < 0 else args.ref_iterations
-    bags_in = [make_inputs(args, b) for b in range(world)]
+    if world > 1:  # the N bags of the joint objective, generated in parallel (the 5 M-point clouds take ~40 s each)
+        import concurrent.futures as cf
+
+        with cf.ProcessPoolExecutor(max_workers=min(world, max(1, host_threads() // 4))) as ex:
+            bags_in = list(ex.map(_make_inputs_star, [(args, b) for b in range(world)]))
+    else:
+        bags_in = [make_inputs(args, 0)]
     bag = bags_in[0]
     O, cam = oracle_objects(bag)
     cores = min(world, host_threads())
@@ -509,7 +519,7 @@ def main():
 
     # ---- P = 1 roofline point: one pose per pass over the resident cloud (pose-list mode, 1 pose per pass) ---------------------
     p1 = None
-    if not grid_mode or True:
+    if True:
         Ts1 = np.stack([bag["starts"][k % len(bag["starts"])] for k in range(24)])
         had_px = px is not None
         if had_px:

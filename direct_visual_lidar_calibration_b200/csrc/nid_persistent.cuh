@@ -33,8 +33,12 @@
 
 namespace vlcal {
 
+// Launch shape: ONE block of 768 threads per SM (24 warps, <= 85 registers).  Three blocks of 256 threads (the A/B build,
+// `make alt`) hold the same 24 warps, but the warp scheduler prefers higher warp slots, so the three blocks of an SM finished
+// their slices at 11 / 14 / 18 us (C2) and every Nelder-Mead batch waited for the 18; one block finishes at 15-16.5 us,
+// merges once instead of three times and arrives once (measured: 28.3 vs 30.8 us per C2 batch, 128 vs 138 us at C3).
 #ifndef PK_THREADS_CFG
-#define PK_THREADS_CFG 256  // threads per block; the A/B build (make alt) uses 768 threads and one block per SM
+#define PK_THREADS_CFG 768
 #endif
 constexpr int PK_THREADS = PK_THREADS_CFG;
 constexpr int PK_WARPS = PK_THREADS / 32;
@@ -53,7 +57,7 @@ struct alignas(64) PkTensorMap {         // a CUtensorMap (cuTensorMapEncodeTile
   unsigned long long opaque[16];
 };
 #ifndef PK_MIN_BLOCKS
-#define PK_MIN_BLOCKS 3  // blocks per SM the register allocation must allow (<= 85 registers per thread)
+#define PK_MIN_BLOCKS 1  // blocks per SM the register allocation must allow (768 threads x 85 registers fill the register file)
 #endif
 
 // score exchange: every double travels as two 8-byte words {32 data bits | 32-bit sequence tag} (an aligned 8-byte store
@@ -225,42 +229,67 @@ static __device__ void nm_warp_loop_top(NmMachine& s, int lane) {
   }
   __syncwarp();
   if (lane == 0) s.num_iterations = s.it;  // :50
-  // :51 std::sort = libstdc++ insertion sort on the values; the permutation is computed by every lane in registers
-  double val[M];
-  int ord[M];
+  // :51 std::sort = libstdc++ insertion sort on the values.  It is a STABLE sort whenever `<` is a strict weak order on the
+  // values, i.e. when none of them is NaN: row i then lands at rank_i = #{j : v_j < v_i} + #{j < i : v_j == v_i}, which
+  // lane i computes with m compares.  With a NaN among the values the result depends on the insertion order itself and
+  // the literal restatement below (every lane walks the insertion sort in registers) takes over.
+  const double my_v = lane < m ? s.x[lane][0] : 0.0;
+  const bool any_nan = __any_sync(0xffffffffu, lane < m && my_v != my_v);
+  int ord[M];  // ord[k] = row of the old simplex that becomes row k
+  if (!any_nan) {
+    int rank = 0;
 #pragma unroll
-  for (int i = 0; i < M; i++) {
-    val[i] = i < m ? s.x[i][0] : 0.0;
-    ord[i] = i;
-  }
+    for (int j = 0; j < M; j++) {
+      const double vj = __shfl_sync(0xffffffffu, my_v, j);
+      if (j < m) rank += (vj < my_v || (j < lane && vj == my_v)) ? 1 : 0;
+    }
+    int inv[M];  // inv[i] = new row of old row i
 #pragma unroll
-  for (int i = 1; i < M; i++) {
-    if (i < m) {
-      const double v = val[i];
-      const int o = ord[i];
-      // unguarded linear insert: walk left while v < element; the first branch (v < *first) moves to the front
-      bool cont = true;
-      int cnt = 0;
+    for (int i = 0; i < M; i++) inv[i] = __shfl_sync(0xffffffffu, rank, i);
 #pragma unroll
-      for (int k = M - 1; k >= 0; k--) {
-        if (k < i) {
-          cont = cont && (v < val[k]);
-          cnt += cont ? 1 : 0;
+    for (int k = 0; k < M; k++) {
+      int o = 0;
+#pragma unroll
+      for (int i = 0; i < M; i++)
+        if (i < m && inv[i] == k) o = i;
+      ord[k] = o;
+    }
+  } else {
+    double val[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      val[i] = i < m ? s.x[i][0] : 0.0;
+      ord[i] = i;
+    }
+#pragma unroll
+    for (int i = 1; i < M; i++) {
+      if (i < m) {
+        const double v = val[i];
+        const int o = ord[i];
+        // unguarded linear insert: walk left while v < element; the first branch (v < *first) moves to the front
+        bool cont = true;
+        int cnt = 0;
+#pragma unroll
+        for (int k = M - 1; k >= 0; k--) {
+          if (k < i) {
+            cont = cont && (v < val[k]);
+            cnt += cont ? 1 : 0;
+          }
         }
-      }
-      const int pos = (v < val[0]) ? 0 : i - cnt;
+        const int pos = (v < val[0]) ? 0 : i - cnt;
 #pragma unroll
-      for (int k = M - 1; k >= 1; k--) {
-        if (k <= i && k > pos) {
-          val[k] = val[k - 1];
-          ord[k] = ord[k - 1];
+        for (int k = M - 1; k >= 1; k--) {
+          if (k <= i && k > pos) {
+            val[k] = val[k - 1];
+            ord[k] = ord[k - 1];
+          }
         }
-      }
 #pragma unroll
-      for (int k = 0; k < M; k++) {
-        if (k <= i && k == pos) {
-          val[k] = v;
-          ord[k] = o;
+        for (int k = 0; k < M; k++) {
+          if (k <= i && k == pos) {
+            val[k] = v;
+            ord[k] = o;
+          }
         }
       }
     }
@@ -641,15 +670,15 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
     dl[j] = (5.25f * F32_U) * (fabsf(q[j].x) + fabsf(q[j].y) + fabsf(q[j].z) + tmax);
     lb[j] = w.hist_addr + 4u * static_cast<unsigned int>(lidar_bin_of(q[j].w, a.bins) * a.bins);
   }
+  unsigned int unc_mask = 0u, unc_bit = 1u;  // deferred verdicts of this tile: bit p * K + j
   int pend_bin[K];  // image bin of the previous pose's verdict, -1 = not counted
   int pend_inc[K];  // ATOM == 1: 0 / 1
 #pragma unroll
   for (int j = 0; j < K; j++) pend_bin[j] = -1, pend_inc[j] = 0;
   unsigned int pend_off = 0;
   for (int p = 0; p <= n_poses; p++) {
-    bool acc[K], unc[K];
+    bool acc[K];
     int pix[K], wx[K], wy[K];
-    bool any_unc = false;
     if (p < n_poses) {
       const float4 r0 = sh.pose32[p][0], r1 = sh.pose32[p][1], r2 = sh.pose32[p][2];
       const float Pm[12] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, r1.w, r2.w};
@@ -657,11 +686,12 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
       for (int j = 0; j < K; j++) {
         const LeanVerdict v = classify_lean<MODEL>(a.fast, a.lean, a.width, Pm, px[j], py[j], pz[j], dl[j]);
         acc[j] = PARTIAL ? (v.accept & valid0) : v.accept;
-        unc[j] = PARTIAL ? (v.uncertain & valid0) : v.uncertain;
+        const bool unc = PARTIAL ? (v.uncertain & valid0) : v.uncertain;
+        if (unc) unc_mask |= unc_bit << j;
         pix[j] = v.idx;
         if constexpr (TMA) wx[j] = v.ixb, wy[j] = v.iyb;
-        any_unc = any_unc | unc[j];
       }
+      unc_bit <<= K;
     }
 #pragma unroll
     for (int j = 0; j < K; j++) {  // :49 hist(image_bin, lidar_bin)++ for the previous pose
@@ -690,26 +720,29 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
           pend_inc[j] = acc[j] ? 1 : 0;
         }
       }
-      if (__any_sync(0xffffffffu, any_unc)) {  // some lane deferred a point: queue it for the exact path
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-          const unsigned int m = __ballot_sync(0xffffffffu, unc[j]);
-          if (m) {
-            if (unc[j]) {
-              const int pos = w.qn + __popc(m & w.lt_mask);
-              w.q_idx[pos] = tile + j * 32 + w.lane;
-              w.q_pose[pos] = static_cast<unsigned char>(p);
-            }
-            w.qn += __popc(m);
-            __syncwarp();
-            if (w.qn >= 32) {
-              pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
-              w.qn -= 32;
-              __syncwarp();
-            }
-          }
-        }
-      }
+    }
+  }
+  // Deferred (point, pose) pairs of this tile -> the warp's queue for the exact path, compacted with one ballot per round
+  // (a round queues one pair of every lane that still has one).  Doing this once per tile instead of inside the pose loop
+  // matters: with ~3 % of the point-poses deferred, SOME lane of the 32 x K has one in 5 of 6 pose steps, and the ballot /
+  // queue code (~95 instructions) ran almost every step -- 160 executed instructions per point-pose against 109 in the
+  // straight-line path (profiles/r02_c_*).
+  while (__any_sync(0xffffffffu, unc_mask != 0u)) {
+    const bool have = unc_mask != 0u;
+    const int b = __ffs(static_cast<int>(unc_mask)) - 1;  // bit p * K + j
+    unc_mask &= unc_mask - 1u;
+    const unsigned int m = __ballot_sync(0xffffffffu, have);
+    if (have) {
+      const int pos = w.qn + __popc(m & w.lt_mask);
+      w.q_idx[pos] = tile + static_cast<unsigned int>(b % K) * 32u + static_cast<unsigned int>(w.lane);
+      w.q_pose[pos] = static_cast<unsigned char>(b / K);
+    }
+    w.qn += __popc(m);
+    __syncwarp();
+    if (w.qn >= 32) {
+      pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
+      w.qn -= 32;
+      __syncwarp();
     }
   }
 }

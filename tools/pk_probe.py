@@ -89,8 +89,8 @@ def main():
         V.set_solver_mode(0)
         if len(st):
             rel = (st - st[:, :1]) * 1e-3  # us since block 0 entered the batch
-            names = ["enter", "main_done", "arrived", "fin_all_arrived", "fin_published", "scores_seen", "poses_ready"]
-            rows = rel[1:, :7]  # skip the 7-pose first batch
+            names = ["enter", "main_done", "arrived", "fin_all_arrived", "fin_published", "scores_seen", "poses_ready", "nm_stepped"]
+            rows = rel[1:, :8]  # skip the 7-pose first batch
             med = {n: float(np.median(rows[:, i])) for i, n in enumerate(names)}
             nxt = (st[1:, 0] - st[:-1, 0]) * 1e-3
             print(json.dumps(dict(base, what="stamps_us_median", batches=int(len(st)), phases=med, batch_period_us=float(np.median(nxt)))), flush=True)
