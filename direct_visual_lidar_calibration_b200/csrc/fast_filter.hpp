@@ -177,8 +177,12 @@ inline LeanCam make_lean_cam(const CameraParams& cam, const FastCam& f, int widt
     c.eq_sv = static_cast<float>(2.0 * cam.intr[1]);
     c.cxh = static_cast<float>(0.5 * cam.intr[0] - 0.5);
     c.cyh = static_cast<float>(0.5 * cam.intr[1] - 0.5);
-    const double cu = SAFETY * (W * LEAN_ATAN_ERR_TURNS + 4.0 * U * (W + Wd + 1.0));
-    const double cv = SAFETY * (2.0 * H * LEAN_ATAN_ERR_TURNS + 4.0 * U * (H + Hd + 1.0));
+    // u' = fma(lon_turns, W, W/2 - 0.5): the angle's error times W, one rounding of the result (|u'| <= W + 1) and the
+    // rounding of the constant (<= u W / 2); W itself is exact.  (project_fast charges 4u (W + Wd + 1) for its three-step
+    // form; the single FMA needs 2u (W + 1), which halves E and the deferral rate of this model.)
+    (void)Wd, (void)Hd;
+    const double cu = SAFETY * (W * LEAN_ATAN_ERR_TURNS + 2.0 * U * (W + 1.0));
+    const double cv = SAFETY * (2.0 * H * LEAN_ATAN_ERR_TURNS + 2.0 * U * (H + 1.0));
     c.hx0 = dn(0.5 - cu);
     c.hy0 = dn(0.5 - cv);
     if (!(c.hx0 > 0.0f) || !(c.hy0 > 0.0f)) return c;

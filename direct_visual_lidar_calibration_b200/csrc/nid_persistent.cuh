@@ -1141,12 +1141,13 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
 }
 
 // debug / test kernel: the lean classifier AND the exact path on every (point, pose); a.dbg: [0] point-poses,
-// [1] verdicts deferred to the exact path, [2] kept verdicts that disagree with the exact path (must be 0)
+// [1] verdicts deferred to the exact path, [2] kept verdicts that disagree with the exact path (must be 0),
+// [3] max over accepted verdicts of |uv_fp32 - uv_exact| / E as float bits (atomicMax; must stay < 1)
 template <int MODEL>
 __global__ void __launch_bounds__(NID_THREADS) nid_lean_verify_kernel(const __grid_constant__ NidArgs a, const __grid_constant__ LeanCam lc) {
   const float4* __restrict__ pts = static_cast<const float4*>(a.points);
   unsigned long long total = 0, uncertain = 0, mismatch = 0;
-  float tmax = 0.f;
+  float tmax = 0.f, max_ratio = 0.f;
   for (int p = 0; p < a.n_poses; p++) tmax = fmaxf(tmax, a.pose32[p][12]);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
@@ -1155,17 +1156,23 @@ __global__ void __launch_bounds__(NID_THREADS) nid_lean_verify_kernel(const __gr
     for (int p = 0; p < a.n_poses; p++) {
       total++;
       const LeanVerdict v = classify_lean<MODEL>(a.fast, lc, a.width, a.pose32[p], q.x, q.y, q.z, delta);
-      const int pe = exact_pixel_hd<MODEL>(a.cam, a.cos_fov, a.width, a.height, a.pose[p], q.x, q.y, q.z);
+      double ue = 0.0, ve = 0.0;
+      const int pe = exact_pixel_hd<MODEL>(a.cam, a.cos_fov, a.width, a.height, a.pose[p], q.x, q.y, q.z, &ue, &ve);
       if (v.uncertain) {
         uncertain++;
       } else if (v.accept ? (v.idx != pe) : (pe != -1)) {
         mismatch++;
+      } else if (v.accept) {
+        const float ru = static_cast<float>(fabs(static_cast<double>(v.up) - (ue - 0.5))) / (0.5f - v.hx);
+        const float rv = static_cast<float>(fabs(static_cast<double>(v.vp) - (ve - 0.5))) / (0.5f - v.hy);
+        max_ratio = fmaxf(max_ratio, fmaxf(ru, rv));
       }
     }
   }
   atomicAdd(a.dbg + 0, total);
   atomicAdd(a.dbg + 1, uncertain);
   atomicAdd(a.dbg + 2, mismatch);
+  atomicMax(reinterpret_cast<unsigned int*>(a.dbg + 3), __float_as_uint(max_ratio));  // non-negative floats order like uints
 }
 
 }  // namespace vlcal

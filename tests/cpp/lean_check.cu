@@ -25,7 +25,7 @@ struct Case {
 static bool adversarial = true;
 
 template <int MODEL>
-static void run_case(const Case& cs, unsigned seed, long long n_points, int n_poses, double spread, long long out[6]) {
+static void run_case(const Case& cs, unsigned seed, long long n_points, int n_poses, double spread, long long out[7]) {
   CameraParams cam;
   std::memset(&cam, 0, sizeof(cam));
   cam.model = MODEL;
@@ -77,6 +77,7 @@ static void run_case(const Case& cs, unsigned seed, long long n_points, int n_po
     tmax_all = std::max(tmax_all, poses32[16 * p + 12]);
   }
   long long total = 0, unc = 0, mism = 0, acc = 0, strip = 0;
+  double max_ratio = 0.0;
   for (long long i = 0; i < n_points; i++) {
     // a direction inside a cone a bit wider than the FoV (so that FoV / border rejects occur), random range;
     // every 4th point is nudged so that its u (or v) lands within 1e-3 .. 1e-8 px of an integer at pose 0
@@ -109,13 +110,14 @@ static void run_case(const Case& cs, unsigned seed, long long n_points, int n_po
       } else if (v.accept) {
         acc++;
         if (v.idx != pe) mism++;
+        else max_ratio = std::max(max_ratio, std::max(std::fabs(v.up - (ue - 0.5)) / (0.5 - v.hx), std::fabs(v.vp - (ve - 0.5)) / (0.5 - v.hy)));
         if (pe >= 0 && (ue < 0.0 || ve < 0.0)) strip++;
       } else if (pe != -1) {
         mism++;
       }
     }
   }
-  out[0] = total, out[1] = unc, out[2] = mism, out[3] = acc, out[4] = strip;
+  out[0] = total, out[1] = unc, out[2] = mism, out[3] = acc, out[4] = strip, out[6] = static_cast<long long>(max_ratio * 1e6);
 }
 
 int main(int argc, char** argv) {
@@ -139,7 +141,7 @@ int main(int argc, char** argv) {
   std::printf("[");
   int k = 0;
   for (const Case& cs : cases) {
-    long long out[6] = {0, 0, 0, 0, 0, 0};
+    long long out[7] = {0, 0, 0, 0, 0, 0, 0};
     switch (cs.model) {
       case CAM_PLUMB_BOB: run_case<CAM_PLUMB_BOB>(cs, 100 + k, n, 4, 1.15, out); break;
       case CAM_FISHEYE: run_case<CAM_FISHEYE>(cs, 100 + k, n, 4, 1.1, out); break;
@@ -148,8 +150,8 @@ int main(int argc, char** argv) {
       case CAM_EQUIRECTANGULAR: run_case<CAM_EQUIRECTANGULAR>(cs, 100 + k, n, 4, 1.0, out); break;
       default: run_case<CAM_RATIONAL_POLYNOMIAL>(cs, 100 + k, n, 4, 1.1, out); break;
     }
-    std::printf("%s{\"case\": %d, \"model\": %d, \"enabled\": %lld, \"point_poses\": %lld, \"uncertain\": %lld, \"mismatches\": %lld, \"accepted\": %lld, \"accepted_in_minus_one_strip\": %lld}", k ? ", " : "", k, cs.model,
-                out[5], out[0], out[1], out[2], out[3], out[4]);
+    std::printf("%s{\"case\": %d, \"model\": %d, \"enabled\": %lld, \"point_poses\": %lld, \"uncertain\": %lld, \"mismatches\": %lld, \"accepted\": %lld, \"accepted_in_minus_one_strip\": %lld, \"max_error_over_bound_ppm\": %lld}", k ? ", " : "", k, cs.model,
+                out[5], out[0], out[1], out[2], out[3], out[4], out[6]);
     k++;
   }
   std::printf("]\n");
