@@ -722,27 +722,59 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
       }
     }
   }
-  // Deferred (point, pose) pairs of this tile -> the warp's queue for the exact path, compacted with one ballot per round
-  // (a round queues one pair of every lane that still has one).  Doing this once per tile instead of inside the pose loop
+  // Deferred (point, pose) pairs of this tile -> the warp's queue for the exact path.  Doing this once per tile instead of inside the pose loop
   // matters: with ~3 % of the point-poses deferred, SOME lane of the 32 x K has one in 5 of 6 pose steps, and the ballot /
   // queue code (~95 instructions) ran almost every step -- 160 executed instructions per point-pose against 109 in the
   // straight-line path (profiles/r02_c_*).
-  while (__any_sync(0xffffffffu, unc_mask != 0u)) {
-    const bool have = unc_mask != 0u;
-    const int b = __ffs(static_cast<int>(unc_mask)) - 1;  // bit p * K + j
-    unc_mask &= unc_mask - 1u;
-    const unsigned int m = __ballot_sync(0xffffffffu, have);
-    if (have) {
-      const int pos = w.qn + __popc(m & w.lt_mask);
+  // Usual case (the tile defers at most 32 pairs): one warp prefix sum gives every lane the queue slots of its pairs.
+  // Otherwise: one ballot per round.
+  const int cnt = __popc(unc_mask);
+  const int total = __reduce_add_sync(0xffffffffu, cnt);
+  if (total > 0 && total <= 32) {
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (w.lane >= o) incl += up;
+    }
+    if (w.qn + total > PK_QUEUE) {  // make room first (qn > 32 here): the last 32 queued pairs go to the exact path now
+      pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
+      w.qn -= 32;
+      __syncwarp();
+    }
+    int pos = w.qn + incl - cnt;
+    while (unc_mask != 0u) {
+      const int b = __ffs(static_cast<int>(unc_mask)) - 1;  // bit p * K + j
+      unc_mask &= unc_mask - 1u;
       w.q_idx[pos] = tile + static_cast<unsigned int>(b % K) * 32u + static_cast<unsigned int>(w.lane);
       w.q_pose[pos] = static_cast<unsigned char>(b / K);
+      pos++;
     }
-    w.qn += __popc(m);
+    w.qn += total;
     __syncwarp();
     if (w.qn >= 32) {
       pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
       w.qn -= 32;
       __syncwarp();
+    }
+  } else if (total > 32) {
+    while (__any_sync(0xffffffffu, unc_mask != 0u)) {
+      const bool have = unc_mask != 0u;
+      const int b = __ffs(static_cast<int>(unc_mask)) - 1;
+      unc_mask &= unc_mask - 1u;
+      const unsigned int m = __ballot_sync(0xffffffffu, have);
+      if (have) {
+        const int pos = w.qn + __popc(m & w.lt_mask);
+        w.q_idx[pos] = tile + static_cast<unsigned int>(b % K) * 32u + static_cast<unsigned int>(w.lane);
+        w.q_pose[pos] = static_cast<unsigned char>(b / K);
+      }
+      w.qn += __popc(m);
+      __syncwarp();
+      if (w.qn >= 32) {
+        pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
+        w.qn -= 32;
+        __syncwarp();
+      }
     }
   }
 }
