@@ -26,10 +26,13 @@ using PkKernel = void (*)(const PkArgs);
 
 // points per lane and tile: 2 or 4 for the light models, 2 for the ones that carry transcendental calls (more live state
 // per point); atom: histogram-increment form (nid_persistent.cuh)
+#ifndef PK_K4_ALL
+#define PK_K4_ALL 0  // A/B builds: also instantiate 4 points per lane for the models whose classifier is register-heavy
+#endif
 template <int MODEL>
 static PkKernel pk_pick_ka(int k, int atom) {
   constexpr bool heavy = MODEL == CAM_FISHEYE || MODEL == CAM_EQUIRECTANGULAR || MODEL == CAM_ATAN;
-  if constexpr (!heavy) {
+  if constexpr (!heavy || PK_K4_ALL) {
     if (k == 4) return atom ? nid_persistent_kernel<MODEL, 4, 1> : nid_persistent_kernel<MODEL, 4, 0>;
   }
   return atom ? nid_persistent_kernel<MODEL, 2, 1> : nid_persistent_kernel<MODEL, 2, 0>;
@@ -177,8 +180,8 @@ struct PkScratchLayout {
       o = (o + bytes + 255) & ~static_cast<size_t>(255);
       return at;
     };
-    ghist = take(sizeof(int) * 2 * n_bags * PK_MAX_POSES * nb);
-    arrive = take(sizeof(unsigned int) * 2 * PK_MAX_BAGS);
+    ghist = take(sizeof(int) * 3 * n_bags * PK_MAX_POSES * nb);  // three rotating buffers (Nelder-Mead mode), two used by the pose list
+    arrive = take(sizeof(unsigned int) * 3 * PK_MAX_BAGS);
     fin_done = take(sizeof(unsigned int) * 2);
     tile_next = take(sizeof(unsigned int) * 2 * PK_MAX_BAGS);
     abort_flag = take(sizeof(unsigned int));

@@ -29,6 +29,7 @@
 
 #include "exact_classify.cuh"
 #include "lean_filter.cuh"
+#include "lean_filter2.cuh"
 #include "nid_kernels.cuh"
 
 namespace vlcal {
@@ -56,6 +57,9 @@ constexpr int PK_TMA_HALO = 12;          // pixels around the bounding box of th
 struct alignas(64) PkTensorMap {         // a CUtensorMap (cuTensorMapEncodeTiled), opaque here
   unsigned long long opaque[16];
 };
+#ifndef PK_PACKED_FP32
+#define PK_PACKED_FP32 1  // classify two points per FFMA2 / FMUL2 / FADD2 (lean_filter2.cuh); 0: scalar classifier (A/B build)
+#endif
 #ifndef PK_MIN_BLOCKS
 #define PK_MIN_BLOCKS 1  // blocks per SM the register allocation must allow (768 threads x 85 registers fill the register file)
 #endif
@@ -618,6 +622,72 @@ static __device__ __noinline__ double pk_block_nid(PkShared& sh, int* __restrict
   return s_nid;
 }
 
+// The same NID by ONE warp (Nelder-Mead mode: every block finalizes every (bag, pose) of the batch itself, one warp per
+// item, instead of waiting for an owner block to publish it).  Identical value: same terms, lane l adds terms l, l+32, ...
+// in ascending order, same xor tree.  Reads the accumulator only (the triple-buffered accumulators of this mode are zeroed
+// two batches ahead).  scr: nb + 2*bins ints of warp-private shared memory.
+static __device__ __noinline__ double pk_warp_nid(const int* __restrict__ g, int nb, int bins, int* __restrict__ scr, int lane) {
+  int* s_c = scr;
+  int* s_marg = scr + nb;  // image marginal, then lidar marginal
+  for (int i = lane; i < 2 * bins; i += 32) s_marg[i] = 0;
+  __syncwarp();
+  int part = 0;
+#pragma unroll 8
+  for (int k = lane; k < nb; k += 32) {
+    const int c = __ldcg(g + k);
+    s_c[k] = c;
+    if (c) {
+      atomicAdd(&s_marg[k % bins], c);         // hist_image[image_bin]   (:50)
+      atomicAdd(&s_marg[bins + k / bins], c);  // hist_points[lidar_bin]  (:51)
+      part += c;
+    }
+  }
+  part = __reduce_add_sync(0xffffffffu, part);
+  __syncwarp();
+  const double sum = static_cast<double>(part);  // :54
+  double t_rs = 0.0, t_r = 0.0, t_s = 0.0;
+#pragma unroll 4
+  for (int k = lane; k < nb; k += 32) {
+    const double pr = static_cast<double>(s_c[k]) / sum;
+    t_rs += pr * log_pos_normal(pr + 1e-6);  // :59-61
+  }
+  for (int k = lane; k < bins; k += 32) {
+    const double pi = static_cast<double>(s_marg[k]) / sum;
+    const double pp = static_cast<double>(s_marg[bins + k]) / sum;
+    t_r += pi * log_pos_normal(pi + 1e-6);
+    t_s += pp * log_pos_normal(pp + 1e-6);
+  }
+  const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);
+  const double MI = Hr + Hs - Hrs;  // :63
+  return (Hrs - MI) / Hrs;          // :64 (NaN when there are no inliers, as in the reference)
+}
+
+// thread b (< n_bags) spins until bag b's arrival counter reaches expected_per_block * (its block count); false for every
+// thread if the launch is being aborted
+__device__ __forceinline__ bool pk_wait_arrivals(const PkArgs& a, const unsigned int* counters, unsigned int rounds) {
+  int failed = 0;
+  if (static_cast<int>(threadIdx.x) < a.n_bags) {
+    const unsigned int expected = rounds * static_cast<unsigned int>(a.bag[threadIdx.x].block_count);
+    const unsigned long long t0 = global_ns();
+    unsigned int spins = 0;
+    while (ld_acquire_u32(counters + threadIdx.x) < expected) {
+      if ((++spins & 255u) == 0) {
+        if (ld_acquire_u32(a.abort_flag) != 0u) {
+          failed = 1;
+          break;
+        }
+        if (global_ns() - t0 > a.timeout_ns) {
+          atomicExch(a.abort_flag, 1u);
+          if (a.error_host) *reinterpret_cast<volatile int*>(a.error_host) = 1;
+          failed = 1;
+          break;
+        }
+      }
+    }
+  }
+  return __syncthreads_or(failed) == 0;
+}
+
 // ---- hot loop -----------------------------------------------------------------------------------------------------------
 
 struct PkWarp {
@@ -670,6 +740,15 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
     dl[j] = (5.25f * F32_U) * (fabsf(q[j].x) + fabsf(q[j].y) + fabsf(q[j].z) + tmax);
     lb[j] = w.hist_addr + 4u * static_cast<unsigned int>(lidar_bin_of(q[j].w, a.bins) * a.bins);
   }
+  constexpr bool PACKED = PK_PACKED_FP32 && !PARTIAL && (K % 2 == 0) && LeanPacked<MODEL>::value;
+  F2 X2[(K + 1) / 2], Y2[(K + 1) / 2], Z2[(K + 1) / 2], D2[(K + 1) / 2];
+  if constexpr (PACKED) {
+#pragma unroll
+    for (int j = 0; j < K; j += 2) {
+      X2[j / 2] = f2_pack(px[j], px[j + 1]), Y2[j / 2] = f2_pack(py[j], py[j + 1]);
+      Z2[j / 2] = f2_pack(pz[j], pz[j + 1]), D2[j / 2] = f2_pack(dl[j], dl[j + 1]);
+    }
+  }
   unsigned int unc_mask = 0u, unc_bit = 1u;  // deferred verdicts of this tile: bit p * K + j
   int pend_bin[K];  // image bin of the previous pose's verdict, -1 = not counted
   int pend_inc[K];  // ATOM == 1: 0 / 1
@@ -682,14 +761,28 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
     if (p < n_poses) {
       const float4 r0 = sh.pose32[p][0], r1 = sh.pose32[p][1], r2 = sh.pose32[p][2];
       const float Pm[12] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, r1.w, r2.w};
+      if constexpr (PACKED) {
 #pragma unroll
-      for (int j = 0; j < K; j++) {
-        const LeanVerdict v = classify_lean<MODEL>(a.fast, a.lean, a.width, Pm, px[j], py[j], pz[j], dl[j]);
-        acc[j] = PARTIAL ? (v.accept & valid0) : v.accept;
-        const bool unc = PARTIAL ? (v.uncertain & valid0) : v.uncertain;
-        if (unc) unc_mask |= unc_bit << j;
-        pix[j] = v.idx;
-        if constexpr (TMA) wx[j] = v.ixb, wy[j] = v.iyb;
+        for (int j = 0; j < K; j += 2) {  // two points per instruction on the packed fp32 pipe (lean_filter2.cuh)
+          const LeanVerdict2 v = classify_lean2<MODEL>(a.fast, a.lean, a.width, Pm, X2[j / 2], Y2[j / 2], Z2[j / 2], D2[j / 2]);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            acc[j + h] = v.accept[h];
+            if (v.uncertain[h]) unc_mask |= unc_bit << (j + h);
+            pix[j + h] = v.idx[h];
+            if constexpr (TMA) wx[j + h] = v.ixb[h], wy[j + h] = v.iyb[h];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          const LeanVerdict v = classify_lean<MODEL>(a.fast, a.lean, a.width, Pm, px[j], py[j], pz[j], dl[j]);
+          acc[j] = PARTIAL ? (v.accept & valid0) : v.accept;
+          const bool unc = PARTIAL ? (v.uncertain & valid0) : v.uncertain;
+          if (unc) unc_mask |= unc_bit << j;
+          pix[j] = v.idx;
+          if constexpr (TMA) wx[j] = v.ixb, wy[j] = v.iyb;
+        }
       }
       unc_bit <<= K;
     }
@@ -815,6 +908,12 @@ __device__ __forceinline__ void pk_range(const PkArgs& a, const PkShared& sh, co
     tpos += 32u;
     if (more) q1[0] = n1[0];
   }
+}
+
+__device__ __forceinline__ float pk_tmax(const PkShared& sh, int n_poses) {
+  float tm = 0.f;
+  for (int p = 0; p < n_poses; p++) tm = fmaxf(tm, sh.pose32[p][3].x);
+  return tm;
 }
 
 __device__ __forceinline__ void pk_stamp(const PkArgs& a, unsigned long long batch, int slot) {
@@ -955,7 +1054,9 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
   for (unsigned long long batch = 0;; batch++) {
     const int n_poses = sh.n_poses;
     if (n_poses == 0) break;
-    const int buf = static_cast<int>(batch & 1ull);
+    // accumulator buffer of this batch: pose-list mode alternates two (each zeroed by its finalizers), Nelder-Mead mode
+    // rotates three (every block reads all of them; buffer b is zeroed while batch b + 1 is finalized, see (B))
+    const int buf = solve_mode ? static_cast<int>(batch % 3ull) : static_cast<int>(batch & 1ull);
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 0);
     // pose-list mode runs ahead of the finalizers: buffer `buf` (accumulators, tile counter) must have been finalized for
     // chunk batch - 2 first.  (Nelder-Mead mode: seeing the scores of batch - 1 already implies it.)
@@ -964,11 +1065,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     }
     const bool time_block = a.block_times != nullptr && batch == static_cast<unsigned long long>(a.block_times_batch) && t == 0;
     if (time_block) a.block_times[4 * blockIdx.x + 0] = global_ns();
-    if (t == 0) {
-      float tm = 0.f;
-      for (int p = 0; p < n_poses; p++) tm = fmaxf(tm, sh.pose32[p][3].x);
-      sh.tmax = tm;
-    }
+    // Nelder-Mead mode, batch > 0: the histogram copies were zeroed and sh.tmax set while warp 0 stepped the simplex (end of
+    // the previous batch), so the batch starts without a barrier
+    const bool fresh = !solve_mode || batch == 0ull;
+    if (fresh && t == 0) sh.tmax = pk_tmax(sh, n_poses);
     // ---- (A) histograms of this block's share of the cloud ----------------------------------------------------------
     const int per_copy = n_poses * a.nb;
     w.hist_addr = smem_base + 4u * static_cast<unsigned int>((warp % a.copies) * per_copy);
@@ -977,8 +1077,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       float4 qk[K];
       const bool preloaded = has_work && begin + 32u * K <= end;
       if (preloaded) pk_load_tile<K>(B.points, begin, end, lane, qk);
-      for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
-      __syncthreads();
+      if (fresh) {
+        for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
+        __syncthreads();
+      }
       if (time_block) a.block_times[4 * blockIdx.x + 1] = global_ns();
       if (has_work) pk_range<MODEL, K, ATOM, TMA>(a, sh, B, n_poses, w, begin, end, qk, preloaded);
     } else {
@@ -994,8 +1096,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       float4 qk[K];
       bool full = static_cast<unsigned long long>(tile) * TP + TP <= bag_n;
       if (full) pk_load_tile<K>(B.points, tile * TP, bag_n, lane, qk);
-      for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
-      __syncthreads();
+      if (fresh) {
+        for (int i = t; i < a.copies * per_copy; i += PK_THREADS) smem_hist[i] = 0;
+        __syncthreads();
+      }
       if (time_block) a.block_times[4 * blockIdx.x + 1] = global_ns();
       while (full) {
         const unsigned int ntile = tile + warps_total;
@@ -1038,40 +1142,30 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     }
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 2);
     if (time_block) a.block_times[4 * blockIdx.x + 3] = global_ns();
-    // ---- (B) finalize the (bag, pose) items this block owns ---------------------------------------------------------------
     const unsigned long long seq = sh.seq_base + batch + 1ull;
     const int slot = static_cast<int>(seq & 1ull);
     const unsigned long long tag = ((seq & 0x7fffffffull) | 0x80000000ull) << 32;  // never 0 (mailboxes start zeroed)
-    for (int item = 0; item < a.n_bags * n_poses; item++) {
-      const int ib = item / n_poses, ip = item % n_poses;
-      if (static_cast<int>((static_cast<long long>(ib * PK_MAX_POSES + ip) * fin_stride) % gridDim.x) != static_cast<int>(blockIdx.x)) continue;
-      const unsigned int expected = static_cast<unsigned int>(((batch >> 1) + 1ull) * static_cast<unsigned long long>(a.bag[ib].block_count));
-      if (!pk_wait_counter(a, sh, a.arrive + buf * PK_MAX_BAGS + ib, expected)) return;
-      if (item == 0 && t == 0) pk_stamp(a, batch, 3);
-      int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
-      int* ho = (a.hist_out && ib == 0) ? a.hist_out + (static_cast<size_t>(batch) * a.chunk + ip) * a.nb : nullptr;
-      const double nid = pk_block_nid(sh, g, a.nb, a.bins, ho, smem_hist);
-      if (solve_mode) {
-        // the score goes to every rank's mailbox (NVLink peer stores when world > 1), tagged words
-        if (t < a.world) {
-          const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(nid));
-          volatile unsigned long long* dst = a.box[t]->w[slot][(a.rank * a.n_bags + ib) * PK_MAX_POSES + ip];
-          dst[0] = tag | (bits & 0xffffffffull);
-          dst[1] = tag | (bits >> 32);
-        }
-      } else {
+    if (!solve_mode) {
+      // ---- (B, pose list) finalize the (bag, pose) items this block owns; nobody waits for them but the chunk after next ----
+      for (int item = 0; item < a.n_bags * n_poses; item++) {
+        const int ib = item / n_poses, ip = item % n_poses;
+        if (static_cast<int>((static_cast<long long>(ib * PK_MAX_POSES + ip) * fin_stride) % gridDim.x) != static_cast<int>(blockIdx.x)) continue;
+        const unsigned int expected = static_cast<unsigned int>(((batch >> 1) + 1ull) * static_cast<unsigned long long>(a.bag[ib].block_count));
+        if (!pk_wait_counter(a, sh, a.arrive + buf * PK_MAX_BAGS + ib, expected)) return;
+        if (item == 0 && t == 0) pk_stamp(a, batch, 3);
+        int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
+        int* ho = (a.hist_out && ib == 0) ? a.hist_out + (static_cast<size_t>(batch) * a.chunk + ip) * a.nb : nullptr;
+        const double nid = pk_block_nid(sh, g, a.nb, a.bins, ho, smem_hist);
         if (t == 0) {
-          // pose-list mode: sum over the launch's bags in bag order needs all of them; single-bag launches store directly
+          // sum over the launch's bags in bag order needs all of them; single-bag launches store directly
           if (a.n_bags == 1) a.scores_out[batch * a.chunk + ip] = nid;
           else a.scores_out[(batch * a.chunk + ip) * a.n_bags + ib] = nid;  // per-bag scores; the host adds them in order
           __threadfence();
           atomicAdd(a.fin_done + buf, 1u);
         }
+        if (item == 0 && t == 0) pk_stamp(a, batch, 4);
+        __syncthreads();
       }
-      if (item == 0 && t == 0) pk_stamp(a, batch, 4);
-      __syncthreads();
-    }
-    if (!solve_mode) {
       // ---- next chunk of the pose list (only the last chunk can be partial, and no merge ever waits for it) ----
       const long long next0 = static_cast<long long>(batch + 1ull) * a.chunk;
       const int pc = static_cast<int>(max(0ll, min(static_cast<long long>(a.chunk), static_cast<long long>(a.n_total) - next0)));
@@ -1081,10 +1175,47 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       __syncthreads();
       continue;
     }
-    // ---- (C) all scores of the batch -> sum over ranks and bags -> Nelder-Mead step -> next poses ---------------------------
+    // ---- (B, Nelder-Mead) every block finalizes every (bag, pose) of the batch itself, one warp per item ---------------------
+    // The next step of the solve needs all scores in every block.  An owner block per item (round-2 first version) cost a
+    // second hop -- all arrived -> owner computes with the whole block -> fence -> publishes -> everybody polls: 4.4 us of
+    // the 26 us batch at C2 -- and the zero-on-read accumulator needed that fence.  Here the arrival wait is the only hop:
+    // each block reads the merged accumulators (4 KB per item, L2) and computes the same canonical NID per item in one warp.
+    // Accumulators rotate over three buffers and are zeroed two batches ahead: buffer (batch + 2) % 3 was last read in
+    // batch - 1 (finished by every block before it arrived here) and is next merged in batch + 2, which no block reaches
+    // before every block arrived for batch + 1, i.e. after this block's zeroing (ordered by the arrival fence).
+    if (!pk_wait_arrivals(a, a.arrive + buf * PK_MAX_BAGS, static_cast<unsigned int>(batch / 3ull + 1ull))) return;
+    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 3);
+    {
+      const int nz = a.n_bags * PK_MAX_POSES * a.nb;
+      int* z = a.ghist + static_cast<size_t>((buf + 2) % 3) * nz;
+      for (int i = static_cast<int>(blockIdx.x) * PK_THREADS + t; i < nz; i += static_cast<int>(gridDim.x) * PK_THREADS) z[i] = 0;
+    }
+    {
+      const int n_items = a.n_bags * n_poses;
+      const int per_w = a.nb + 2 * a.bins;
+      const int fw = min(PK_WARPS, (a.copies * PK_MAX_POSES * a.nb) / per_w);  // >= 7: the histogram copies are dead after the merge
+      if (warp < fw) {
+        for (int item = warp; item < n_items; item += fw) {
+          const int ib = item / n_poses, ip = item % n_poses;
+          const int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
+          const double nid = pk_warp_nid(g, a.nb, a.bins, smem_hist + warp * per_w, lane);
+          const int word = (a.rank * a.n_bags + ib) * PK_MAX_POSES + ip;
+          if (lane == 0) sh.parts[word] = nid;
+          // the other ranks get it from one block (NVLink peer stores, tagged words)
+          if (a.world > 1 && static_cast<unsigned int>(item) % gridDim.x == blockIdx.x && lane < a.world && lane != a.rank) {
+            const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(nid));
+            volatile unsigned long long* dst = a.box[lane]->w[slot][word];
+            dst[0] = tag | (bits & 0xffffffffull);
+            dst[1] = tag | (bits >> 32);
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 4);
+    // ---- (C) the other ranks' scores -> sum over ranks and bags -> Nelder-Mead step -> next poses ---------------------------
     const int n_words = a.world * a.n_bags * n_poses;
     bool timed_out = false;
-    if (t < n_words) {
+    if (a.world > 1 && t < n_words && t / (a.n_bags * n_poses) != a.rank) {
       const int src = t / n_poses, p = t % n_poses;  // src = rank * n_bags + bag
       volatile unsigned long long* wsrc = a.box[a.rank]->w[slot][src * PK_MAX_POSES + p];
       const unsigned long long t0 = global_ns();
@@ -1137,7 +1268,14 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       }
       const int n_next = sh.nm.n_cand;  // 0 when finished
       pk_poses_of_candidates(sh, n_next, lane);
-      if (lane == 0) sh.n_poses = n_next;
+      if (lane == 0) {
+        sh.n_poses = n_next;
+        sh.tmax = pk_tmax(sh, n_next);
+      }
+    } else {
+      // meanwhile the other warps clear the histogram copies for the next batch (all PK_MAX_POSES slots: its pose count is
+      // being decided by warp 0); the warp-private finalizer scratch in the same array is dead since the barrier above
+      for (int i = t - 32; i < a.copies * PK_MAX_POSES * a.nb; i += PK_THREADS - 32) smem_hist[i] = 0;
     }
     __syncthreads();
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 6);
@@ -1182,22 +1320,40 @@ __global__ void __launch_bounds__(NID_THREADS) nid_lean_verify_kernel(const __gr
   float tmax = 0.f, max_ratio = 0.f;
   for (int p = 0; p < a.n_poses; p++) tmax = fmaxf(tmax, a.pose32[p][12]);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-    const float4 q = __ldg(pts + i);
-    const float delta = (5.25f * F32_U) * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + tmax);
+  // points in pairs (2k, 2k + 1), as the hot loop classifies them when the packed classifier is compiled in
+  for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; 2 * k < a.n; k += stride) {
+    const long long i0 = 2 * k, i1 = min(2 * k + 1, static_cast<long long>(a.n) - 1);
+    const int n_here = 2 * k + 1 < a.n ? 2 : 1;
+    const float4 q2[2] = {__ldg(pts + i0), __ldg(pts + i1)};
+    float delta[2];
+    for (int h = 0; h < 2; h++) delta[h] = (5.25f * F32_U) * (fabsf(q2[h].x) + fabsf(q2[h].y) + fabsf(q2[h].z) + tmax);
     for (int p = 0; p < a.n_poses; p++) {
-      total++;
-      const LeanVerdict v = classify_lean<MODEL>(a.fast, lc, a.width, a.pose32[p], q.x, q.y, q.z, delta);
-      double ue = 0.0, ve = 0.0;
-      const int pe = exact_pixel_hd<MODEL>(a.cam, a.cos_fov, a.width, a.height, a.pose[p], q.x, q.y, q.z, &ue, &ve);
-      if (v.uncertain) {
-        uncertain++;
-      } else if (v.accept ? (v.idx != pe) : (pe != -1)) {
-        mismatch++;
-      } else if (v.accept) {
-        const float ru = static_cast<float>(fabs(static_cast<double>(v.up) - (ue - 0.5))) / (0.5f - v.hx);
-        const float rv = static_cast<float>(fabs(static_cast<double>(v.vp) - (ve - 0.5))) / (0.5f - v.hy);
-        max_ratio = fmaxf(max_ratio, fmaxf(ru, rv));
+      LeanVerdict v2[2];
+      if constexpr (PK_PACKED_FP32 && LeanPacked<MODEL>::value) {
+        const LeanVerdict2 w = classify_lean2<MODEL>(a.fast, lc, a.width, a.pose32[p], f2_pack(q2[0].x, q2[1].x), f2_pack(q2[0].y, q2[1].y),
+                                                     f2_pack(q2[0].z, q2[1].z), f2_pack(delta[0], delta[1]));
+        for (int h = 0; h < 2; h++) {
+          v2[h].accept = w.accept[h], v2[h].uncertain = w.uncertain[h], v2[h].idx = w.idx[h];
+          v2[h].up = w.up[h], v2[h].vp = w.vp[h], v2[h].hx = w.hx[h], v2[h].hy = w.hy[h];
+        }
+      } else {
+        for (int h = 0; h < 2; h++) v2[h] = classify_lean<MODEL>(a.fast, lc, a.width, a.pose32[p], q2[h].x, q2[h].y, q2[h].z, delta[h]);
+      }
+      for (int h = 0; h < n_here; h++) {
+        const LeanVerdict& v = v2[h];
+        const float4 q = q2[h];
+        total++;
+        double ue = 0.0, ve = 0.0;
+        const int pe = exact_pixel_hd<MODEL>(a.cam, a.cos_fov, a.width, a.height, a.pose[p], q.x, q.y, q.z, &ue, &ve);
+        if (v.uncertain) {
+          uncertain++;
+        } else if (v.accept ? (v.idx != pe) : (pe != -1)) {
+          mismatch++;
+        } else if (v.accept) {
+          const float ru = static_cast<float>(fabs(static_cast<double>(v.up) - (ue - 0.5))) / (0.5f - v.hx);
+          const float rv = static_cast<float>(fabs(static_cast<double>(v.vp) - (ve - 0.5))) / (0.5f - v.hy);
+          max_ratio = fmaxf(max_ratio, fmaxf(ru, rv));
+        }
       }
     }
   }
