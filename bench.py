@@ -331,6 +331,43 @@ def cpu_baseline(bag, points, intens, max_fov, label):
     }
 
 
+def bind_rank_to_cores(local_rank, world):
+    """One slice of the host's cores per rank, NUMA node by NUMA node (what `numactl` does for a launcher): the e2e path
+    converts and uploads 200 MB of host doubles per solve at C3, and with every rank's pages and conversion threads on
+    whichever node the scheduler picked, two ranks ran that at 2.7x the single-rank time (profiles/r02_bench_e_c3_n2.json).
+    Returns a description for the JSON line (None when nothing was changed)."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        allowed = set(os.sched_getaffinity(0))
+        ordered = []
+        import glob
+
+        def cpulist(text):
+            out = []
+            for part in text.strip().split(","):
+                if not part:
+                    continue
+                a, _, b = part.partition("-")
+                out.extend(range(int(a), int(b or a) + 1))
+            return out
+
+        nodes = sorted(glob.glob("/sys/devices/system/node/node[0-9]*"), key=lambda d: int(d.rsplit("node", 1)[1]))
+        for d in nodes:
+            with open(os.path.join(d, "cpulist")) as f:
+                ordered.extend(c for c in cpulist(f.read()) if c in allowed)
+        if len(ordered) != len(allowed):
+            ordered = sorted(allowed)
+        per = len(ordered) // world
+        if per < 2:
+            return None
+        mine = ordered[local_rank * per : (local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return {"cores_per_rank": per, "numa_nodes": len(nodes), "first_core": mine[0], "last_core": mine[-1]}
+    except OSError:
+        return None
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -339,6 +376,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    affinity = bind_rank_to_cores(local_rank, world)  # before any buffer is allocated or thread started
     if args.warmup < 3:
         args.warmup = 3
     cfg = CONFIGS[args.config]
@@ -594,7 +632,7 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak" if not grid_mode else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "dtype_note": "geometry decided in f64 semantics: fp32 filter with a rigorous error bound + exact f64 recheck (integer histograms identical to the all-f64 kernel); histogram int32; entropies f64",
         "config": config,
-        "run": {"culled_points": n_resident, "exchange": (args.exchange if world > 1 and not grid_mode else None), "kernel_variant": args.variant, "solver": args.solver, "solves_per_step": n_solves},
+        "run": {"culled_points": n_resident, "exchange": (args.exchange if world > 1 and not grid_mode else None), "kernel_variant": args.variant, "solver": args.solver, "solves_per_step": n_solves, "host_cores_of_rank0": affinity},
         "evals_per_step": evals_ref / args.steps, "evals_computed_per_step": evals_cmp / args.steps, "batches_per_step": batches / args.steps,
         "mpoints_per_s": mpoints, "wall_s_timed_region": wall,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_breakdown_ms_per_solve": host_break},

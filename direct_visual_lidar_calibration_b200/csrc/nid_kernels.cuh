@@ -214,24 +214,33 @@ constexpr int FIN_CH = 8;
 // branches of the library routine, so that the independent terms a lane evaluates interleave instead of serialising
 // (the library log cost 0.5 us per term in the launch's serial tail).  Algorithm of fdlibm's __ieee754_log (argument
 // reduction to [sqrt(1/2), sqrt(2)), s = f/(2+f), degree-14 even/odd polynomial split, hi/lo ln2), error < 1 ulp.
+// Every operation is an explicit round-to-nearest intrinsic: the value is a function of x alone, whatever code the call is
+// inlined into (the finalizers of the round-1 kernels and of the persistent kernel must produce the same bits -- the solver
+// trajectories are compared evaluation by evaluation -- and left to itself the compiler contracts a*b+c differently from one
+// inlining context to the next).
 __device__ __forceinline__ double log_pos_normal(double x) {
   const long long bits = __double_as_longlong(x);
   int k = static_cast<int>((bits >> 52) & 0x7ff) - 1023;
   double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);  // [1, 2)
   const bool hi = m > 1.4142135623730951;
-  m = hi ? m * 0.5 : m;
+  m = hi ? __dmul_rn(m, 0.5) : m;
   k += hi ? 1 : 0;
-  const double f = m - 1.0;
-  const double s = f / (2.0 + f);
-  const double z = s * s;
-  const double w = z * z;
-  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
-  const double R = t1 + t2;
-  const double hfsq = 0.5 * f * f;
+  const double f = __dadd_rn(m, -1.0);
+  const double s = __ddiv_rn(f, __dadd_rn(2.0, f));
+  const double z = __dmul_rn(s, s);
+  const double w = __dmul_rn(z, z);
+  const double t1 = __dmul_rn(w, __fma_rn(w, __fma_rn(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01));
+  const double t2 = __dmul_rn(z, __fma_rn(w, __fma_rn(w, __fma_rn(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01));
+  const double R = __dadd_rn(t1, t2);
+  const double hfsq = __dmul_rn(__dmul_rn(0.5, f), f);
   const double dk = static_cast<double>(k);
-  return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+  const double b = __fma_rn(s, __dadd_rn(hfsq, R), __dmul_rn(dk, 1.90821492927058770002e-10));
+  const double c = __dadd_rn(__dadd_rn(hfsq, -b), -f);
+  return __fma_rn(dk, 6.93147180369123816490e-01, -c);
 }
+
+// p * log(p + 1e-6) (cost_calculator_nid.cpp:59-61), rounded after the sum, the logarithm and the product
+__device__ __forceinline__ double entropy_term(double p) { return __dmul_rn(p, log_pos_normal(__dadd_rn(p, 1e-6))); }
 
 __device__ __forceinline__ double warp_tree_sum(double v) {
 #pragma unroll
@@ -409,11 +418,11 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
           const int k = k0 + m * span + sub * 32 + lane;
           if (k < a.nb) {
             const double pr = static_cast<double>(c[m]) / sum;
-            const double term = pr * log_pos_normal(pr + 1e-6);
+            const double term = entropy_term(pr);
             if (wpp > 1) {
               s_term[slot * a.nb + k] = term;
             } else {
-              t_rs += term;  // k ascends with (k0, m): already the canonical order
+              t_rs = __dadd_rn(t_rs, term);  // k ascends with (k0, m): already the canonical order
             }
             if (a.hist_out) a.hist_out[static_cast<size_t>(p) * a.nb + k] = c[m];
             g[k] = 0;
@@ -424,7 +433,7 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
     if (wpp > 1 && active) {  // marginal terms too are spread over the pose's warps (same arithmetic per term)
       for (int f = sub * 32 + lane; f < 2 * a.bins; f += span) {
         const double pm = static_cast<double>(f < a.bins ? h_image[f] : h_points[f - a.bins]) / sum;
-        s_mterm[slot * 2 * a.bins + f] = pm * log_pos_normal(pm + 1e-6);
+        s_mterm[slot * 2 * a.bins + f] = entropy_term(pm);
       }
     }
     if (wpp > 1) __syncthreads();
@@ -441,8 +450,8 @@ static __device__ void nid_finalize(const NidArgs& a, int n_poses, int* smem_i) 
         for (int k = lane; k < a.bins; k += 32) {
           const double pi = static_cast<double>(h_image[k]) / sum;
           const double pp = static_cast<double>(h_points[k]) / sum;
-          t_r += pi * log_pos_normal(pi + 1e-6);
-          t_s += pp * log_pos_normal(pp + 1e-6);
+          t_r = __dadd_rn(t_r, entropy_term(pi));
+          t_s = __dadd_rn(t_s, entropy_term(pp));
         }
       }
       const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);

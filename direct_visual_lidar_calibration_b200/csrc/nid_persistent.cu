@@ -172,7 +172,7 @@ struct PinBuf {
 
 // device scratch of one launch, one allocation, zeroed by one memset
 struct PkScratchLayout {
-  size_t ghist, arrive, fin_done, tile_next, abort_flag, seq, tma_stats, box, solve, total;
+  size_t ghist, gmarg, arrive, fin_done, tile_next, abort_flag, seq, tma_stats, box, solve, total;
   PkScratchLayout(int n_bags, int nb) {
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -181,6 +181,7 @@ struct PkScratchLayout {
       return at;
     };
     ghist = take(sizeof(int) * 3 * n_bags * PK_MAX_POSES * nb);  // three rotating buffers (Nelder-Mead mode), two used by the pose list
+    gmarg = take(sizeof(int) * 3 * n_bags * PK_MAX_POSES * PK_MARG_STRIDE);
     arrive = take(sizeof(unsigned int) * 3 * PK_MAX_BAGS);
     fin_done = take(sizeof(unsigned int) * 2);
     tile_next = take(sizeof(unsigned int) * 2 * PK_MAX_BAGS);
@@ -220,6 +221,7 @@ void pk_fill_common(PkArgs& a, vlcal_nid_ctx* const* ctxs, int n_ctxs, const PkG
     assigned += share;
   }
   a.ghist = reinterpret_cast<int*>(scratch + L.ghist);
+  a.gmarg = reinterpret_cast<int*>(scratch + L.gmarg);
   a.arrive = reinterpret_cast<unsigned int*>(scratch + L.arrive);
   a.fin_done = reinterpret_cast<unsigned int*>(scratch + L.fin_done);
   a.abort_flag = reinterpret_cast<unsigned int*>(scratch + L.abort_flag);

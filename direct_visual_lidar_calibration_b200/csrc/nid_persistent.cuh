@@ -47,7 +47,8 @@ constexpr int PK_MAX_POSES = 8;
 constexpr int PK_MAX_BAGS = 8;
 constexpr int PK_MAX_WORDS = 256;  // world x bags x 8 score words per batch, one polling thread each
 constexpr int PK_QUEUE = 64;
-constexpr int PK_MAX_BINS = 32;    // nb <= 1024: the finalizing block keeps its share of the joint histogram in registers
+constexpr int PK_MAX_BINS = 32;
+constexpr int PK_MARG_STRIDE = 2 * PK_MAX_BINS + 32;  // ints per (bag, pose) record of PkArgs::gmarg    // nb <= 1024: the finalizing block keeps its share of the joint histogram in registers
 constexpr int PK_STAMP_SLOTS = 8;
 constexpr unsigned int PK_TILE_ROWS = 4;
 // TMA variant (A/B, VLCAL_PK_TMA=1): the block's window of the image-bin plane staged in shared memory once per solve
@@ -59,6 +60,9 @@ struct alignas(64) PkTensorMap {         // a CUtensorMap (cuTensorMapEncodeTile
 };
 #ifndef PK_PACKED_FP32
 #define PK_PACKED_FP32 1  // classify two points per FFMA2 / FMUL2 / FADD2 (lean_filter2.cuh); 0: scalar classifier (A/B build)
+#endif
+#ifndef PK_DIAG_STAMPS
+#define PK_DIAG_STAMPS 0  // diagnostic build: stamp 3 moves behind the two-ahead zeroing, stamp 5 to the finalizer's inner barrier
 #endif
 #ifndef PK_MIN_BLOCKS
 #define PK_MIN_BLOCKS 1  // blocks per SM the register allocation must allow (768 threads x 85 registers fill the register file)
@@ -113,8 +117,9 @@ struct PkArgs {
   double* scores_out;        // pose-list mode: [n_total] (sum over bags of this launch)
   int* hist_out;             // optional [n_total][nb] (bag 0 only)
   // synchronisation scratch (zero on entry)
-  int* ghist;                // [2][n_bags][8][nb]
-  unsigned int* arrive;      // [2][PK_MAX_BAGS]
+  int* ghist;                // [3][n_bags][8][nb] joint accumulators (three rotating buffers in Nelder-Mead mode, two in pose-list mode)
+  int* gmarg;                // [3][n_bags][8][PK_MARG_STRIDE] Nelder-Mead mode: marginals (image bins, then lidar bins) and [2*PK_MAX_BINS] the inlier count
+  unsigned int* arrive;      // [3][PK_MAX_BAGS]
   unsigned int* fin_done;    // [2]
   unsigned int* abort_flag;  // set by any block that timed out: everybody leaves
   PkMailbox* box[P2P_MAX_RANKS];  // box[r]: rank r's mailbox as mapped here (self included; world == 1: local scratch)
@@ -138,6 +143,8 @@ struct PkShared {
   float4 pose32[PK_MAX_POSES][4];  // rows: [R00 R01 R02 t0] [R10 R11 R12 t1] [R20 R21 R22 t2] [max|t| 0 0 0]
   double ys[PK_MAX_POSES];
   double parts[PK_MAX_WORDS];
+  double fin_out[PK_WARPS];  // NIDs of the items one finalizer round covers (Nelder-Mead mode)
+  int bmarg[PK_MAX_POSES][2 * PK_MAX_BINS];  // Nelder-Mead mode: this block's marginals of the batch (zero between batches)
   float tmax;
   int n_poses;
   int wait_failed;
@@ -151,6 +158,7 @@ struct PkShared {
   int box_x0b, box_y0b, box_w, box_h;
   unsigned int q_idx[PK_WARPS][PK_QUEUE];
   unsigned char q_pose[PK_WARPS][PK_QUEUE];
+  int q_cnt[PK_WARPS];  // fill count of each warp's queue
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------------------
@@ -594,14 +602,14 @@ static __device__ __noinline__ double pk_block_nid(PkShared& sh, int* __restrict
     const int k = m * PK_THREADS + t;
     if (k < nb) {
       const double pr = static_cast<double>(c[m]) / sum;
-      s_term[k] = pr * log_pos_normal(pr + 1e-6);  // :59-61
+      s_term[k] = entropy_term(pr);  // :59-61
       if (hist_out) hist_out[k] = c[m];
       if (c[m]) g[k] = 0;
     }
   }
   for (int f = t; f < 2 * bins; f += PK_THREADS) {
     const double pm = static_cast<double>(s_marg[f]) / sum;
-    s_mterm[f] = pm * log_pos_normal(pm + 1e-6);
+    s_mterm[f] = entropy_term(pm);
   }
   __threadfence();  // the zeroed accumulator must be visible before anybody can see the score
   __syncthreads();
@@ -622,44 +630,65 @@ static __device__ __noinline__ double pk_block_nid(PkShared& sh, int* __restrict
   return s_nid;
 }
 
-// The same NID by ONE warp (Nelder-Mead mode: every block finalizes every (bag, pose) of the batch itself, one warp per
-// item, instead of waiting for an owner block to publish it).  Identical value: same terms, lane l adds terms l, l+32, ...
-// in ascending order, same xor tree.  Reads the accumulator only (the triple-buffered accumulators of this mode are zeroed
-// two batches ahead).  scr: nb + 2*bins ints of warp-private shared memory.
-static __device__ __noinline__ double pk_warp_nid(const int* __restrict__ g, int nb, int bins, int* __restrict__ scr, int lane) {
-  int* s_c = scr;
-  int* s_marg = scr + nb;  // image marginal, then lidar marginal
-  for (int i = lane; i < 2 * bins; i += 32) s_marg[i] = 0;
-  __syncwarp();
-  int part = 0;
-#pragma unroll 8
-  for (int k = lane; k < nb; k += 32) {
-    const int c = __ldcg(g + k);
-    s_c[k] = c;
-    if (c) {
-      atomicAdd(&s_marg[k % bins], c);         // hist_image[image_bin]   (:50)
-      atomicAdd(&s_marg[bins + k / bins], c);  // hist_points[lidar_bin]  (:51)
-      part += c;
+// Nelder-Mead mode: the NIDs of `count` (bag, pose) items at once, by the whole block -- every block finalizes every item of
+// the batch itself instead of waiting for an owner block to publish it.  The blocks merged the marginals and the inlier
+// count next to the joint histogram (gmarg), so all count * (nb + 2 bins) entropy terms are independent: one L2 round trip,
+// one division and one logarithm per thread, one barrier, then per item the canonical sum of pk_block_nid (lane l of one
+// warp adds terms l, l+32, ... in ascending order, then the xor tree) -- identical values.  Reads the accumulators only (this
+// mode's triple-buffered accumulators are zeroed two batches ahead).
+// Item j is (bag ib, pose ip) = ((first + j) / n_poses, (first + j) % n_poses).
+// scratch: count * pk_fin_item_bytes(nb, bins) bytes; out[j] <- NID of item j (written by lane 0 of warp j; count <= PK_WARPS).
+__host__ __device__ constexpr int pk_fin_item_bytes(int nb, int bins) { return 8 * (nb + 2 * bins); }
+
+static __device__ __noinline__ void pk_block_nid_items(const int* __restrict__ gbuf, const int* __restrict__ mbuf, int first, int count, int n_poses, int nb, int bins, void* scratch,
+                                                       double* out, unsigned long long* diag_stamp) {
+  double* s_term = static_cast<double*>(scratch);  // [count][nb + 2*bins]: joint terms, image-marginal terms, lidar-marginal terms
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int per_item = nb + 2 * bins;
+  const int n_terms = count * per_item;
+  // two terms per round and thread, loads first: the divisions and logarithms of a thread's terms interleave
+  for (int base = t; base < n_terms; base += 2 * PK_THREADS) {
+    int c[2];
+    double sum[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int idx = base + u * PK_THREADS;
+      c[u] = 0, sum[u] = 1.0;
+      if (idx < n_terms) {
+        const int j = idx / per_item, r = idx - j * per_item;
+        const int item = first + j, ib = item / n_poses, ip = item - ib * n_poses;
+        const size_t rec = static_cast<size_t>(ib) * PK_MAX_POSES + ip;
+        const int* m = mbuf + rec * PK_MARG_STRIDE;
+        c[u] = r < nb ? __ldcg(gbuf + rec * nb + r) : __ldcg(m + (r - nb));
+        sum[u] = static_cast<double>(__ldcg(m + 2 * PK_MAX_BINS));  // :54 sum = hist_image.sum()
+      }
+    }
+    double e[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) e[u] = entropy_term(static_cast<double>(c[u]) / sum[u]);  // :59-61
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int idx = base + u * PK_THREADS;
+      if (idx < n_terms) s_term[idx] = e[u];
     }
   }
-  part = __reduce_add_sync(0xffffffffu, part);
-  __syncwarp();
-  const double sum = static_cast<double>(part);  // :54
-  double t_rs = 0.0, t_r = 0.0, t_s = 0.0;
-#pragma unroll 4
-  for (int k = lane; k < nb; k += 32) {
-    const double pr = static_cast<double>(s_c[k]) / sum;
-    t_rs += pr * log_pos_normal(pr + 1e-6);  // :59-61
+  __syncthreads();
+  if (diag_stamp && t == 0) *diag_stamp = global_ns();
+  if (warp < count) {
+    const double* tj = s_term + static_cast<size_t>(warp) * per_item;
+    double t_rs = 0.0, t_r = 0.0, t_s = 0.0;
+    for (int k = lane; k < nb; k += 32) t_rs += tj[k];
+    for (int k = lane; k < bins; k += 32) {
+      t_r += tj[nb + k];
+      t_s += tj[nb + bins + k];
+    }
+    const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);
+    if (lane == 0) {
+      const double MI = Hr + Hs - Hrs;  // :63
+      out[warp] = (Hrs - MI) / Hrs;     // :64 (NaN when there are no inliers, as in the reference)
+    }
   }
-  for (int k = lane; k < bins; k += 32) {
-    const double pi = static_cast<double>(s_marg[k]) / sum;
-    const double pp = static_cast<double>(s_marg[bins + k]) / sum;
-    t_r += pi * log_pos_normal(pi + 1e-6);
-    t_s += pp * log_pos_normal(pp + 1e-6);
-  }
-  const double Hrs = -warp_tree_sum(t_rs), Hr = -warp_tree_sum(t_r), Hs = -warp_tree_sum(t_s);
-  const double MI = Hr + Hs - Hrs;  // :63
-  return (Hrs - MI) / Hrs;          // :64 (NaN when there are no inliers, as in the reference)
+  __syncthreads();
 }
 
 // thread b (< n_bags) spins until bag b's arrival counter reaches expected_per_block * (its block count); false for every
@@ -690,6 +719,24 @@ __device__ __forceinline__ bool pk_wait_arrivals(const PkArgs& a, const unsigned
 
 // ---- hot loop -----------------------------------------------------------------------------------------------------------
 
+__device__ __forceinline__ void sts_u32(unsigned int addr, unsigned int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(unsigned int addr, unsigned int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int lds_u32(unsigned int addr) {
+  unsigned int v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int lds_u8(unsigned int addr) {
+  unsigned int v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ int atoms_add(unsigned int addr, int v) {
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+
 struct PkWarp {
   unsigned int hist_addr;  // shared-memory byte address of this warp's histogram copy [P][nb]
   // TMA variant
@@ -697,8 +744,11 @@ struct PkWarp {
   int win_x0b, win_y0b;
   unsigned int win_w, win_h;
   unsigned int n_window, n_escaped;
-  unsigned int* q_idx;
-  unsigned char* q_pose;
+  // the warp's queue of deferred (point, pose) pairs, as shared-window byte addresses (generic pointers would turn the pushes into
+  // generic stores / generic atomics)
+  unsigned int q_idx;   // unsigned int [PK_QUEUE]
+  unsigned int q_pose;  // unsigned char [PK_QUEUE]
+  unsigned int q_cnt;   // int: shared-memory copy of qn (the lanes claim queue slots from it)
   int qn;
   int lane;
   unsigned int lt_mask;
@@ -713,8 +763,8 @@ struct PkBagRegs {
 template <int MODEL>
 __device__ __noinline__ void pk_drain32(const PkArgs& a, const PkShared& sh, const PkBagRegs& B, PkWarp& w, int first, int count) {
   if (w.lane < count) {  // one deferred (point, pose) per lane, exact path
-    const unsigned int i = w.q_idx[first + w.lane];
-    const int p = w.q_pose[first + w.lane];
+    const unsigned int i = lds_u32(w.q_idx + 4u * static_cast<unsigned int>(first + w.lane));
+    const int p = static_cast<int>(lds_u8(w.q_pose + static_cast<unsigned int>(first + w.lane)));
     const float4 q = __ldg(B.points + i);
     const int pix = exact_pixel_hd<MODEL>(a.cam, a.cos_fov, a.width, a.height, sh.pose64[p], q.x, q.y, q.z);
     if (pix >= 0) {
@@ -824,30 +874,30 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
   const int cnt = __popc(unc_mask);
   const int total = __reduce_add_sync(0xffffffffu, cnt);
   if (total > 0 && total <= 32) {
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (w.lane >= o) incl += up;
-    }
     if (w.qn + total > PK_QUEUE) {  // make room first (qn > 32 here): the last 32 queued pairs go to the exact path now
       pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
       w.qn -= 32;
+      if (w.lane == 0) sts_u32(w.q_cnt, static_cast<unsigned int>(w.qn));
       __syncwarp();
     }
-    int pos = w.qn + incl - cnt;
-    while (unc_mask != 0u) {
-      const int b = __ffs(static_cast<int>(unc_mask)) - 1;  // bit p * K + j
-      unc_mask &= unc_mask - 1u;
-      w.q_idx[pos] = tile + static_cast<unsigned int>(b % K) * 32u + static_cast<unsigned int>(w.lane);
-      w.q_pose[pos] = static_cast<unsigned char>(b / K);
-      pos++;
+    if (unc_mask != 0u) {
+      // the queue slots of this lane's pairs: one shared-memory atomic on the warp's fill count (the order of the queue does
+      // not matter -- histogram increments commute -- so no prefix sum over the lanes is needed)
+      int pos = atoms_add(w.q_cnt, cnt);
+      do {
+        const int b = __ffs(static_cast<int>(unc_mask)) - 1;  // bit p * K + j
+        unc_mask &= unc_mask - 1u;
+        sts_u32(w.q_idx + 4u * static_cast<unsigned int>(pos), tile + static_cast<unsigned int>(b % K) * 32u + static_cast<unsigned int>(w.lane));
+        sts_u8(w.q_pose + static_cast<unsigned int>(pos), static_cast<unsigned int>(b / K));
+        pos++;
+      } while (unc_mask != 0u);
     }
     w.qn += total;
     __syncwarp();
     if (w.qn >= 32) {
       pk_drain32<MODEL>(a, sh, B, w, w.qn - 32, 32);
       w.qn -= 32;
+      if (w.lane == 0) sts_u32(w.q_cnt, static_cast<unsigned int>(w.qn));
       __syncwarp();
     }
   } else if (total > 32) {
@@ -858,8 +908,8 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
       const unsigned int m = __ballot_sync(0xffffffffu, have);
       if (have) {
         const int pos = w.qn + __popc(m & w.lt_mask);
-        w.q_idx[pos] = tile + static_cast<unsigned int>(b % K) * 32u + static_cast<unsigned int>(w.lane);
-        w.q_pose[pos] = static_cast<unsigned char>(b / K);
+        sts_u32(w.q_idx + 4u * static_cast<unsigned int>(pos), tile + static_cast<unsigned int>(b % K) * 32u + static_cast<unsigned int>(w.lane));
+        sts_u8(w.q_pose + static_cast<unsigned int>(pos), static_cast<unsigned int>(b / K));
       }
       w.qn += __popc(m);
       __syncwarp();
@@ -869,6 +919,8 @@ __device__ __forceinline__ void pk_tile(const PkArgs& a, const PkShared& sh, con
         __syncwarp();
       }
     }
+    if (w.lane == 0) sts_u32(w.q_cnt, static_cast<unsigned int>(w.qn));
+    __syncwarp();
   }
 }
 
@@ -951,8 +1003,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
   PkWarp w;
   w.lane = lane;
   w.lt_mask = (1u << lane) - 1u;
-  w.q_idx = sh.q_idx[warp];
-  w.q_pose = sh.q_pose[warp];
+  w.q_idx = static_cast<unsigned int>(__cvta_generic_to_shared(sh.q_idx[warp]));
+  w.q_pose = static_cast<unsigned int>(__cvta_generic_to_shared(sh.q_pose[warp]));
+  w.q_cnt = static_cast<unsigned int>(__cvta_generic_to_shared(&sh.q_cnt[warp]));
+  if (lane == 0) sh.q_cnt[warp] = 0;
   w.qn = 0;
   const unsigned int smem_base = static_cast<unsigned int>(__cvta_generic_to_shared(smem_hist));
   const int n_items_per_batch = a.n_bags * (solve_mode ? PK_MAX_POSES : a.chunk);  // finalizer items of a full pose-list chunk
@@ -973,6 +1027,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     if (t < pc) pk_pose_from_list(sh, t, a.poses_in + 12 * static_cast<size_t>(t));
     if (t == 0) sh.n_poses = pc;
   }
+  for (int i = t; i < PK_MAX_POSES * 2 * PK_MAX_BINS; i += PK_THREADS) (&sh.bmarg[0][0])[i] = 0;
   if (t == 0) {
     sh.seq_base = *a.seq_counter;
     sh.trace_count = 0;
@@ -1120,6 +1175,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     if (w.qn > 0) {
       pk_drain32<MODEL>(a, sh, B, w, 0, w.qn);
       w.qn = 0;
+      if (lane == 0) sts_u32(w.q_cnt, 0u);
     }
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 1);
     __syncthreads();
@@ -1130,7 +1186,28 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       for (int k = t; k < per_copy; k += PK_THREADS) {
         int s = 0;
         for (int c = 0; c < a.copies; c++) s += smem_hist[c * per_copy + k];
-        if (s) atomicAdd(g + k, s);
+        if (s) {
+          atomicAdd(g + k, s);
+          if (solve_mode) {  // the block's marginals (cost_calculator_nid.cpp:50-51), merged below
+            const int p = k / a.nb, kk = k - p * a.nb;
+            atomicAdd(&sh.bmarg[p][kk % a.bins], s);
+            atomicAdd(&sh.bmarg[p][a.bins + kk / a.bins], s);
+          }
+        }
+      }
+      if (solve_mode) {
+        __syncthreads();
+        int* gm = a.gmarg + (static_cast<size_t>(buf) * a.n_bags + bag) * PK_MAX_POSES * PK_MARG_STRIDE;
+        for (int i = t; i < n_poses * 2 * a.bins; i += PK_THREADS) {
+          const int p = i / (2 * a.bins), f = i - p * 2 * a.bins;
+          const int v = sh.bmarg[p][f];
+          if (v) atomicAdd(gm + p * PK_MARG_STRIDE + f, v);
+        }
+        if (warp >= PK_WARPS - n_poses) {  // inlier count of pose p (:54): one of the last warps each (the first ones carry the marginals)
+          const int p = PK_WARPS - 1 - warp;
+          const int tot = __reduce_add_sync(0xffffffffu, lane < a.bins ? sh.bmarg[p][lane] : 0);  // bins <= 32
+          if (lane == 0 && tot) atomicAdd(gm + p * PK_MARG_STRIDE + 2 * PK_MAX_BINS, tot);
+        }
       }
     }
     // every thread's reductions are ordered before the barrier, the barrier before thread 0's fence, the fence before the
@@ -1184,29 +1261,44 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
     // batch - 1 (finished by every block before it arrived here) and is next merged in batch + 2, which no block reaches
     // before every block arrived for batch + 1, i.e. after this block's zeroing (ordered by the arrival fence).
     if (!pk_wait_arrivals(a, a.arrive + buf * PK_MAX_BAGS, static_cast<unsigned int>(batch / 3ull + 1ull))) return;
-    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 3);
+    if (!PK_DIAG_STAMPS && blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 3);
     {
       const int nz = a.n_bags * PK_MAX_POSES * a.nb;
       int* z = a.ghist + static_cast<size_t>((buf + 2) % 3) * nz;
       for (int i = static_cast<int>(blockIdx.x) * PK_THREADS + t; i < nz; i += static_cast<int>(gridDim.x) * PK_THREADS) z[i] = 0;
+      const int nm = a.n_bags * PK_MAX_POSES * PK_MARG_STRIDE;
+      int* zm = a.gmarg + static_cast<size_t>((buf + 2) % 3) * nm;
+      // (from the last block down: the first blocks carry most of the joint accumulators)
+      for (int i = static_cast<int>(gridDim.x - 1u - blockIdx.x) * PK_THREADS + t; i < nm; i += static_cast<int>(gridDim.x) * PK_THREADS) zm[i] = 0;
     }
     {
       const int n_items = a.n_bags * n_poses;
-      const int per_w = a.nb + 2 * a.bins;
-      const int fw = min(PK_WARPS, (a.copies * PK_MAX_POSES * a.nb) / per_w);  // >= 7: the histogram copies are dead after the merge
-      if (warp < fw) {
-        for (int item = warp; item < n_items; item += fw) {
-          const int ib = item / n_poses, ip = item % n_poses;
-          const int* g = a.ghist + ((static_cast<size_t>(buf) * a.n_bags + ib) * PK_MAX_POSES + ip) * a.nb;
-          const double nid = pk_warp_nid(g, a.nb, a.bins, smem_hist + warp * per_w, lane);
+      const int* gbuf = a.ghist + static_cast<size_t>(buf) * a.n_bags * PK_MAX_POSES * a.nb;
+      const int* mbuf = a.gmarg + static_cast<size_t>(buf) * a.n_bags * PK_MAX_POSES * PK_MARG_STRIDE;
+      // items per round: what the dead histogram copies hold of staged terms, at most one item per warp
+      const int round_items = min(PK_WARPS, (a.copies * PK_MAX_POSES * a.nb * 4) / pk_fin_item_bytes(a.nb, a.bins));
+      for (int first = 0; first < n_items; first += round_items) {
+        const int count = min(round_items, n_items - first);
+        unsigned long long* diag = nullptr;
+        if (PK_DIAG_STAMPS && blockIdx.x == 0 && first == 0 && a.stamps && batch < static_cast<unsigned long long>(a.stamps_cap)) {
+          diag = a.stamps + batch * PK_STAMP_SLOTS + 5;
+          if (t == 0) pk_stamp(a, batch, 3);
+        }
+        pk_block_nid_items(gbuf, mbuf, first, count, n_poses, a.nb, a.bins, smem_hist, sh.fin_out, diag);
+        if (t < count) {
+          const int item = first + t, ib = item / n_poses, ip = item - ib * n_poses;
           const int word = (a.rank * a.n_bags + ib) * PK_MAX_POSES + ip;
-          if (lane == 0) sh.parts[word] = nid;
+          const double nid = sh.fin_out[t];
+          sh.parts[word] = nid;
           // the other ranks get it from one block (NVLink peer stores, tagged words)
-          if (a.world > 1 && static_cast<unsigned int>(item) % gridDim.x == blockIdx.x && lane < a.world && lane != a.rank) {
+          if (a.world > 1 && static_cast<unsigned int>(item) % gridDim.x == blockIdx.x) {
             const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(nid));
-            volatile unsigned long long* dst = a.box[lane]->w[slot][word];
-            dst[0] = tag | (bits & 0xffffffffull);
-            dst[1] = tag | (bits >> 32);
+            for (int r = 0; r < a.world; r++) {
+              if (r == a.rank) continue;
+              volatile unsigned long long* dst = a.box[r]->w[slot][word];
+              dst[0] = tag | (bits & 0xffffffffull);
+              dst[1] = tag | (bits >> 32);
+            }
           }
         }
       }
@@ -1240,7 +1332,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       sh.parts[src * PK_MAX_POSES + p] = __longlong_as_double(static_cast<long long>((wh << 32) | (wl & 0xffffffffull)));
     }
     if (__syncthreads_or(timed_out ? 1 : 0)) return;
-    if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 5);
+    if (!PK_DIAG_STAMPS && blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 5);
     if (t < n_poses) {
       double total = 0.0;
       for (int s = 0; s < a.world * a.n_bags; s++) total += sh.parts[s * PK_MAX_POSES + t];  // (rank, bag) order: identical everywhere
@@ -1276,6 +1368,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       // meanwhile the other warps clear the histogram copies for the next batch (all PK_MAX_POSES slots: its pose count is
       // being decided by warp 0); the warp-private finalizer scratch in the same array is dead since the barrier above
       for (int i = t - 32; i < a.copies * PK_MAX_POSES * a.nb; i += PK_THREADS - 32) smem_hist[i] = 0;
+      for (int i = t - 32; i < PK_MAX_POSES * 2 * PK_MAX_BINS; i += PK_THREADS - 32) (&sh.bmarg[0][0])[i] = 0;
     }
     __syncthreads();
     if (blockIdx.x == 0 && t == 0) pk_stamp(a, batch, 6);
