@@ -332,15 +332,14 @@ def cpu_baseline(bag, points, intens, max_fov, label):
 
 
 def bind_rank_to_cores(local_rank, world):
-    """One slice of the host's cores per rank, NUMA node by NUMA node (what `numactl` does for a launcher): the e2e path
-    converts and uploads 200 MB of host doubles per solve at C3, and with every rank's pages and conversion threads on
-    whichever node the scheduler picked, two ranks ran that at 2.7x the single-rank time (profiles/r02_bench_e_c3_n2.json).
+    """One slice of the host's cores per rank, NUMA node by NUMA node, whole physical cores (what `numactl` does for a
+    launcher): the e2e path converts and uploads 200 MB of host doubles per solve at C3, and with every rank's pages and
+    conversion threads on whichever node the scheduler picked, two ranks ran that at 2.7x the single-rank time
+    (profiles/r02_bench_e_c3_n2.json; 1.2x with the binding, r02_bench_k_c3_n2.json).
     Returns a description for the JSON line (None when nothing was changed)."""
     if world <= 1 or not hasattr(os, "sched_setaffinity"):
         return None
     try:
-        allowed = set(os.sched_getaffinity(0))
-        ordered = []
         import glob
 
         def cpulist(text):
@@ -352,18 +351,35 @@ def bind_rank_to_cores(local_rank, world):
                 out.extend(range(int(a), int(b or a) + 1))
             return out
 
+        allowed = set(os.sched_getaffinity(0))
         nodes = sorted(glob.glob("/sys/devices/system/node/node[0-9]*"), key=lambda d: int(d.rsplit("node", 1)[1]))
+        ordered = []
         for d in nodes:
             with open(os.path.join(d, "cpulist")) as f:
                 ordered.extend(c for c in cpulist(f.read()) if c in allowed)
         if len(ordered) != len(allowed):
             ordered = sorted(allowed)
-        per = len(ordered) // world
-        if per < 2:
+        # physical cores in that order, each with its hardware threads
+        cores, seen = [], set()
+        for c in ordered:
+            if c in seen:
+                continue
+            try:
+                with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                    sib = [x for x in cpulist(f.read()) if x in allowed]
+            except OSError:
+                sib = [c]
+            sib = sib or [c]
+            cores.append(sib)
+            seen.update(sib)
+        per = len(cores) // world
+        if per < 1:
             return None
-        mine = ordered[local_rank * per : (local_rank + 1) * per]
+        mine = sorted(x for core in cores[local_rank * per : (local_rank + 1) * per] for x in core)
+        if len(mine) < 2:
+            return None
         os.sched_setaffinity(0, mine)
-        return {"cores_per_rank": per, "numa_nodes": len(nodes), "first_core": mine[0], "last_core": mine[-1]}
+        return {"physical_cores_per_rank": per, "threads_per_rank": len(mine), "numa_nodes": len(nodes), "first_cpu": mine[0], "last_cpu": mine[-1]}
     except OSError:
         return None
 

@@ -198,11 +198,14 @@ int vlcal_nid_filter_enabled(const vlcal_nid_ctx* ctx);
 int vlcal_nid_debug_filter_check(vlcal_nid_ctx* ctx, const double* T_camera_lidar, int n_poses, uint64_t counts[3], double* max_bound_ratio);
 
 /* ---- multi-GPU: fused bag all-reduce over NVLink peer memory ---------------------------------------------------------
- * One process per GPU, ONE bag (cost object) per process.  The joint objective is sum_bags NID
- * (visual_camera_calibration.cpp:105-110): with an exchange attached, the finalizing block of every evaluation stores its
- * scores into every peer's mailbox (P2P stores, cudaIpc-shared buffers), waits for the peers' and adds the contributions
- * in rank order, so vlcal_nid_evaluate / _wait return the SUM OVER RANKS, identical bits on every rank, without a
- * separate collective.  All ranks must evaluate the same number of poses in the same order (Nelder-Mead does).
+ * One process per GPU, the same number of bags (cost objects) per process.  The joint objective is sum_bags NID
+ * (visual_camera_calibration.cpp:105-110).  With an exchange attached, an inner solve (vlcal_estimate_pose_* on the
+ * attached contexts) is one persistent launch per rank: per Nelder-Mead batch one block per (bag, pose) stores the score into
+ * every other rank's mailbox (P2P stores, cudaIpc-shared buffers, tagged words) and every block of every rank adds the
+ * contributions in (rank, bag) order -- identical bits on every rank, no separate collective, no host in the loop.
+ * vlcal_nid_evaluate / _wait on an attached context (one bag per process) run the round-1 kernels, whose finalizing block
+ * performs the same exchange and returns the SUM OVER RANKS.  All ranks must evaluate the same number of poses in the same
+ * order (Nelder-Mead does).
  *   1. every rank: vlcal_nid_p2p_create(device, rank, world, &px, handle)   (handle: 64 bytes out)
  *   2. exchange the 64-byte handles between the ranks (e.g. torch.distributed.all_gather), concatenate in rank order
  *   3. every rank: vlcal_nid_p2p_connect(px, all_handles);   4. vlcal_nid_p2p_attach(ctx, px) on each new context */

@@ -69,6 +69,8 @@ def run_case(name, kind, bags_per_rank, px):
     ok = same_ranks
     if rank == 0:
         allc = [cost_of(b) for b in range(n_bags)]
+        if n_bags > 8:
+            V.set_solver_mode(0)  # one launch holds at most 8 bags: the library picks the host loop for this reference solve
         T1, r1 = VC.estimate_pose_on_costs(allc, T0, params)  # all bags in one launch, no exchange
         V.set_solver_mode(1)
         Th, rh = VC.estimate_pose_on_costs(allc, T0, params)  # round-1 host loop: one launch per bag and batch
