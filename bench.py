@@ -56,7 +56,7 @@ CONFIGS = {
 SIGNS = [(1, 1, 1, 1, 1, 1), (-1, 1, 1, 1, -1, 1), (1, -1, 1, -1, 1, 1), (1, 1, -1, 1, 1, -1), (-1, -1, 1, -1, -1, 1), (1, -1, -1, -1, 1, -1), (-1, 1, -1, 1, -1, -1), (-1, -1, -1, -1, -1, -1)]
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -70,7 +70,7 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: in-kernel peer-memory exchange (default) or host loop + NCCL all-reduce per batch")
     ap.add_argument("--ref-iterations", type=int, default=-1, help="NM iterations per reference-arm step (bounded sample); -1 = per-config default")
     ap.add_argument("--grid-poses", type=int, default=16384, help="C5: poses of the grid (16384 = the BASELINE figure)")
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 def start_poses(cfg, T_gt, count):

@@ -303,6 +303,32 @@ def test_persistent_solve_two_bags_one_launch(gpu, oracle):
     assert np.array_equal(rp["x"], ref["x"]) and rp["num_evaluations"] == ref["num_evaluations"] and np.abs(Tp - ref["T"]).max() == 0.0
 
 
+@pytest.mark.parametrize("bins,n_bags", [(8, 1), (10, 2), (32, 2), (16, 4)])
+def test_persistent_solve_other_bin_counts_and_finalizer_rounds(gpu, bins, n_bags):
+    """The every-block finalizer stages bins^2 + 2 bins entropy terms per (bag, pose) in the dead histogram copies and works
+    through the items in rounds of what fits (7 items at 32 bins, 21 at 16): bin counts that are not 16, not a power of two,
+    and bag counts that need several rounds must walk the host loop's trajectory, bit for bit."""
+    V = gpu
+    bags = [_synthetic_bag(20000 + 3000 * k, cfg=4 + (k % 3)) for k in range(n_bags)]
+    cam = V.create_camera(bags[0]["camera_model"], bags[0]["intrinsics"], bags[0]["distortion"])
+    ds = [V.VisualLiDARData(b["image"], b["points"], b["intensities"]) for b in bags]
+    params = V.VisualCameraCalibrationParams()
+    params.max_inner_iterations = 30
+    params.nid_bins = bins
+    out = {}
+    try:
+        for mode in (1, 3):
+            V.set_solver_mode(mode)
+            calib = V.VisualCameraCalibration(cam, ds, params)
+            T, r = calib.estimate_pose_nelder_mead(bags[0]["T_init"])
+            out[mode] = (T, r, [c for _, c in calib.trace])
+    finally:
+        V.set_solver_mode(0)
+    (Th, rh, trh), (Tp, rp, trp) = out[1], out[3]
+    assert np.array_equal(Th, Tp) and np.array_equal(rh["x"], rp["x"]) and rh["y"] == rp["y"] and trh == trp
+    assert rh["num_evaluations"] == rp["num_evaluations"] and rh["num_batches"] == rp["num_batches"]
+
+
 def test_score_poses_equals_calculate(gpu, oracle):
     """vlcal_nid_score_poses (one persistent launch for a pose list of any length, several bags) == calculate() per pose."""
     V = gpu
