@@ -331,6 +331,23 @@ def cpu_baseline(bag, points, intens, max_fov, label):
     }
 
 
+def rank_cpus(ordered, siblings_of, local_rank, world):
+    """CPUs of one rank: the allowed CPUs in NUMA order are grouped into physical cores (a core = its hardware threads),
+    the cores are dealt out in equal contiguous runs.  Returns (sorted CPU list, physical cores per rank)."""
+    allowed = set(ordered)
+    cores, seen = [], set()
+    for c in ordered:
+        if c in seen:
+            continue
+        sib = [x for x in siblings_of(c) if x in allowed] or [c]
+        cores.append(sib)
+        seen.update(sib)
+    per = len(cores) // world
+    if per < 1:
+        return [], 0
+    return sorted(x for core in cores[local_rank * per : (local_rank + 1) * per] for x in core), per
+
+
 def bind_rank_to_cores(local_rank, world):
     """One slice of the host's cores per rank, NUMA node by NUMA node, whole physical cores (what `numactl` does for a
     launcher): the e2e path converts and uploads 200 MB of host doubles per solve at C3, and with every rank's pages and
@@ -359,28 +376,21 @@ def bind_rank_to_cores(local_rank, world):
                 ordered.extend(c for c in cpulist(f.read()) if c in allowed)
         if len(ordered) != len(allowed):
             ordered = sorted(allowed)
-        # physical cores in that order, each with its hardware threads
-        cores, seen = [], set()
-        for c in ordered:
-            if c in seen:
-                continue
+
+        def siblings_of(c):
             try:
                 with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
-                    sib = [x for x in cpulist(f.read()) if x in allowed]
+                    return cpulist(f.read())
             except OSError:
-                sib = [c]
-            sib = sib or [c]
-            cores.append(sib)
-            seen.update(sib)
-        per = len(cores) // world
-        if per < 1:
-            return None
-        mine = sorted(x for core in cores[local_rank * per : (local_rank + 1) * per] for x in core)
+                return [c]
+
+        mine, per = rank_cpus(ordered, siblings_of, local_rank, world)
         if len(mine) < 2:
             return None
         os.sched_setaffinity(0, mine)
         return {"physical_cores_per_rank": per, "threads_per_rank": len(mine), "numa_nodes": len(nodes), "first_cpu": mine[0], "last_cpu": mine[-1]}
-    except OSError:
+    except Exception as e:  # binding is an optimisation: never fail the run over it
+        print(f"[bench] core binding skipped: {e}", file=sys.stderr)
         return None
 
 

@@ -50,3 +50,25 @@ def test_both_arms_describe_the_same_config():
             a = bench.config_dict(args, world, 1000, 640, 480)
             b = bench.config_dict(ref, world, 1000, 640, 480)
             assert a == b and a["workload"].startswith(cfg)
+
+
+def test_rank_cpus_on_a_two_socket_hyperthreaded_topology():
+    """128 CPUs as Linux numbers them on a 2 x 32-core host with SMT: node 0 = 0-31,64-95, node 1 = 32-63,96-127, CPU c and
+    c +/- 64 share a core.  Eight ranks: whole cores, 8 each, ranks 0-3 on node 0, 4-7 on node 1, nothing shared."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    ordered = list(range(0, 32)) + list(range(64, 96)) + list(range(32, 64)) + list(range(96, 128))
+    sib = lambda c: sorted({c % 64, c % 64 + 64})
+    seen = set()
+    for r in range(8):
+        cpus, per = bench.rank_cpus(ordered, sib, r, 8)
+        assert per == 8 and len(cpus) == 16 and not (seen & set(cpus))
+        seen |= set(cpus)
+        node = 0 if r < 4 else 1
+        assert all((c % 64 < 32) == (node == 0) for c in cpus)
+        assert all((c + 64) % 128 in cpus for c in cpus)  # both hardware threads of every core
+    assert seen == set(range(128))
+    assert bench.rank_cpus(ordered, sib, 0, 2)[0] == sorted(list(range(0, 32)) + list(range(64, 96)))
+    # more ranks than cores: no binding
+    assert bench.rank_cpus([0, 1], lambda c: [0, 1], 0, 2) == ([], 0)
