@@ -5,20 +5,25 @@
 // src/vlcal/calib/visual_camera_calibration.cpp:103-119), the round-1 scheme "one launch per Nelder-Mead batch + host
 // round trip" (36 us kernel of which ~16 us were launch ramp / serial tail, + ~5 us host gap, x 115 batches at C2).
 //
-// One launch, grid = every co-resident block of the GPU (cooperative launch, so the waits below cannot deadlock), each
-// warp owning a fixed contiguous slice of the cloud for the whole solve.  Per Nelder-Mead batch:
-//   (A) every block scores the batch's P <= 8 candidate poses on its slice -- lean fp32 filter (lean_filter.cuh) with the
-//       exact fp64 recheck for the ~3 % of point-poses near a decision edge (exact_classify.cuh), privatised shared-memory
-//       histograms, predicated red.shared -- and merges its non-zero bins into the global accumulators (red.global);
-//   (B) one block per (bag, pose) waits for the bag's blocks (arrival counter), reduces the accumulator to the NID score
-//       (:54-64; same canonical summation order as nid_finalize, so scores are a function of the histogram alone) and
-//       stores it, as two tagged 8-byte words, into the mailbox of EVERY rank (NVLink peer stores when world > 1);
-//   (C) every block of every rank waits for the world x bags x P words, adds them in (rank, bag) order -- the joint
-//       objective sum_bags NID (:105-110), bit-identical everywhere -- and then steps the Nelder-Mead state machine
-//       REDUNDANTLY in its own shared memory (warp-parallel over the simplex coordinates, nm_warp_step below; same
-//       operations in the same order as NmMachine::step) and computes the next candidates' poses T = init_T * Expmap(x)
-//       (:104), one lane per candidate.  No broadcast of poses, no host, no launch.
-// The same kernel in pose-list mode (no step (C): the next 8 poses come from a device array) serves batched evaluation
+// One launch, grid = one 768-thread block per SM, all co-resident (cooperative launch, so the waits below cannot deadlock);
+// tile k (64 consecutive points of the tile-ordered cloud) belongs to warp k mod W of its bag for the whole solve.
+// Per Nelder-Mead batch:
+//   (A) every block scores the batch's P <= 8 candidate poses on its tiles -- lean fp32 filter, two points per packed
+//       FFMA2 / FMUL2 / FADD2 (lean_filter.cuh, lean_filter2.cuh), with the exact fp64 recheck for the ~2-3 % of point-poses
+//       near a decision edge (exact_classify.cuh), privatised shared-memory histograms -- and merges its non-zero bins,
+//       its marginals and its inlier counts into the global accumulators (red.global), then arrives (one fence per block);
+//   (B) EVERY block waits for the arrivals and reduces every (bag, pose) accumulator to its NID score itself (:54-64; all
+//       entropy terms in parallel, then per item the canonical summation order of nid_finalize, so a score is a function of
+//       the histogram alone); the accumulators rotate over three buffers that are zeroed two batches ahead;
+//   (C) world > 1: one block per item stores the score, as two tagged 8-byte words, into the mailboxes of the other ranks
+//       (NVLink peer stores) and every block polls its own rank's mailbox for the remote words; then all blocks add the
+//       world x bags contributions per pose in (rank, bag) order -- the joint objective sum_bags NID (:105-110),
+//       bit-identical everywhere -- and warp 0 steps the Nelder-Mead state machine REDUNDANTLY in the block's shared memory
+//       (warp-parallel over the simplex coordinates, nm_warp_step below; same operations in the same order as
+//       NmMachine::step) and computes the next candidates' poses T = init_T * Expmap(x) (:104), three lanes per candidate,
+//       while the other warps clear the histogram copies.  No broadcast of poses, no host, no launch.
+// The same kernel in pose-list mode (no step (C): the next 8 poses come from a device array, and an owner block per
+// (bag, pose) finalizes behind the scoring blocks, which run up to two chunks ahead) serves batched evaluation
 // (vlcal_nid_evaluate) and the pose-grid search (vlcal_nid_score_poses): one launch for any number of poses.
 //
 // Several bags per GPU: the grid is partitioned over the bags in proportion to their sizes (one tail for all bags).
@@ -47,8 +52,8 @@ constexpr int PK_MAX_POSES = 8;
 constexpr int PK_MAX_BAGS = 8;
 constexpr int PK_MAX_WORDS = 256;  // world x bags x 8 score words per batch, one polling thread each
 constexpr int PK_QUEUE = 64;
-constexpr int PK_MAX_BINS = 32;
-constexpr int PK_MARG_STRIDE = 2 * PK_MAX_BINS + 32;  // ints per (bag, pose) record of PkArgs::gmarg    // nb <= 1024: the finalizing block keeps its share of the joint histogram in registers
+constexpr int PK_MAX_BINS = 32;  // nb <= 1024
+constexpr int PK_MARG_STRIDE = 2 * PK_MAX_BINS + 32;  // ints per (bag, pose) record of PkArgs::gmarg
 constexpr int PK_STAMP_SLOTS = 8;
 constexpr unsigned int PK_TILE_ROWS = 4;
 // TMA variant (A/B, VLCAL_PK_TMA=1): the block's window of the image-bin plane staged in shared memory once per solve
