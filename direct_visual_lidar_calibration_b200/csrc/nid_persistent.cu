@@ -138,8 +138,8 @@ static unsigned long long pk_timeout_ns() {
 }
 
 // Points per lane and tile (K).  Tiles are dealt to the warps round-robin, so K = 4 (128-point tiles) needs a cloud large
-// enough for several tiles per warp to stay balanced -- and there the lighter register footprint of K = 2 (3 blocks per SM
-// without spills in the hot loop) measured faster anyway.  K = 4 remains as variant 3 / VLCAL_PK_KPT=4 for A/B runs.
+// enough for several tiles per warp to stay balanced -- and there the lighter register footprint of K = 2 (768 threads per
+// SM without spills in the pose loop, one packed register pair per coordinate) measured faster anyway.  K = 4 remains as variant 3 / VLCAL_PK_KPT=4 for A/B runs.
 static int pk_points_per_lane(const vlcal_nid_ctx* ctx, long long /*total_points*/) {
   if (const char* e = std::getenv("VLCAL_PK_KPT")) return std::atoi(e) == 4 ? 4 : 2;
   return ctx->variant == 3 ? 4 : 2;

@@ -39,8 +39,8 @@
 
 namespace vlcal {
 
-// Launch shape: ONE block of 768 threads per SM (24 warps, <= 85 registers).  Three blocks of 256 threads (the A/B build,
-// `make alt`) hold the same 24 warps, but the warp scheduler prefers higher warp slots, so the three blocks of an SM finished
+// Launch shape: ONE block of 768 threads per SM (24 warps, <= 85 registers).  Three blocks of 256 threads (A/B build,
+// `make alt ALTFLAGS="-DPK_THREADS_CFG=256 -DPK_MIN_BLOCKS=3"`) hold the same 24 warps, but the warp scheduler prefers higher warp slots, so the three blocks of an SM finished
 // their slices at 11 / 14 / 18 us (C2) and every Nelder-Mead batch waited for the 18; one block finishes at 15-16.5 us,
 // merges once instead of three times and arrives once (measured: 28.3 vs 30.8 us per C2 batch, 128 vs 138 us at C3).
 #ifndef PK_THREADS_CFG
@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS) nid_persistent_kern
       if (has_work) pk_range<MODEL, K, ATOM, TMA>(a, sh, B, n_poses, w, begin, end, qk, preloaded);
     } else {
       // Interleaved split: tile k (32 * K consecutive points of the tile-ordered cloud) goes to warp k mod W of the bag, so
-      // every warp -- and every block: its 8 warps take 8 neighbouring tiles per round -- samples the whole image instead of
+      // every warp -- and every block: its 24 warps take 24 neighbouring tiles per round -- samples the whole image instead of
       // owning one region.  With contiguous slices the cost of a slice followed its region (deferred rechecks, histogram bin
       // collisions, cache hit rates): the slowest block finished 35 % (C2) / 14 % (C3) after the median one, and every
       // Nelder-Mead batch waits for the slowest.  (Claiming tiles from an atomic counter was measured too: no better than
